@@ -1,0 +1,675 @@
+// bgx_api.cu — sections 2..6 of include/bgx.h: the engine handle and the batched GPU
+// entry points.  Everything here launches the kernels of bgx_kernels.cuh / bgx_td.cuh on
+// the engine's stream; there is no CPU path — without a device bgx_create fails.
+#include "../../include/bgx.h"
+#include "bgx_internal.h"
+#include "bgx_kernels.cuh"
+#include "bgx_td.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace bgx;
+
+struct bgx_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0, clock_khz = 0;
+    size_t global_mem = 0;
+    // model
+    float *flat = nullptr;        // [25604] state_dict order
+    float *table = nullptr;       // [198][128] feature-major cumulative table
+    float *wt = nullptr;          // [198][128] W1 transposed (TD kernel)
+    bool have_weights = false;
+    // scratch
+    static constexpr int kScratch = 12;
+    void *dbuf[kScratch] = {};
+    size_t dcap[kScratch] = {};
+    unsigned long long *counter = nullptr;   // work queue
+    unsigned long long *stats = nullptr;     // 8 counters
+    double *dstats = nullptr;                // TD: sum of squared errors
+    uint32_t *uniq_tables = nullptr;
+    int uniq_grid = 0;
+    // self-play population
+    long long n_slots = 0, first_id = 0, id_stride = 0;
+    uint32_t seed_lo = 0, seed_hi = 0;
+    int first_mover = 0, traj_cap = 0;
+    int8_t *slots = nullptr, *traj_pre = nullptr, *traj_chosen = nullptr;
+    int32_t *ply = nullptr;
+    long long *game_id = nullptr;
+    // TD
+    float *td_partial = nullptr;             // [td_grid][25604] per-CTA delta accumulators
+    int td_grid = 0;
+    // bookkeeping
+    long long launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t err__ = (call);                                                           \
+        if (err__ != cudaSuccess) {                                                           \
+            set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+            return BGX_E_CUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+#define NEED(cond, msg)                                   \
+    do {                                                  \
+        if (!(cond)) { set_error("%s: %s", __func__, msg); return BGX_E_INVALID; } \
+    } while (0)
+
+static int use(bgx_engine *e)
+{
+    if (!e) { set_error("null engine"); return BGX_E_INVALID; }
+    CU(cudaSetDevice(e->device));
+    return BGX_OK;
+}
+#define USE(e)                       \
+    do {                             \
+        int rc__ = use(e);           \
+        if (rc__ != BGX_OK) return rc__; \
+    } while (0)
+
+static int scratch(bgx_engine *e, int i, size_t bytes, void **out)
+{
+    if (e->dcap[i] < bytes) {
+        if (e->dbuf[i]) CU(cudaFree(e->dbuf[i]));
+        e->dbuf[i] = nullptr;
+        e->dcap[i] = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CU(cudaMalloc(&e->dbuf[i], want));
+        e->dcap[i] = want;
+    }
+    *out = e->dbuf[i];
+    return BGX_OK;
+}
+
+static void tick(bgx_engine *e) { cudaEventRecord(e->ev0, e->stream); }
+static void tock(bgx_engine *e) { cudaEventRecord(e->ev1, e->stream); e->timed = true; }
+
+static int game_grid(bgx_engine *e) { return e->sm_count; }   // persistent: one 16-warp CTA per SM
+
+extern "C" {
+
+int bgx_device_count(int *n)
+{
+    if (!n) { set_error("bgx_device_count: null"); return BGX_E_INVALID; }
+    int c = 0;
+    cudaError_t err = cudaGetDeviceCount(&c);
+    if (err != cudaSuccess) { *n = 0; set_error("cudaGetDeviceCount: %s", cudaGetErrorString(err)); return BGX_E_NO_DEVICE; }
+    *n = c;
+    return BGX_OK;
+}
+
+int bgx_create(int device, bgx_engine **out)
+{
+    if (!out) { set_error("bgx_create: null out"); return BGX_E_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n == 0) {
+        set_error("bgx_create: no CUDA device (%s); libbgx has no CPU path", err == cudaSuccess ? "0 devices" : cudaGetErrorString(err));
+        return BGX_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { set_error("bgx_create: device %d of %d", device, n); return BGX_E_INVALID; }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { set_error("bgx_create: device %d is sm_%d%d; libbgx is built for sm_100a only", device, prop.major, prop.minor); return BGX_E_NO_DEVICE; }
+    bgx_engine *e = new bgx_engine();
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    e->global_mem = prop.totalGlobalMem;
+    cudaDeviceGetAttribute(&e->clock_khz, cudaDevAttrClockRate, device);
+    CU(cudaMalloc(&e->flat, BGX_NPARAMS_PADDED * sizeof(float)));
+    CU(cudaMemset(e->flat, 0, BGX_NPARAMS_PADDED * sizeof(float)));
+    CU(cudaMalloc(&e->table, kTableBytes));
+    CU(cudaMalloc(&e->wt, kTableBytes));
+    CU(cudaMalloc(&e->counter, sizeof(unsigned long long)));
+    CU(cudaMalloc(&e->stats, 8 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&e->dstats, 2 * sizeof(double)));
+    CU(cudaEventCreate(&e->ev0));
+    CU(cudaEventCreate(&e->ev1));
+    CU(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, kGameSmem));
+    CU(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kGameSmem));
+    CU(cudaFuncSetAttribute(k_selfplay, cudaFuncAttributeMaxDynamicSharedMemorySize, kGameSmem));
+    CU(cudaFuncSetAttribute(k_td_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
+    *out = e;
+    return BGX_OK;
+}
+
+int bgx_destroy(bgx_engine *e)
+{
+    if (!e) return BGX_OK;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < bgx_engine::kScratch; i++) cudaFree(e->dbuf[i]);
+    cudaFree(e->flat); cudaFree(e->table); cudaFree(e->wt); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats);
+    cudaFree(e->uniq_tables); cudaFree(e->slots); cudaFree(e->traj_pre); cudaFree(e->traj_chosen);
+    cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial);
+    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+    delete e;
+    return BGX_OK;
+}
+
+int bgx_set_stream(bgx_engine *e, void *cuda_stream)
+{
+    USE(e);
+    e->stream = (cudaStream_t)cuda_stream;
+    return BGX_OK;
+}
+
+int bgx_synchronize(bgx_engine *e)
+{
+    USE(e);
+    CU(cudaStreamSynchronize(e->stream));
+    return BGX_OK;
+}
+
+static int rebuild_table(bgx_engine *e)
+{
+    k_build_table<<<(kTableFloats + 255) / 256, 256, 0, e->stream>>>(e->flat, e->table, e->wt);
+    e->launches++;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
+int bgx_set_weights(bgx_engine *e, const float *W1, const float *b1, const float *w2, const float *b2)
+{
+    USE(e);
+    NEED(W1 && b1 && w2 && b2, "null weight pointer");
+    std::vector<float> flat(BGX_NPARAMS_PADDED, 0.f);
+    std::memcpy(flat.data(), W1, kTableFloats * sizeof(float));
+    std::memcpy(flat.data() + kTableFloats, b1, kHidden * sizeof(float));
+    std::memcpy(flat.data() + kTableFloats + kHidden, w2, kHidden * sizeof(float));
+    flat[kTableFloats + 2 * kHidden] = b2[0];
+    CU(cudaMemcpyAsync(e->flat, flat.data(), flat.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->have_weights = true;
+    return rebuild_table(e);
+}
+
+int bgx_get_weights(bgx_engine *e, float *W1, float *b1, float *w2, float *b2)
+{
+    USE(e);
+    NEED(W1 && b1 && w2 && b2, "null weight pointer");
+    std::vector<float> flat(BGX_NPARAMS_PADDED);
+    CU(cudaMemcpyAsync(flat.data(), e->flat, flat.size() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    std::memcpy(W1, flat.data(), kTableFloats * sizeof(float));
+    std::memcpy(b1, flat.data() + kTableFloats, kHidden * sizeof(float));
+    std::memcpy(w2, flat.data() + kTableFloats + kHidden, kHidden * sizeof(float));
+    b2[0] = flat[kTableFloats + 2 * kHidden];
+    return BGX_OK;
+}
+
+// ------------------------------------------------------------------------ enumeration
+
+static int ensure_uniq_tables(bgx_engine *e)
+{
+    if (e->uniq_tables) return BGX_OK;
+    int per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_enumerate_summary, kGameThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    e->uniq_grid = e->sm_count * per_sm;
+    const size_t bytes = (size_t)e->uniq_grid * kGameWarps * kUniqBytesPerWarp;
+    CU(cudaMalloc(&e->uniq_tables, bytes));
+    CU(cudaMemsetAsync(e->uniq_tables, 0, bytes, e->stream));
+    return BGX_OK;
+}
+
+int bgx_enumerate_summary(bgx_engine *e, const int8_t *queries, int64_t n, int32_t *n_seq, int32_t *n_unique, uint64_t *digest)
+{
+    USE(e);
+    NEED(queries && n_seq && n_unique && digest && n >= 0, "bad argument");
+    int rc = ensure_uniq_tables(e);
+    if (rc) return rc;
+    if (n == 0) return BGX_OK;
+    CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
+    tick(e);
+    k_enumerate_summary<<<e->uniq_grid, kGameThreads, 0, e->stream>>>(queries, n, n_seq, n_unique,
+                                                                       (unsigned long long *)digest, e->uniq_tables, e->counter);
+    tock(e);
+    e->launches++;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
+int bgx_enumerate_summary_host(bgx_engine *e, const int8_t *queries, int64_t n, int32_t *n_seq, int32_t *n_unique, uint64_t *digest)
+{
+    USE(e);
+    NEED(queries && n_seq && n_unique && digest && n >= 0, "bad argument");
+    if (n == 0) return BGX_OK;
+    void *dq, *dn, *du, *dd;
+    int rc;
+    if ((rc = scratch(e, 0, (size_t)n * 32, &dq))) return rc;
+    if ((rc = scratch(e, 1, (size_t)n * 4, &dn))) return rc;
+    if ((rc = scratch(e, 2, (size_t)n * 4, &du))) return rc;
+    if ((rc = scratch(e, 3, (size_t)n * 8, &dd))) return rc;
+    CU(cudaMemcpyAsync(dq, queries, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = bgx_enumerate_summary(e, (const int8_t *)dq, n, (int32_t *)dn, (int32_t *)du, (uint64_t *)dd))) return rc;
+    CU(cudaMemcpyAsync(n_seq, dn, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(n_unique, du, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(digest, dd, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BGX_OK;
+}
+
+int bgx_enumerate(bgx_engine *e, const int8_t *queries, int64_t n, const int64_t *offsets,
+                  int8_t *seq_moves, int8_t *seq_len, int8_t *states)
+{
+    USE(e);
+    NEED(queries && offsets && seq_moves && seq_len && states && n >= 0, "bad argument");
+    if (n == 0) return BGX_OK;
+    CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
+    tick(e);
+    k_enumerate_write<<<e->sm_count * 2, kGameThreads, 0, e->stream>>>(queries, n, (const long long *)offsets,
+                                                                        seq_moves, seq_len, states, e->counter);
+    tock(e);
+    e->launches++;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
+int bgx_enumerate_host(bgx_engine *e, const int8_t *queries, int64_t n, int64_t cap, int64_t *offsets,
+                       int8_t *seq_moves, int8_t *seq_len, int8_t *states, int64_t *total)
+{
+    USE(e);
+    NEED(queries && total && n >= 0 && cap >= 0, "bad argument");
+    *total = 0;
+    if (n == 0) { if (offsets) offsets[0] = 0; return BGX_OK; }
+    void *dq, *dn, *du, *dd, *doff;
+    int rc;
+    if ((rc = scratch(e, 0, (size_t)n * 32, &dq))) return rc;
+    if ((rc = scratch(e, 1, (size_t)n * 4, &dn))) return rc;
+    if ((rc = scratch(e, 2, (size_t)n * 4, &du))) return rc;
+    if ((rc = scratch(e, 3, (size_t)n * 8, &dd))) return rc;
+    if ((rc = scratch(e, 4, (size_t)(n + 1) * 8, &doff))) return rc;
+    CU(cudaMemcpyAsync(dq, queries, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = bgx_enumerate_summary(e, (const int8_t *)dq, n, (int32_t *)dn, (int32_t *)du, (uint64_t *)dd))) return rc;
+    std::vector<int32_t> cnt((size_t)n);
+    CU(cudaMemcpyAsync(cnt.data(), dn, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    std::vector<int64_t> off((size_t)n + 1);
+    off[0] = 0;
+    for (int64_t i = 0; i < n; i++) off[i + 1] = off[i] + cnt[i];
+    *total = off[n];
+    if (offsets) std::memcpy(offsets, off.data(), (size_t)(n + 1) * 8);
+    if (off[n] > cap) { set_error("bgx_enumerate_host: %lld rows needed, cap %lld", (long long)off[n], (long long)cap); return BGX_E_CAPACITY; }
+    NEED(seq_moves && seq_len && states, "null output buffer");
+    const size_t rows = (size_t)off[n];
+    if (rows == 0) return BGX_OK;
+    void *dm, *dl, *ds;
+    if ((rc = scratch(e, 5, rows * 8, &dm))) return rc;
+    if ((rc = scratch(e, 6, rows, &dl))) return rc;
+    if ((rc = scratch(e, 7, rows * 32, &ds))) return rc;
+    CU(cudaMemcpyAsync(doff, off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = bgx_enumerate(e, (const int8_t *)dq, n, (const int64_t *)doff, (int8_t *)dm, (int8_t *)dl, (int8_t *)ds))) return rc;
+    CU(cudaMemcpyAsync(seq_moves, dm, rows * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(seq_len, dl, rows, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(states, ds, rows * 32, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BGX_OK;
+}
+
+// ------------------------------------------------------------------------ encode / evaluate
+
+int bgx_encode(bgx_engine *e, const int8_t *records, int64_t n, float *X)
+{
+    USE(e);
+    NEED(records && X && n >= 0, "bad argument");
+    NEED(((uintptr_t)X & 15) == 0 && ((uintptr_t)records & 3) == 0, "X must be 16-byte aligned, records 4-byte aligned");
+    if (n == 0) return BGX_OK;
+    const long long tiles = (n + kEncRows - 1) / kEncRows;
+    long long grid = (long long)e->sm_count * 8;
+    if (grid > tiles) grid = tiles;
+    tick(e);
+    k_encode<<<(int)grid, kEncWarps * 32, 0, e->stream>>>(records, n, X);
+    tock(e);
+    e->launches++;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
+int bgx_encode_host(bgx_engine *e, const int8_t *records, int64_t n, float *X)
+{
+    USE(e);
+    NEED(records && X && n >= 0, "bad argument");
+    if (n == 0) return BGX_OK;
+    void *dq, *dx;
+    int rc;
+    if ((rc = scratch(e, 0, (size_t)n * 32, &dq))) return rc;
+    if ((rc = scratch(e, 8, (size_t)n * kFeatures * 4, &dx))) return rc;
+    CU(cudaMemcpyAsync(dq, records, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = bgx_encode(e, (const int8_t *)dq, n, (float *)dx))) return rc;
+    CU(cudaMemcpyAsync(X, dx, (size_t)n * kFeatures * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BGX_OK;
+}
+
+int bgx_evaluate(bgx_engine *e, const int8_t *records, int64_t n, float *V)
+{
+    USE(e);
+    NEED(records && V && n >= 0, "bad argument");
+    if (!e->have_weights) { set_error("bgx_evaluate: weights not set"); return BGX_E_STATE; }
+    if (n == 0) return BGX_OK;
+    tick(e);
+    k_evaluate<<<game_grid(e), kGameThreads, kGameSmem, e->stream>>>(records, n, V, e->table, e->flat);
+    tock(e);
+    e->launches++;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
+int bgx_evaluate_host(bgx_engine *e, const int8_t *records, int64_t n, float *V)
+{
+    USE(e);
+    NEED(records && V && n >= 0, "bad argument");
+    if (n == 0) return BGX_OK;
+    void *dq, *dv;
+    int rc;
+    if ((rc = scratch(e, 0, (size_t)n * 32, &dq))) return rc;
+    if ((rc = scratch(e, 1, (size_t)n * 4, &dv))) return rc;
+    CU(cudaMemcpyAsync(dq, records, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = bgx_evaluate(e, (const int8_t *)dq, n, (float *)dv))) return rc;
+    CU(cudaMemcpyAsync(V, dv, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BGX_OK;
+}
+
+// ------------------------------------------------------------------------ batched make_move
+
+int bgx_select_moves(bgx_engine *e, const int8_t *queries, int64_t n, float epsilon, uint64_t seed,
+                     int8_t *chosen, int8_t *moves, int8_t *moves_len, float *value, int32_t *n_seq, int32_t *n_scored)
+{
+    USE(e);
+    NEED(queries && n >= 0, "bad argument");
+    if (!e->have_weights) { set_error("bgx_select_moves: weights not set"); return BGX_E_STATE; }
+    if (n == 0) return BGX_OK;
+    SelectOut out = {chosen, moves, moves_len, value, n_seq, n_scored};
+    CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
+    tick(e);
+    k_select<<<game_grid(e), kGameThreads, kGameSmem, e->stream>>>(queries, n, epsilon, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                                    out, e->table, e->flat, e->counter);
+    tock(e);
+    e->launches++;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
+int bgx_select_moves_host(bgx_engine *e, const int8_t *queries, int64_t n, float epsilon, uint64_t seed,
+                          int8_t *chosen, int8_t *moves, int8_t *moves_len, float *value, int32_t *n_seq, int32_t *n_scored)
+{
+    USE(e);
+    NEED(queries && n >= 0, "bad argument");
+    if (n == 0) return BGX_OK;
+    void *dq, *dc, *dm, *dl, *dv, *dn, *ds;
+    int rc;
+    if ((rc = scratch(e, 0, (size_t)n * 32, &dq))) return rc;
+    if ((rc = scratch(e, 1, (size_t)n * 32, &dc))) return rc;
+    if ((rc = scratch(e, 2, (size_t)n * 8, &dm))) return rc;
+    if ((rc = scratch(e, 3, (size_t)n, &dl))) return rc;
+    if ((rc = scratch(e, 4, (size_t)n * 4, &dv))) return rc;
+    if ((rc = scratch(e, 5, (size_t)n * 4, &dn))) return rc;
+    if ((rc = scratch(e, 6, (size_t)n * 4, &ds))) return rc;
+    CU(cudaMemcpyAsync(dq, queries, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
+    rc = bgx_select_moves(e, (const int8_t *)dq, n, epsilon, seed, chosen ? (int8_t *)dc : nullptr, moves ? (int8_t *)dm : nullptr,
+                          moves_len ? (int8_t *)dl : nullptr, value ? (float *)dv : nullptr,
+                          n_seq ? (int32_t *)dn : nullptr, n_scored ? (int32_t *)ds : nullptr);
+    if (rc) return rc;
+    if (chosen) CU(cudaMemcpyAsync(chosen, dc, (size_t)n * 32, cudaMemcpyDeviceToHost, e->stream));
+    if (moves) CU(cudaMemcpyAsync(moves, dm, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (moves_len) CU(cudaMemcpyAsync(moves_len, dl, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    if (value) CU(cudaMemcpyAsync(value, dv, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (n_seq) CU(cudaMemcpyAsync(n_seq, dn, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (n_scored) CU(cudaMemcpyAsync(n_scored, ds, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BGX_OK;
+}
+
+// ------------------------------------------------------------------------ self-play
+
+int bgx_selfplay_init(bgx_engine *e, int64_t n_slots, int64_t first_id, int64_t id_stride, uint64_t seed,
+                      int first_mover, int32_t traj_cap)
+{
+    USE(e);
+    NEED(n_slots > 0 && id_stride > 0 && first_id >= 0 && traj_cap >= 0, "bad argument");
+    NEED(first_mover == BGX_FIRST_ROLLOFF || first_mover == BGX_FIRST_PARITY, "unknown first-mover rule");
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(e->slots); cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->traj_pre); cudaFree(e->traj_chosen);
+    e->slots = nullptr; e->ply = nullptr; e->game_id = nullptr; e->traj_pre = nullptr; e->traj_chosen = nullptr;
+    e->n_slots = 0;
+    CU(cudaMalloc(&e->slots, (size_t)n_slots * 32));
+    CU(cudaMalloc(&e->ply, (size_t)n_slots * 4));
+    CU(cudaMalloc(&e->game_id, (size_t)n_slots * 8));
+    if (traj_cap > 0) {
+        CU(cudaMalloc(&e->traj_pre, (size_t)n_slots * traj_cap * 32));
+        CU(cudaMalloc(&e->traj_chosen, (size_t)n_slots * traj_cap * 32));
+    }
+    e->n_slots = n_slots; e->first_id = first_id; e->id_stride = id_stride;
+    e->seed_lo = (uint32_t)seed; e->seed_hi = (uint32_t)(seed >> 32);
+    e->first_mover = first_mover; e->traj_cap = traj_cap;
+    k_selfplay_reset<<<e->sm_count * 4, 256, 0, e->stream>>>(e->slots, e->ply, e->game_id, n_slots, first_id, id_stride, 0,
+                                                            e->seed_lo, e->seed_hi, first_mover);
+    e->launches++;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
+int bgx_selfplay_next_round(bgx_engine *e)
+{
+    USE(e);
+    if (e->n_slots == 0) { set_error("bgx_selfplay_next_round: call bgx_selfplay_init first"); return BGX_E_STATE; }
+    k_selfplay_reset<<<e->sm_count * 4, 256, 0, e->stream>>>(e->slots, e->ply, e->game_id, e->n_slots, e->first_id, e->id_stride, 1,
+                                                            e->seed_lo, e->seed_hi, e->first_mover);
+    e->launches++;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
+static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilon, bgx_stats *out)
+{
+    if (e->n_slots == 0) { set_error("self-play: call bgx_selfplay_init first"); return BGX_E_STATE; }
+    if (!e->have_weights) { set_error("self-play: weights not set"); return BGX_E_STATE; }
+    SelfplayParams p;
+    p.slots = e->slots; p.ply = e->ply; p.game_id = e->game_id;
+    p.traj_pre = e->traj_pre; p.traj_chosen = e->traj_chosen;
+    p.n_slots = e->n_slots; p.id_stride = e->id_stride;
+    p.seed_lo = e->seed_lo; p.seed_hi = e->seed_hi;
+    p.first_mover = e->first_mover; p.traj_cap = e->traj_cap;
+    p.n_plies = n_plies; p.round_mode = round_mode; p.epsilon = epsilon;
+    p.counter = e->counter; p.stats = e->stats;
+    CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
+    CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
+    tick(e);
+    k_selfplay<<<game_grid(e), kGameThreads, kGameSmem, e->stream>>>(p, e->table, e->flat);
+    tock(e);
+    e->launches++;
+    CU(cudaGetLastError());
+    if (out) {
+        unsigned long long h[8];
+        CU(cudaMemcpyAsync(h, e->stats, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        std::memset(out, 0, sizeof *out);
+        out->plies = (int64_t)h[0]; out->sequences = (int64_t)h[1]; out->scored = (int64_t)h[2];
+        out->games_finished = (int64_t)h[3]; out->p1_wins = (int64_t)h[4]; out->truncated = (int64_t)h[5];
+    }
+    return BGX_OK;
+}
+
+int bgx_selfplay_step(bgx_engine *e, int32_t n_plies, float epsilon, bgx_stats *out)
+{
+    USE(e);
+    NEED(n_plies > 0, "n_plies must be positive");
+    return run_selfplay(e, n_plies, 0, epsilon, out);
+}
+
+int bgx_selfplay_round(bgx_engine *e, float epsilon, bgx_stats *out)
+{
+    USE(e);
+    return run_selfplay(e, 0, 1, epsilon, out);
+}
+
+int bgx_selfplay_read(bgx_engine *e, int8_t *records, int32_t *ply, int64_t *game_id)
+{
+    USE(e);
+    if (e->n_slots == 0) { set_error("bgx_selfplay_read: call bgx_selfplay_init first"); return BGX_E_STATE; }
+    if (records) CU(cudaMemcpyAsync(records, e->slots, (size_t)e->n_slots * 32, cudaMemcpyDeviceToHost, e->stream));
+    if (ply) CU(cudaMemcpyAsync(ply, e->ply, (size_t)e->n_slots * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (game_id) CU(cudaMemcpyAsync(game_id, e->game_id, (size_t)e->n_slots * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BGX_OK;
+}
+
+int bgx_export_trajectory(bgx_engine *e, int64_t slot, int32_t cap, int8_t *pre, int8_t *chosen, int32_t *T)
+{
+    USE(e);
+    NEED(T && slot >= 0 && slot < e->n_slots, "bad slot");
+    if (!e->traj_pre) { set_error("bgx_export_trajectory: population was created with traj_cap = 0"); return BGX_E_STATE; }
+    int32_t ply = 0;
+    CU(cudaMemcpyAsync(&ply, e->ply + slot, 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (ply > e->traj_cap) ply = e->traj_cap;
+    *T = ply;
+    if (ply > cap) { set_error("bgx_export_trajectory: %d plies, cap %d", ply, cap); return BGX_E_CAPACITY; }
+    if (ply == 0) return BGX_OK;
+    if (pre) CU(cudaMemcpyAsync(pre, e->traj_pre + (size_t)slot * e->traj_cap * 32, (size_t)ply * 32, cudaMemcpyDeviceToHost, e->stream));
+    if (chosen) CU(cudaMemcpyAsync(chosen, e->traj_chosen + (size_t)slot * e->traj_cap * 32, (size_t)ply * 32, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BGX_OK;
+}
+
+// ------------------------------------------------------------------------ TD(lambda)
+
+static int ensure_td(bgx_engine *e)
+{
+    if (e->td_partial) return BGX_OK;
+    e->td_grid = e->sm_count;
+    CU(cudaMalloc(&e->td_partial, (size_t)e->td_grid * BGX_NPARAMS_PADDED * sizeof(float)));
+    return BGX_OK;
+}
+
+static int launch_td(bgx_engine *e, const int8_t *traj, const int8_t *slots, const int32_t *ply, long long n_games, int traj_cap,
+                     float lr, float lambda, float *delta_dev, float *final_weights, double *sq_errors, bgx_stats *out)
+{
+    int rc = ensure_td(e);
+    if (rc) return rc;
+    int grid = e->td_grid;
+    if (grid > n_games) grid = (int)n_games;
+    TdParams p;
+    p.traj = traj; p.slots = slots; p.ply = ply; p.n_games = n_games; p.traj_cap = traj_cap;
+    p.lr = (double)lr; p.lambda = lambda;
+    p.flat = e->flat; p.wt = e->wt; p.partial = e->td_partial;
+    p.final_weights = final_weights; p.sq_errors = sq_errors;
+    p.stats = e->stats; p.dstats = e->dstats;
+    CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
+    CU(cudaMemsetAsync(e->dstats, 0, 2 * sizeof(double), e->stream));
+    tick(e);
+    k_td_replay<<<grid, kTdThreads, kTdSmem, e->stream>>>(p);
+    e->launches++;
+    CU(cudaGetLastError());
+    if (delta_dev) {
+        k_td_reduce<<<(BGX_NPARAMS_PADDED + 255) / 256, 256, 0, e->stream>>>(e->td_partial, grid, delta_dev);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    tock(e);
+    if (out) {
+        unsigned long long h[8];
+        double d[2];
+        CU(cudaMemcpyAsync(h, e->stats, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(d, e->dstats, sizeof d, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        std::memset(out, 0, sizeof *out);
+        out->td_steps = (int64_t)h[6];
+        out->games_finished = (int64_t)h[3];
+        out->truncated = (int64_t)h[5];
+        out->td_sq_error = d[0];
+    }
+    return BGX_OK;
+}
+
+int bgx_td_replay(bgx_engine *e, float lr, float lambda, float *delta_dev, bgx_stats *out)
+{
+    USE(e);
+    NEED(delta_dev, "null delta buffer");
+    if (e->n_slots == 0 || !e->traj_pre) { set_error("bgx_td_replay: needs a population created with traj_cap > 0"); return BGX_E_STATE; }
+    if (!e->have_weights) { set_error("bgx_td_replay: weights not set"); return BGX_E_STATE; }
+    return launch_td(e, e->traj_pre, e->slots, e->ply, e->n_slots, e->traj_cap, lr, lambda, delta_dev, nullptr, nullptr, out);
+}
+
+int bgx_apply_delta(bgx_engine *e, const float *delta_dev, float scale)
+{
+    USE(e);
+    NEED(delta_dev, "null delta buffer");
+    k_axpy<<<(BGX_NPARAMS + 255) / 256, 256, 0, e->stream>>>(e->flat, delta_dev, scale, BGX_NPARAMS);
+    e->launches++;
+    CU(cudaGetLastError());
+    return rebuild_table(e);
+}
+
+int bgx_td_replay_host(bgx_engine *e, const int8_t *records, int32_t T, int player1_won, float lr, float lambda,
+                       float *new_W1, float *new_b1, float *new_w2, float *new_b2, double *sq_errors)
+{
+    USE(e);
+    NEED(records && T > 0 && new_W1 && new_b1 && new_w2 && new_b2, "bad argument");
+    if (!e->have_weights) { set_error("bgx_td_replay_host: weights not set"); return BGX_E_STATE; }
+    void *dtraj, *dslot, *dply, *dfinal, *dsq;
+    int rc;
+    if ((rc = scratch(e, 0, (size_t)T * 32, &dtraj))) return rc;
+    if ((rc = scratch(e, 1, 32, &dslot))) return rc;
+    if ((rc = scratch(e, 2, 4, &dply))) return rc;
+    if ((rc = scratch(e, 9, BGX_NPARAMS_PADDED * sizeof(float), &dfinal))) return rc;
+    if ((rc = scratch(e, 10, (size_t)T * 8, &dsq))) return rc;
+    int8_t slot[32] = {0};
+    slot[31] = player1_won ? kP1Won : kP2Won;
+    CU(cudaMemcpyAsync(dtraj, records, (size_t)T * 32, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(dslot, slot, 32, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(dply, &T, 4, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemsetAsync(dsq, 0, (size_t)T * 8, e->stream));
+    if ((rc = launch_td(e, (const int8_t *)dtraj, (const int8_t *)dslot, (const int32_t *)dply, 1, T, lr, lambda,
+                        nullptr, (float *)dfinal, (double *)dsq, nullptr)))
+        return rc;
+    std::vector<float> flat(BGX_NPARAMS_PADDED);
+    CU(cudaMemcpyAsync(flat.data(), dfinal, flat.size() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (sq_errors && T > 1) CU(cudaMemcpyAsync(sq_errors, dsq, (size_t)(T - 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    std::memcpy(new_W1, flat.data(), kTableFloats * sizeof(float));
+    std::memcpy(new_b1, flat.data() + kTableFloats, kHidden * sizeof(float));
+    std::memcpy(new_w2, flat.data() + kTableFloats + kHidden, kHidden * sizeof(float));
+    new_b2[0] = flat[kTableFloats + 2 * kHidden];
+    return BGX_OK;
+}
+
+// ------------------------------------------------------------------------ introspection
+
+int bgx_launch_count(bgx_engine *e, int64_t *n)
+{
+    if (!e || !n) { set_error("bgx_launch_count: null"); return BGX_E_INVALID; }
+    *n = e->launches;
+    return BGX_OK;
+}
+
+int bgx_last_kernel_ms(bgx_engine *e, float *ms)
+{
+    USE(e);
+    NEED(ms, "null");
+    if (!e->timed) { set_error("bgx_last_kernel_ms: nothing launched yet"); return BGX_E_STATE; }
+    CU(cudaEventSynchronize(e->ev1));
+    CU(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return BGX_OK;
+}
+
+int bgx_device_props(bgx_engine *e, int *sm_count, int *clock_khz, int64_t *global_mem)
+{
+    if (!e) { set_error("bgx_device_props: null"); return BGX_E_INVALID; }
+    if (sm_count) *sm_count = e->sm_count;
+    if (clock_khz) *clock_khz = e->clock_khz;
+    if (global_mem) *global_mem = (int64_t)e->global_mem;
+    return BGX_OK;
+}
+
+} // extern "C"

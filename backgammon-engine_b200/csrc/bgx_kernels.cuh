@@ -1,0 +1,439 @@
+// bgx_kernels.cuh — the __global__ kernels of libbgx (sm_100a).  See bgx_device.cuh for
+// the execution model; DESIGN.md for the roofline of each kernel.
+#pragma once
+#include "bgx_device.cuh"
+
+namespace bgx {
+
+constexpr int kGameWarps = 16;                     // warps per CTA in the warp-per-position kernels
+constexpr int kGameThreads = kGameWarps * 32;
+// dynamic shared memory of the kernels that score positions: table + per-warp caches + barrier
+constexpr int kGameSmem = kTableBytes + kGameWarps * kCacheBytesPerWarp + 16;
+
+// exact-dedup table of the summary kernel: per warp, in global memory (L2 resident)
+constexpr int kUniqSlots = 4096;                   // 8 words each, probed as buckets of 4 slots
+constexpr int kUniqWords = 8;
+constexpr size_t kUniqBytesPerWarp = (size_t)kUniqSlots * kUniqWords * 4;   // 128 KiB
+
+// ---- weights: state_dict order -> feature-major cumulative table -----------------------
+// flat = [W1[128][198] | b1[128] | w2[128] | b2[1]]  (model.py:36-37)
+__global__ void k_build_table(const float *__restrict__ flat, float *__restrict__ T, float *__restrict__ Wt)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kTableFloats) return;
+    const int f = idx / kHidden, j = idx % kHidden;
+    const float *w = flat + j * kFeatures;
+    float s = w[f];
+    Wt[idx] = s;                                   // plain transpose, for the TD kernel
+    if (f < 192 && (f & 3) != 3) {
+        const int base = f & ~3;
+        s = w[base];
+        for (int t = base + 1; t <= f; t++) s += w[t];
+    }
+    T[idx] = s;
+}
+
+// a warp-wide work queue: lane 0 claims, everybody learns
+__device__ __forceinline__ long long claim(unsigned long long *counter, int lane)
+{
+    unsigned long long i = 0;
+    if (lane == 0) i = atomicAdd(counter, 1ull);
+    return (long long)__shfl_sync(kFull, i, 0);
+}
+
+// one 32-byte record per warp: lane i gets byte i
+__device__ __forceinline__ int load_record_byte(const int8_t *rec, int lane) { return (int)rec[lane]; }
+
+// ---- batched evaluateTurnSequences, summary form (cppsrc/game.cpp:193-222) -------------
+struct SummaryLeaf {
+    uint32_t *table;       // this warp's exact-dedup table (global)
+    uint32_t gen;
+    int lane;
+    int n_seq = 0, n_unique = 0;
+    bool overflow = false;
+    uint64_t digest = 0;
+
+    __device__ __forceinline__ void operator()(int v, uint64_t moves, int)
+    {
+        uint32_t k[5];
+        key_planes(v, k);
+        n_seq++;
+        digest = digest * kDigestMul + leaf_hash(k, moves);
+        if (overflow) return;
+        // bucket of 4 slots x 8 words = one 128-byte line; lane l looks at word l%8 of slot l/8
+        const uint32_t k4g = k[4] | (gen << 24);
+        const int w = lane & 7;
+        const uint32_t mine = w == 0 ? k[0] : w == 1 ? k[1] : w == 2 ? k[2] : w == 3 ? k[3] : k4g;
+        uint32_t bucket = hash_planes(k) & (kUniqSlots / 4 - 1);
+        for (int probe = 0; probe < kUniqSlots / 4; probe++) {
+            uint32_t *line = table + (size_t)bucket * 32;
+            const uint32_t got = line[lane];
+            const uint32_t same = __ballot_sync(kFull, w >= 5 || got == mine);
+            const uint32_t stale = __ballot_sync(kFull, w == 4 && (got >> 24) != gen);
+            for (int s = 0; s < 4; s++) {
+                if (((same >> (8 * s)) & 0xFFu) == 0xFFu) return;              // seen before
+                if ((stale >> (8 * s + 4)) & 1u) {                              // first free slot: insert
+                    if ((lane >> 3) == s && w < 5) line[lane] = mine;
+                    __syncwarp();
+                    n_unique++;
+                    return;
+                }
+            }
+            bucket = (bucket + 1) & (kUniqSlots / 4 - 1);
+        }
+        overflow = true;
+    }
+};
+
+__global__ void __launch_bounds__(kGameThreads, 1)
+k_enumerate_summary(const int8_t *__restrict__ queries, long long n, int32_t *__restrict__ n_seq,
+                    int32_t *__restrict__ n_unique, unsigned long long *__restrict__ digest,
+                    uint32_t *__restrict__ tables, unsigned long long *counter)
+{
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t *table = tables + (size_t)gwarp * (kUniqBytesPerWarp / 4);
+    uint32_t gen = 0;
+    for (;;) {
+        const long long q = claim(counter, lane);
+        if (q >= n) break;
+        const int b = load_record_byte(queries + q * 32, lane);
+        const int root = lane < 28 ? b : 0;
+        const int player = __shfl_sync(kFull, b, 28), d1 = __shfl_sync(kFull, b, 29), d2 = __shfl_sync(kFull, b, 30);
+        gen = (gen + 1) & 0xFFu;
+        if (gen == 0) {
+            for (int i = lane; i < kUniqSlots * kUniqWords; i += 32) table[i] = 0;
+            gen = 1;
+            __syncwarp();
+        }
+        SummaryLeaf leaf;
+        leaf.table = table; leaf.gen = gen; leaf.lane = lane;
+        walk_turn(root, lane, player, d1, d2, leaf);
+        if (lane == 0) {
+            n_seq[q] = leaf.n_seq;
+            n_unique[q] = leaf.overflow ? -1 : leaf.n_unique;
+            digest[q] = leaf.digest;
+        }
+    }
+}
+
+// ---- batched evaluateTurnSequences, materialised (game.cpp:193-222, bindings:27-39) ----
+struct WriteLeaf {
+    int8_t *moves, *lens, *states;   // already offset to this query's first row
+    int lane, player;
+    long long row = 0;
+    __device__ __forceinline__ void operator()(int v, uint64_t mv, int len)
+    {
+        int8_t *st = states + row * 32;
+        const int out = lane < 28 ? v : (lane == 28 ? player : 0);
+        st[lane] = (int8_t)out;                                        // one 32-byte sector per sequence
+        if (lane < 8) {
+            const int j = lane >> 1;
+            const int code = (int)((mv >> (10 * j + 5 * (lane & 1))) & 31u);
+            moves[row * 8 + lane] = (int8_t)(j < len ? code : 0);
+        }
+        if (lane == 8) lens[row] = (int8_t)len;
+        row++;
+    }
+};
+
+__global__ void __launch_bounds__(kGameThreads, 1)
+k_enumerate_write(const int8_t *__restrict__ queries, long long n, const long long *__restrict__ offsets,
+                  int8_t *__restrict__ seq_moves, int8_t *__restrict__ seq_len, int8_t *__restrict__ states,
+                  unsigned long long *counter)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        const long long q = claim(counter, lane);
+        if (q >= n) break;
+        const int b = load_record_byte(queries + q * 32, lane);
+        const int root = lane < 28 ? b : 0;
+        const int player = __shfl_sync(kFull, b, 28), d1 = __shfl_sync(kFull, b, 29), d2 = __shfl_sync(kFull, b, 30);
+        const long long base = offsets[q];
+        WriteLeaf leaf;
+        leaf.moves = seq_moves + base * 8; leaf.lens = seq_len + base; leaf.states = states + base * 32;
+        leaf.lane = lane; leaf.player = player;
+        walk_turn(root, lane, player, d1, d2, leaf);
+    }
+}
+
+// ---- _encode_states_np (model.py:111-144): records -> fp32 [n][198], HBM-bound -----------
+// A CTA stages a tile of kEncRows rows (kEncRows*792 B, a 16-byte multiple starting on a
+// 16-byte boundary because tiles start on even rows) in shared memory, then streams it out
+// with 16-byte vector stores: every store instruction of a warp covers 512 contiguous bytes.
+constexpr int kEncWarps = 8;
+constexpr int kEncRows = 32;                        // rows per tile (4 per warp)
+constexpr int kEncTileFloats = kEncRows * kFeatures;
+
+__global__ void __launch_bounds__(kEncWarps * 32)
+k_encode(const int8_t *__restrict__ records, long long n, float *__restrict__ X)
+{
+    __shared__ __align__(16) float tile[kEncTileFloats];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long n_tiles = (n + kEncRows - 1) / kEncRows;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const long long row0 = t * kEncRows;
+        // 4 records (128 B) per warp in one coalesced 4-byte-per-lane load
+        const long long r_first = row0 + warp * 4;
+        int word = 0;
+        {
+            const long long byte = r_first * 32 + lane * 4;
+            if (byte + 3 < n * 32) word = *reinterpret_cast<const int *>(records + byte);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int w = __shfl_sync(kFull, word, r * 8 + (lane >> 2));
+            const int v = (int)(int8_t)(w >> (8 * (lane & 3)));        // byte `lane` of record r
+            const int turn = __shfl_sync(kFull, v, 28);
+            const int jail1 = __shfl_sync(kFull, v, 24), jail2 = __shfl_sync(kFull, v, 25);
+            const int off1 = __shfl_sync(kFull, v, 26), off2 = __shfl_sync(kFull, v, 27);
+            float *row = tile + (warp * 4 + r) * kFeatures;
+            if (lane < 24) {
+                const int c = v < 0 ? -v : v;
+                const float a = c >= 1 ? 1.f : 0.f, b = c >= 2 ? 1.f : 0.f, cc = c >= 3 ? 1.f : 0.f;
+                const float d = c >= 4 ? (float)(c - 3) * 0.5f : 0.f;
+                float2 *dst = reinterpret_cast<float2 *>(row + 8 * lane);   // 8-byte aligned always
+                const bool p1 = v > 0;
+                dst[0] = p1 ? make_float2(a, b) : make_float2(0.f, 0.f);
+                dst[1] = p1 ? make_float2(cc, d) : make_float2(0.f, 0.f);
+                dst[2] = p1 ? make_float2(0.f, 0.f) : make_float2(a, b);
+                dst[3] = p1 ? make_float2(0.f, 0.f) : make_float2(cc, d);
+            } else if (lane == 24) {
+                row[192] = turn == 0 ? 1.f : 0.f;
+                row[193] = turn == 0 ? 0.f : 1.f;
+                row[194] = (float)jail1 * 0.5f;
+                row[195] = (float)jail2 * 0.5f;
+            } else if (lane == 25) {
+                row[196] = off_feature(off1);
+                row[197] = off_feature(off2);
+            }
+        }
+        __syncthreads();
+        const long long rows_here = (n - row0) < kEncRows ? (n - row0) : kEncRows;
+        const int floats_here = (int)rows_here * kFeatures;
+        float *out = X + row0 * kFeatures;
+        const int vec = floats_here / 4;
+        const float4 *src4 = reinterpret_cast<const float4 *>(tile);
+        float4 *out4 = reinterpret_cast<float4 *>(out);
+        for (int i = threadIdx.x; i < vec; i += blockDim.x) __stcs(out4 + i, src4[i]);
+        for (int i = vec * 4 + threadIdx.x; i < floats_here; i += blockDim.x) out[i] = tile[i];
+        __syncthreads();
+    }
+}
+
+// ---- forward(_encode_states_np(states, turn)) (model.py:63-67): records -> V ------------
+__global__ void __launch_bounds__(kGameThreads, 1)
+k_evaluate(const int8_t *__restrict__ records, long long n, float *__restrict__ V,
+           const float *__restrict__ T, const float *__restrict__ flat)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float *sT = reinterpret_cast<float *>(smem);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kGameWarps * kCacheBytesPerWarp);
+    stage_table(sT, T, bar);
+    const int lane = threadIdx.x & 31;
+    Evaluator ev;
+    ev.T4 = reinterpret_cast<const float4 *>(sT);
+    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, lane);
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += warps) {
+        const int b = load_record_byte(records + q * 32, lane);
+        const int v = lane < 28 ? b : 0;
+        ev.begin(__shfl_sync(kFull, b, 28) ? 1 : 0, lane);
+        const float val = ev.value(v, lane);
+        if (lane == 0) V[q] = val;
+    }
+}
+
+// ---- batched make_move (model.py:180-222) ------------------------------------------------
+struct SelectOut {
+    int8_t *chosen, *moves, *moves_len;
+    float *value;
+    int32_t *n_seq, *n_scored;
+};
+
+__device__ __forceinline__ void store_choice(const SelectOut &o, long long q, const Choice &c, int lane, int player)
+{
+    const int len = (int)(c.moves >> 40);
+    if (o.chosen) {
+        const int out = lane < 28 ? c.v : (lane == 28 ? player : (lane == 31 ? (len > 0 ? 1 : 0) : 0));
+        o.chosen[q * 32 + lane] = (int8_t)out;
+    }
+    if (o.moves && lane < 8) {
+        const int j = lane >> 1;
+        const int code = (int)((c.moves >> (10 * j + 5 * (lane & 1))) & 31u);
+        o.moves[q * 8 + lane] = (int8_t)(j < len ? code : 0);
+    }
+    if (lane == 0) {
+        if (o.moves_len) o.moves_len[q] = (int8_t)len;
+        if (o.value) o.value[q] = c.value;
+        if (o.n_seq) o.n_seq[q] = c.n_seq;
+        if (o.n_scored) o.n_scored[q] = c.n_scored;
+    }
+}
+
+__global__ void __launch_bounds__(kGameThreads, 1)
+k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_t seed_lo, uint32_t seed_hi,
+         SelectOut out, const float *__restrict__ T, const float *__restrict__ flat, unsigned long long *counter)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float *sT = reinterpret_cast<float *>(smem);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kGameWarps * kCacheBytesPerWarp);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SeenCache cache;
+    cache.slots = reinterpret_cast<uint32_t *>(smem + kTableBytes + warp * kCacheBytesPerWarp);
+    cache.gen = 0;
+    for (int i = lane; i < kCacheSlots * kCacheWords; i += 32) cache.slots[i] = 0;
+    stage_table(sT, T, bar);
+    Evaluator ev;
+    ev.T4 = reinterpret_cast<const float4 *>(sT);
+    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, lane);
+    for (;;) {
+        const long long q = claim(counter, lane);
+        if (q >= n) break;
+        const int b = load_record_byte(queries + q * 32, lane);
+        const int root = lane < 28 ? b : 0;
+        const int player = __shfl_sync(kFull, b, 28) ? 1 : 0, d1 = __shfl_sync(kFull, b, 29), d2 = __shfl_sync(kFull, b, 30);
+        bool explore = false;
+        uint32_t u = 0;
+        if (epsilon > 0.f) {
+            const Philox r = philox4x32_10(seed_lo, seed_hi, 0u, (uint32_t)q, (uint32_t)((unsigned long long)q >> 32), 2u);
+            explore = (float)r.x[0] * 2.3283064365386963e-10f < epsilon;
+            u = r.x[1];
+        }
+        const Choice c = choose_ply(root, lane, player, d1, d2, ev, cache, explore, u);
+        store_choice(out, q, c, lane, player);
+    }
+}
+
+// ---- self-play population: play_game (train.py:64-121) for n_slots games at once ---------
+struct SelfplayParams {
+    int8_t *slots;          // [n_slots][32]: position, byte 28 player to move, byte 31 status
+    int32_t *ply;           // [n_slots] plies played in the current game
+    long long *game_id;     // [n_slots]
+    int8_t *traj_pre;       // [n_slots][traj_cap][32] pre-move records (bytes 29,30 = dice) or NULL
+    int8_t *traj_chosen;    // [n_slots][traj_cap][32] chosen afterstates or NULL
+    long long n_slots, id_stride;
+    uint32_t seed_lo, seed_hi;
+    int first_mover, traj_cap;
+    int n_plies;            // step mode: plies per slot per call
+    int round_mode;         // 1: play the current game to its end, no restart
+    float epsilon;
+    unsigned long long *counter;
+    unsigned long long *stats;   // plies, sequences, scored, finished, p1 wins, truncated
+};
+
+__global__ void __launch_bounds__(kGameThreads, 1)
+k_selfplay(SelfplayParams p, const float *__restrict__ T, const float *__restrict__ flat)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float *sT = reinterpret_cast<float *>(smem);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kGameWarps * kCacheBytesPerWarp);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SeenCache cache;
+    cache.slots = reinterpret_cast<uint32_t *>(smem + kTableBytes + warp * kCacheBytesPerWarp);
+    cache.gen = 0;
+    for (int i = lane; i < kCacheSlots * kCacheWords; i += 32) cache.slots[i] = 0;
+    stage_table(sT, T, bar);
+    Evaluator ev;
+    ev.T4 = reinterpret_cast<const float4 *>(sT);
+    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, lane);
+
+    unsigned long long s_plies = 0, s_seq = 0, s_scored = 0, s_fin = 0, s_p1 = 0, s_trunc = 0;
+    for (;;) {
+        const long long slot = claim(p.counter, lane);
+        if (slot >= p.n_slots) break;
+        int8_t *rec = p.slots + slot * 32;
+        const int b = load_record_byte(rec, lane);
+        int v = lane < 28 ? b : 0;
+        int player = __shfl_sync(kFull, b, 28) ? 1 : 0;
+        int status = __shfl_sync(kFull, b, 31);
+        int ply = p.ply[slot];
+        unsigned long long gid = (unsigned long long)p.game_id[slot];
+        if (p.round_mode && status != kRunning) continue;
+        const int budget = p.round_mode ? 0x7fffffff : p.n_plies;
+        for (int step = 0; step < budget; step++) {
+            if (p.round_mode && p.traj_cap > 0 && ply >= p.traj_cap) {   // the log is full: give the game up
+                status = kTruncated;
+                s_trunc++;
+                break;
+            }
+            const Philox r = philox4x32_10(p.seed_lo, p.seed_hi, (uint32_t)ply, (uint32_t)gid, (uint32_t)(gid >> 32), 0u);
+            const int d1 = die_of(r.x[0]), d2 = die_of(r.x[1]);
+            const bool rec_traj = p.traj_pre != nullptr && ply < p.traj_cap && status == kRunning;
+            if (rec_traj) {
+                int8_t *t = p.traj_pre + ((size_t)slot * p.traj_cap + ply) * 32;
+                const int out = lane < 28 ? v : (lane == 28 ? player : (lane == 29 ? d1 : (lane == 30 ? d2 : 0)));
+                t[lane] = (int8_t)out;                               // train.py:105-106
+            }
+            bool explore = false;
+            uint32_t u = 0;
+            if (p.epsilon > 0.f) {
+                const Philox e = philox4x32_10(p.seed_lo, p.seed_hi, (uint32_t)ply, (uint32_t)gid, (uint32_t)(gid >> 32), 2u);
+                explore = (float)e.x[0] * 2.3283064365386963e-10f < p.epsilon;
+                u = e.x[1];
+            }
+            const Choice c = choose_ply(v, lane, player, d1, d2, ev, cache, explore, u);   // model.py:180-222
+            v = c.v;
+            s_plies++;
+            s_seq += (unsigned long long)c.n_seq;
+            s_scored += (unsigned long long)c.n_scored;
+            if (rec_traj && p.traj_chosen) {
+                int8_t *t = p.traj_chosen + ((size_t)slot * p.traj_cap + ply) * 32;
+                const int len = (int)(c.moves >> 40);
+                const int out = lane < 28 ? v : (lane == 28 ? player : (lane == 31 ? (len > 0 ? 1 : 0) : 0));
+                t[lane] = (int8_t)out;
+            }
+            // is_game_over (game.cpp:388-407): PLAYER1 is checked first
+            const int off1 = __shfl_sync(kFull, v, 26), off2 = __shfl_sync(kFull, v, 27);
+            const int winner = off1 == 15 ? 0 : (off2 == 15 ? 1 : -1);
+            ply++;
+            if (winner >= 0) {
+                s_fin++;
+                s_p1 += winner == 0;
+                if (p.round_mode) {
+                    status = winner == 0 ? kP1Won : kP2Won;
+                    break;
+                }
+                gid += (unsigned long long)p.id_stride;              // restart in place
+                v = start_value(lane);
+                player = first_mover_of(p.seed_lo, p.seed_hi, gid, p.first_mover);
+                ply = 0;
+                status = kRunning;
+            } else {
+                player ^= 1;                                         // train.py:119-120
+            }
+        }
+        const int out = lane < 28 ? v : (lane == 28 ? player : (lane == 31 ? status : 0));
+        rec[lane] = (int8_t)out;
+        if (lane == 0) {
+            p.ply[slot] = ply;
+            p.game_id[slot] = (long long)gid;
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(p.stats + 0, s_plies);
+        atomicAdd(p.stats + 1, s_seq);
+        atomicAdd(p.stats + 2, s_scored);
+        atomicAdd(p.stats + 3, s_fin);
+        atomicAdd(p.stats + 4, s_p1);
+        atomicAdd(p.stats + 5, s_trunc);
+    }
+}
+
+// (re)seat every slot: opening position, first mover, ply 0
+__global__ void k_selfplay_reset(int8_t *slots, int32_t *ply, long long *game_id, long long n_slots,
+                                 long long first_id, long long id_stride, int advance,
+                                 uint32_t seed_lo, uint32_t seed_hi, int first_mover)
+{
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int lane = threadIdx.x & 31;
+    for (long long s = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_slots; s += warps) {
+        const unsigned long long gid = advance ? (unsigned long long)(game_id[s] + id_stride) : (unsigned long long)(first_id + s);
+        const int player = first_mover_of(seed_lo, seed_hi, gid, first_mover);
+        const int out = lane < 28 ? start_value(lane) : (lane == 28 ? player : 0);
+        slots[s * 32 + lane] = (int8_t)out;
+        if (lane == 0) { ply[s] = 0; game_id[s] = (long long)gid; }
+    }
+}
+
+} // namespace bgx

@@ -1,0 +1,240 @@
+/* bgx.h — C-ABI of libbgx, the B200-native batched backgammon self-play engine.
+ *
+ * This is the drop-in boundary for ONE hot path of romanoshiliarhopoulos/Backgammon-Engine:
+ *   enumerate every legal afterstate of (position, dice)  ->  encode 198 features  ->
+ *   score with the 198-128-1 sigmoid MLP  ->  argmax/argmin  ->  apply  ->  TD(lambda) update.
+ * The reference binds that path to Python through cppsrc/backgammon_bindings.cpp; the
+ * entry points below are what that binding file would call instead (INTEGRATION.md shows
+ * the pybind11 stubs).  Plain C types only: pointers + sizes, caller-allocated buffers,
+ * no exceptions; every function returns 0 on success or a negative BGX_E_* code and
+ * leaves a message in bgx_last_error() (thread-local).
+ *
+ * Citations "file:line" are relative to the reference checkout.
+ *
+ * POSITION  = the reference's TurnEval row (cppsrc/game.hpp:17-28), 28 ints:
+ *             [0..23] board (+ PLAYER1 / - PLAYER2, index = point-1),
+ *             [24] jailed P1, [25] jailed P2, [26] borne-off P1, [27] borne-off P2.
+ * RECORD    = the 32-byte int8 form every batched call uses:
+ *             bytes 0..27 the position, byte 28 player to move (0/1), byte 29 die 1,
+ *             byte 30 die 2, byte 31 reserved (0).  Arrays of records are 32-byte strided,
+ *             so one warp reads/writes a record as one 32-byte sector.
+ * MOVES     = a turn sequence: up to 4 (origin, dest) int8 pairs, origin/dest coded as the
+ *             reference does (0 = P1 bar / P2 off, 1..24 points, 25 = P2 bar / P1 off).
+ * WEIGHTS   = the reference state_dict tensors (model.py:36-37), fp32, row-major:
+ *             W1[128][198] fc1.weight, b1[128] fc1.bias, w2[128] fc2.weight, b2[1] fc2.bias.
+ *
+ * The batched entry points run on the GPU only.  There is no CPU fallback: without a
+ * CUDA device bgx_create fails with BGX_E_NO_DEVICE and nothing batched can be called.
+ * The single-position functions (section 1) are host code; they back the per-object
+ * compat API (Game.legalMoves, Game.tryMove ...) whose cost is Python-call bound.
+ */
+#ifndef BGX_H
+#define BGX_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGX_STATE_INTS 28
+#define BGX_RECORD_BYTES 32
+#define BGX_FEATURES 198
+#define BGX_HIDDEN 128
+#define BGX_NPARAMS 25601          /* 198*128 + 128 + 128 + 1 */
+#define BGX_NPARAMS_PADDED 25604   /* 16-byte multiple: the allreduce message */
+
+enum {
+    BGX_OK = 0,
+    BGX_E_INVALID = -1,      /* bad argument */
+    BGX_E_NO_DEVICE = -2,    /* no CUDA device / driver: the batched path cannot run */
+    BGX_E_CUDA = -3,         /* a CUDA call failed; see bgx_last_error() */
+    BGX_E_CAPACITY = -4,     /* caller buffer too small; *needed is filled */
+    BGX_E_STATE = -5         /* call order (e.g. selfplay step before init, weights unset) */
+};
+
+/* tryMove outcome codes; bgx_move_error_string() gives the reference's exact text
+ * (cppsrc/game.cpp:585-642). */
+enum {
+    BGX_MOVE_OK = 0,
+    BGX_MOVE_INVALID_ORIGIN = 1,
+    BGX_MOVE_ORIGIN_RANGE = 2,
+    BGX_MOVE_DEST_RANGE = 3,
+    BGX_MOVE_DIRECTION = 4,
+    BGX_MOVE_DICE = 5,
+    BGX_MOVE_INVALID_DEST = 6,
+    BGX_MOVE_BEAR_FROM_JAIL = 7
+};
+
+const char *bgx_last_error(void);
+int bgx_abi_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * 1. Single-position host functions (compat Game object)
+ * ---------------------------------------------------------------------------------- */
+
+/* replaces Game::legalMoves(player, die)                      cppsrc/game.cpp:80-105
+ * out_pairs[2*i], out_pairs[2*i+1] = origin, dest; at most 26 pairs. */
+int bgx_legal_moves(const int32_t *position, int player, int die, int8_t *out_pairs, int cap, int *n);
+
+/* replaces Game::tryMove(player*, dice, origin, dest, err)     cppsrc/game.cpp:573-663
+ * position is updated in place on success; *move_code gets a BGX_MOVE_* value. */
+int bgx_try_move(int32_t *position, int player, int dice, int origin, int dest, int *move_code);
+const char *bgx_move_error_string(int move_code);
+
+/* replaces Game::over(&winner) / is_game_over                  cppsrc/game.cpp:388-407,
+ *                                                              backgammon_bindings.cpp:11-16
+ * *winner = -1 while the game is running. */
+int bgx_game_over(const int32_t *position, int *winner);
+
+/* replaces Game::legalTurnSequences + Game::evaluateTurnSequences
+ *                                                              cppsrc/game.cpp:134-222
+ * seq_moves[cap][4][2], seq_len[cap], states[cap][28] (any may be NULL); reference order,
+ * duplicates kept.  *n = number of sequences; BGX_E_CAPACITY if n > cap. */
+int bgx_turn_sequences(const int32_t *position, int player, int d1, int d2, int64_t cap,
+                       int8_t *seq_moves, int8_t *seq_len, int32_t *states, int64_t *n);
+
+/* ------------------------------------------------------------------------------------
+ * 2. Engine handle (one per device, not thread-safe)
+ * ---------------------------------------------------------------------------------- */
+typedef struct bgx_engine bgx_engine;
+
+int bgx_device_count(int *n);
+int bgx_create(int device, bgx_engine **out);
+int bgx_destroy(bgx_engine *e);
+/* all later launches of this engine go to `cuda_stream` (a cudaStream_t; NULL = default) */
+int bgx_set_stream(bgx_engine *e, void *cuda_stream);
+int bgx_synchronize(bgx_engine *e);
+
+/* replaces model.load_state_dict / state_dict()               model.py:36-37, train.py:513-515
+ * host pointers, WEIGHTS layout. */
+int bgx_set_weights(bgx_engine *e, const float *W1, const float *b1, const float *w2, const float *b2);
+int bgx_get_weights(bgx_engine *e, float *W1, float *b1, float *w2, float *b2);
+
+/* ------------------------------------------------------------------------------------
+ * 3. Batched position kernels.  `*_host` variants take HOST buffers and do the H2D/D2H
+ *    copies themselves (the end-to-end path); the plain variants take DEVICE pointers
+ *    and only enqueue work on the engine's stream.
+ * ---------------------------------------------------------------------------------- */
+
+/* Batched Game::evaluateTurnSequences, summary form            cppsrc/game.cpp:193-222
+ * per query: number of sequences N (reference count, duplicates included), number of
+ * distinct afterstates U (-1 if the exact-dedup table overflowed, never seen in practice),
+ * and the order-dependent 64-bit digest over every (sequence, afterstate) — DESIGN.md
+ * "enumeration digest" — that pins the ORDERED list bit-exactly without moving it. */
+int bgx_enumerate_summary(bgx_engine *e, const int8_t *queries, int64_t n_queries,
+                          int32_t *n_seq, int32_t *n_unique, uint64_t *digest);
+int bgx_enumerate_summary_host(bgx_engine *e, const int8_t *queries, int64_t n_queries,
+                               int32_t *n_seq, int32_t *n_unique, uint64_t *digest);
+
+/* Batched Game::evaluateTurnSequences, materialised            cppsrc/game.cpp:193-222,
+ *                                                              backgammon_bindings.cpp:27-39
+ * offsets[n_queries+1] = exclusive prefix sum of N (from a previous summary call);
+ * sequence k of query q lands at row offsets[q]+k: seq_moves[row][8], seq_len[row],
+ * states[row][32] (RECORD, byte 28 = mover). */
+int bgx_enumerate(bgx_engine *e, const int8_t *queries, int64_t n_queries, const int64_t *offsets,
+                  int8_t *seq_moves, int8_t *seq_len, int8_t *states);
+/* host convenience: runs summary + scan + enumerate; *total = sum N.  Output buffers hold
+ * `cap` rows; BGX_E_CAPACITY (with *total set) when more are needed. offsets may be NULL. */
+int bgx_enumerate_host(bgx_engine *e, const int8_t *queries, int64_t n_queries, int64_t cap,
+                       int64_t *offsets, int8_t *seq_moves, int8_t *seq_len, int8_t *states,
+                       int64_t *total);
+
+/* replaces TDLGammonModel._encode_states_np(states, turn)      model.py:111-144
+ * records[n][32] (byte 28 = the `turn` flag) -> X[n][198] fp32, bit-exact. */
+int bgx_encode(bgx_engine *e, const int8_t *records, int64_t n, float *X);
+int bgx_encode_host(bgx_engine *e, const int8_t *records, int64_t n, float *X);
+
+/* replaces TDLGammonModel.forward(_encode_states_np(states, turn))   model.py:63-67
+ * V[n] fp32; features are generated in-kernel, X never touches HBM. */
+int bgx_evaluate(bgx_engine *e, const int8_t *records, int64_t n, float *V);
+int bgx_evaluate_host(bgx_engine *e, const int8_t *records, int64_t n, float *V);
+
+/* Batched TDLGammonModel.make_move(game, epsilon)              model.py:180-222
+ * per query: enumerate, score every distinct afterstate with the mover's flag, take
+ * argmax (P1) / argmin (P2) with the reference's first-index tie-break, or — with
+ * probability epsilon — a uniformly random SEQUENCE (duplicates weighted like
+ * random.randrange(len(actions)), model.py:205-206; draws come from Philox keyed by
+ * (seed, query index)).  Outputs (any may be NULL):
+ *   chosen[n][32]   afterstate RECORD; byte 28 = mover, byte 31 = 1 if a sequence was played
+ *                   (0: no legal sequence, or the single empty sequence of a blocked double)
+ *   moves[n][8], moves_len[n]   the chosen sequence
+ *   value[n]        V of the chosen afterstate (NaN when nothing was scored)
+ *   n_seq[n], n_scored[n]       sequences enumerated / afterstates actually scored */
+int bgx_select_moves(bgx_engine *e, const int8_t *queries, int64_t n, float epsilon, uint64_t seed,
+                     int8_t *chosen, int8_t *moves, int8_t *moves_len, float *value,
+                     int32_t *n_seq, int32_t *n_scored);
+int bgx_select_moves_host(bgx_engine *e, const int8_t *queries, int64_t n, float epsilon, uint64_t seed,
+                          int8_t *chosen, int8_t *moves, int8_t *moves_len, float *value,
+                          int32_t *n_seq, int32_t *n_scored);
+
+/* ------------------------------------------------------------------------------------
+ * 4. Self-play population (replaces play_game, train.py:64-121, for many games at once)
+ * ---------------------------------------------------------------------------------- */
+typedef struct bgx_stats {
+    int64_t plies;            /* plies played in this call (no-move plies included, train.py:103-121) */
+    int64_t sequences;        /* legal turn sequences enumerated (reference-equivalent count) */
+    int64_t scored;           /* afterstates scored by the MLP */
+    int64_t games_finished;
+    int64_t p1_wins;
+    int64_t truncated;        /* games that hit traj_cap before ending */
+    int64_t td_steps;         /* TD(lambda) steps replayed (bgx_td_replay) */
+    double td_sq_error;       /* sum of td_error^2 over the non-terminal steps (train.py:162) */
+} bgx_stats;
+
+/* first-mover rule */
+#define BGX_FIRST_ROLLOFF 0   /* play_game's roll-off by dice sums, train.py:89-97 */
+#define BGX_FIRST_PARITY 1    /* game id % 2, benchmark.py:74 / train.py:265 */
+
+/* n_slots concurrent games.  Slot s plays global game ids first_id + s, then
+ * + id_stride, + 2*id_stride ... (id_stride = global population, so sharding the slots
+ * over ranks does not change any game).  Dice of ply p of game g are Philox4x32-10 with
+ * key = seed and counter = (p, g_lo, g_hi, 0): d1 = 1 + ((x0*6)>>32), d2 likewise from x1
+ * (replayable into the reference through Game.setDice, backgammon_bindings.cpp:86).
+ * traj_cap > 0 records every pre-move RECORD (train.py:105-106) for bgx_td_replay. */
+int bgx_selfplay_init(bgx_engine *e, int64_t n_slots, int64_t first_id, int64_t id_stride,
+                      uint64_t seed, int first_mover, int32_t traj_cap);
+/* every slot advances by n_plies plies; finished games restart in place with the next id */
+int bgx_selfplay_step(bgx_engine *e, int32_t n_plies, float epsilon, bgx_stats *out);
+/* every slot plays its current game to the end (or traj_cap), no restart: one "round" of
+ * self-play from one weight snapshot (train.py:527-537) */
+int bgx_selfplay_round(bgx_engine *e, float epsilon, bgx_stats *out);
+/* start the next round: every slot gets its next game id and the opening position */
+int bgx_selfplay_next_round(bgx_engine *e);
+
+/* host copies of slot state: records[n_slots][32] (byte 28 = player to move, byte 31 =
+ * 0 running / 1 PLAYER1 won / 2 PLAYER2 won), ply[n_slots], game_id[n_slots] */
+int bgx_selfplay_read(bgx_engine *e, int8_t *records, int32_t *ply, int64_t *game_id);
+/* trajectory of one slot's current game: pre[T][32] pre-move RECORDs with the dice rolled
+ * (bytes 29,30), chosen[T][32] afterstates (byte 31 = sequence played flag); *T plies. */
+int bgx_export_trajectory(bgx_engine *e, int64_t slot, int32_t cap, int8_t *pre, int8_t *chosen, int32_t *T);
+
+/* ------------------------------------------------------------------------------------
+ * 5. TD(lambda)  (replaces apply_td_updates, train.py:124-172)
+ * ---------------------------------------------------------------------------------- */
+
+/* Exact online TD(lambda) replay of every finished slot trajectory, each from the engine's
+ * current weights (the round snapshot) with zeroed traces; the per-game weight changes are
+ * SUMMED into delta[BGX_NPARAMS_PADDED] (device fp32, WEIGHTS order flattened: W1,b1,w2,b2;
+ * overwritten, not accumulated).  Weights are not modified. */
+int bgx_td_replay(bgx_engine *e, float lr, float lambda, float *delta_dev, bgx_stats *out);
+/* weights += scale * delta   (after the caller's allreduce over ranks) */
+int bgx_apply_delta(bgx_engine *e, const float *delta_dev, float scale);
+/* one external trajectory (host buffers): records[T][32] with byte 28 = the turn flag of each
+ * pre-move state; new_* receive the weights after the replay; sq_errors[T-1] may be NULL */
+int bgx_td_replay_host(bgx_engine *e, const int8_t *records, int32_t T, int player1_won,
+                       float lr, float lambda,
+                       float *new_W1, float *new_b1, float *new_w2, float *new_b2, double *sq_errors);
+
+/* ------------------------------------------------------------------------------------
+ * 6. Introspection for benchmarks
+ * ---------------------------------------------------------------------------------- */
+/* kernels launched by this engine since creation (bench.py's gpu_launches) */
+int bgx_launch_count(bgx_engine *e, int64_t *n);
+/* CUDA-event duration (ms) of the last self-play / select / enumerate kernel launch */
+int bgx_last_kernel_ms(bgx_engine *e, float *ms);
+int bgx_device_props(bgx_engine *e, int *sm_count, int *clock_khz, int64_t *global_mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGX_H */

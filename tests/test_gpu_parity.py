@@ -1,0 +1,384 @@
+"""GPU parity tests: every batched C-ABI entry point of libbgx against the reference's golden
+vectors and the CPU oracle on the same seeded inputs.  Integer results (move sets, order,
+boards, bar/off counts, winners, encodings) must be bit-exact; values and TD updates must be
+within 1e-5 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import golden_weights
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x5EED2026
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from bgx.engine import BatchEngine
+    e = BatchEngine(0)
+    yield e
+    e.close()
+
+
+def records_from(states, player, dice=None):
+    st = np.asarray(states)
+    r = np.zeros((st.shape[0], 32), np.int8)
+    r[:, :28] = st[:, :28]
+    r[:, 28] = player
+    if dice is not None:
+        r[:, 29:31] = dice
+    return r
+
+
+# ------------------------------------------------------------------ enumeration (bit-exact)
+
+def test_enumerate_summary_golden(eng, golden):
+    g = golden("enum_summary.npz")
+    n, u, d = eng.enumerate_summary_host(g["queries"])
+    assert np.array_equal(n, g["n_seq"])
+    assert np.array_equal(u, g["n_unique"])
+    assert np.array_equal(d, g["digest"])
+
+
+def test_enumerate_full_golden(eng, golden):
+    g = golden("enum_full.npz")
+    offsets, mv, ln, st = eng.enumerate_host(g["queries"])
+    assert np.array_equal(offsets, g["offsets"])
+    assert np.array_equal(mv.reshape(-1, 8), g["moves"])
+    assert np.array_equal(ln, g["lens"])
+    assert np.array_equal(st[:, :28], g["states"])
+    mover = np.repeat(g["queries"][:, 28], np.diff(g["offsets"]))
+    assert np.array_equal(st[:, 28], mover)
+
+
+def test_enumerate_edge_cases(eng, orc):
+    from bgx.synth import start_record
+    # empty batch
+    n, u, d = eng.enumerate_summary_host(np.zeros((0, 32), np.int8))
+    assert len(n) == 0
+    offsets, mv, ln, st = eng.enumerate_host(np.zeros((0, 32), np.int8))
+    assert offsets.tolist() == [0] and len(ln) == 0
+    # blocked: non-double -> 0 sequences; double -> one empty sequence (quirk Q5)
+    blocked = np.zeros((2, 32), np.int8)
+    blocked[:, :6] = -2
+    blocked[:, 24] = 1
+    blocked[:, 26] = 14
+    blocked[:, 27] = 3
+    blocked[0, 29:31] = (3, 4)
+    blocked[1, 29:31] = (3, 3)
+    n, u, d = eng.enumerate_summary_host(blocked)
+    assert n.tolist() == [0, 1] and u.tolist() == [0, 1]
+    offsets, mv, ln, st = eng.enumerate_host(blocked)
+    assert offsets.tolist() == [0, 0, 1] and ln.tolist() == [0]
+    assert np.array_equal(st[0, :28], blocked[1, :28])
+    # the heaviest opening roll (2-2: 538 sequences) and a single ragged batch of 3
+    q = np.stack([start_record(0, 2, 2), start_record(1, 6, 5), start_record(0, 3, 3)])
+    n, u, d = eng.enumerate_summary_host(q)
+    assert n.tolist() == [538, 14, 536] and u.tolist() == [75, 7, 73]
+
+
+def test_enumerate_vs_oracle_fresh_seed(eng, orc):
+    from bgx.synth import make_queries
+    q, _ = make_queries(30000, seed=424242)
+    n, u, d = eng.enumerate_summary_host(q)
+    for i in range(0, len(q), 7):                      # every 7th query: ~4.3k oracle enumerations
+        r = q[i]
+        assert orc.turn_summary(r[:28].astype(np.int32), r[28], r[29], r[30]) == (int(n[i]), int(u[i]), int(d[i])), i
+    # ordered lists for a slice, against the oracle
+    sub = q[:600]
+    offsets, mv, ln, st = eng.enumerate_host(sub)
+    for i, r in enumerate(sub):
+        omv, oln, ost = orc.turn_sequences(r[:28].astype(np.int32), r[28], r[29], r[30])
+        a, b = offsets[i], offsets[i + 1]
+        assert np.array_equal(mv[a:b], omv) and np.array_equal(ln[a:b], oln)
+        assert np.array_equal(st[a:b, :28], ost.astype(np.int8))
+
+
+def test_enumerate_million_position_properties(eng):
+    """BASELINE configs[1] at full size: 10^6 seeded positions.  Size-independent properties:
+    swapping the dice permutes the sequence list (same N, same U, different order => different
+    digest unless N <= 1), doubles never emit more than 4 moves, and the run is deterministic."""
+    from bgx.synth import make_queries
+    q, _ = make_queries(1_000_000, seed=20260101)
+    n, u, d = eng.enumerate_summary_host(q)
+    sw = q.copy()
+    sw[:, 29], sw[:, 30] = q[:, 30], q[:, 29]
+    n2, u2, d2 = eng.enumerate_summary_host(sw)
+    assert np.array_equal(n, n2) and np.array_equal(u, u2)
+    dbl = q[:, 29] == q[:, 30]
+    assert np.array_equal(d[dbl], d2[dbl])
+    assert (u >= 0).all() and (u <= n).all() and ((n == 0) == (u == 0)).all()
+    n3, u3, d3 = eng.enumerate_summary_host(q)
+    assert np.array_equal(n, n3) and np.array_equal(u, u3) and np.array_equal(d, d3)
+    assert int(n.sum()) > 30_000_000
+
+
+# ------------------------------------------------------------------ encoding (bit-exact) and values
+
+def test_encode_golden_bit_exact(eng, golden):
+    g = golden("model.npz")
+    X = eng.encode_host(records_from(g["states"], g["turn"]))
+    assert np.array_equal(X.view(np.uint32), g["X"].view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 1000, 65537])
+def test_encode_ragged_sizes_vs_oracle(eng, orc, n):
+    from bgx.synth import make_queries
+    q, _ = make_queries(n, seed=n)
+    X = eng.encode_host(q)
+    for t in (0, 1):
+        sel = q[:, 28] == t
+        if sel.any():
+            ref = orc.encode(q[sel, :28].astype(np.int32), t)
+            assert np.array_equal(X[sel].view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("tag", ["rand", "trained"])
+def test_values_golden(eng, golden, tag):
+    g = golden("model.npz")
+    eng.set_weights(*golden_weights(g, tag))
+    V = eng.evaluate_host(records_from(g["states"], g["turn"]))
+    ref = g[f"v_{tag}"]
+    assert np.max(np.abs(V - ref) / np.abs(ref)) <= 1e-5
+    got = eng.get_weights()
+    for a, b in zip(got, golden_weights(g, tag)):
+        assert np.array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1))
+
+
+# ------------------------------------------------------------------ batched make_move
+
+def check_choice(orc, w, rec, chosen, value=None, n_seq=None):
+    """The engine's pick for one query is the oracle's, or differs only inside the 1e-5 value tolerance.
+    Returns 1 for such a near-tie, 0 for an identical pick."""
+    s = rec[:28].astype(np.int32)
+    pl = int(rec[28])
+    idx, after, v, n = orc.greedy_ply(w, s, pl, rec[29], rec[30])
+    if n_seq is not None:
+        assert n == n_seq
+    got = chosen[:28].astype(np.int32)
+    if idx < 0:
+        assert np.array_equal(got, s) and chosen[31] == 0
+        return 0
+    assert chosen[28] == pl
+    vg = v if np.array_equal(got, after) else orc.forward(w, orc.encode(got[None], pl))[0]
+    if value is not None:
+        assert abs(value - vg) <= 1e-5 * abs(vg)          # the reported value is the oracle's for that afterstate
+    if np.array_equal(got, after):
+        return 0
+    assert abs(vg - v) <= 1e-5 * abs(v), "different afterstate outside the value tolerance"
+    return 1
+
+
+@pytest.mark.parametrize("tag", ["rand", "trained"])
+def test_select_moves_vs_oracle(eng, orc, golden, tag):
+    from bgx.synth import make_queries
+    w = golden_weights(golden("model.npz"), tag)
+    eng.set_weights(*w)
+    q, _ = make_queries(3000, seed=31337)
+    out = eng.select_moves_host(q)
+    soft = 0
+    for i, r in enumerate(q):
+        soft += check_choice(orc, w, r, out["chosen"][i], out["value"][i], int(out["n_seq"][i]))
+        # the reported sequence really leads to the reported afterstate
+        s = r[:28].astype(np.int32)
+        for j in range(out["moves_len"][i]):
+            o, d = (int(x) for x in out["moves"][i, j])
+            ok, _, s = orc.try_move(s, int(r[28]), abs(o - d), o, d)
+            assert ok
+        assert np.array_equal(s, out["chosen"][i, :28].astype(np.int32))
+        assert 0 <= out["n_scored"][i] <= max(out["n_seq"][i], 0)
+    assert soft <= (300 if tag == "rand" else 30), soft     # near-ties: ~10 % with random-init weights
+
+
+def test_select_moves_golden_games(eng, orc, golden):
+    """The reference's own greedy games (model.make_move on the reference engine), ply by ply."""
+    g = golden("games.npz")
+    gm = golden("model.npz")
+    for name in g["names"]:
+        name = str(name)
+        tag = "rand" if name.startswith("rand") else "trained"
+        w = golden_weights(gm, tag)
+        eng.set_weights(*w)
+        q = records_from(g[f"{name}.pre"], g[f"{name}.player"], g[f"{name}.dice"])
+        out = eng.select_moves_host(q)
+        assert np.array_equal(out["n_seq"], g[f"{name}.nseq"].astype(np.int32))
+        same = (out["chosen"][:, :28] == g[f"{name}.after"]).all(1)
+        for t in np.nonzero(~same)[0]:
+            check_choice(orc, w, q[t], out["chosen"][t], out["value"][t], int(out["n_seq"][t]))
+        exact_moves = (out["moves"].reshape(-1, 8) == g[f"{name}.chosen"].reshape(-1, 8)).all(1) & \
+                      (out["moves_len"] == g[f"{name}.chosen_len"])
+        assert exact_moves[same].mean() > 0.85        # same afterstate, usually the same first-index sequence
+        assert same.mean() > (0.8 if tag == "rand" else 0.97), (name, same.mean())
+
+
+def test_select_moves_epsilon_one_is_uniform_over_sequences(eng, orc, golden):
+    """epsilon = 1: sequence floor(x1 * N / 2^32) of Philox(seed; 0, q, 0, 2), duplicates weighted (model.py:205-206)."""
+    from bgx.synth import make_queries
+    eng.set_weights(*golden_weights(golden("model.npz"), "rand"))
+    q, _ = make_queries(800, seed=5)
+    out = eng.select_moves_host(q, epsilon=1.0, seed=1234567)
+    for i, r in enumerate(q):
+        mv, ln, st = orc.turn_sequences(r[:28].astype(np.int32), r[28], r[29], r[30])
+        assert out["n_seq"][i] == len(ln)
+        if len(ln) == 0:
+            continue
+        x = orc.philox(1234567, 0, i, 0, 2)
+        k = (x[1] * len(ln)) >> 32
+        assert np.array_equal(out["chosen"][i, :28], st[k].astype(np.int8))
+        assert out["moves_len"][i] == ln[k] and np.array_equal(out["moves"][i], mv[k])
+
+
+# ------------------------------------------------------------------ self-play population
+
+def verify_trajectory(orc, w, pre, cho, gid, first_rule_rolloff=True):
+    """Step the oracle through an exported GPU trajectory (dice spec, legality, choice, turn order)."""
+    T = len(pre)
+    assert T > 0
+    soft = 0
+    if first_rule_rolloff:
+        k = 0
+        while True:
+            x = orc.philox(SEED, k, gid, 0, 1)
+            s1, s2 = orc.die(x[0]) + orc.die(x[1]), orc.die(x[2]) + orc.die(x[3])
+            if s1 != s2:
+                break
+            k += 1
+        assert pre[0, 28] == (0 if s1 > s2 else 1)
+    from bgx.synth import START_BOARD
+    assert np.array_equal(pre[0, :24], START_BOARD) and not pre[0, 24:28].any()
+    for t in range(T):
+        x = orc.philox(SEED, t, gid, 0, 0)
+        assert (orc.die(x[0]), orc.die(x[1])) == (int(pre[t, 29]), int(pre[t, 30])), (gid, t)
+        soft += check_choice(orc, w, pre[t], cho[t])
+        if t + 1 < T:
+            assert np.array_equal(pre[t + 1, :28], cho[t, :28]), (gid, t)     # next pre-move state = chosen afterstate
+            assert pre[t + 1, 28] == 1 - pre[t, 28]                           # train.py:119-120
+            assert orc.game_over(cho[t, :28].astype(np.int32)) == -1
+    return soft
+
+
+@pytest.mark.parametrize("tag", ["trained", "rand"])
+def test_selfplay_round_trajectories(eng, orc, golden, tag):
+    w = golden_weights(golden("model.npz"), tag)
+    eng.set_weights(*w)
+    n = 48
+    eng.selfplay_init(n, first_id=1000, id_stride=n, seed=SEED, traj_cap=2048)
+    st = eng.selfplay_round()
+    rec, ply, gid = eng.selfplay_read()
+    assert st["games_finished"] == n and st["truncated"] == 0
+    assert st["plies"] == int(ply.sum())
+    assert np.array_equal(gid, 1000 + np.arange(n))
+    assert st["p1_wins"] == int((rec[:, 31] == 1).sum())
+    for slot in range(0, n, 6):
+        pre, cho = eng.export_trajectory(slot)
+        assert len(pre) == ply[slot]
+        verify_trajectory(orc, w, pre, cho, int(gid[slot]))
+        winner = orc.game_over(cho[-1, :28].astype(np.int32))
+        assert winner == int(rec[slot, 31]) - 1
+        assert np.array_equal(rec[slot, :28], cho[-1, :28])
+    # a second round continues with the next ids
+    eng.selfplay_next_round()
+    rec2, ply2, gid2 = eng.selfplay_read()
+    assert np.array_equal(gid2, gid + n) and not ply2.any() and not rec2[:, 31].any()
+
+
+def test_selfplay_golden_game_ids(eng, golden):
+    """Same seed and game ids as the reference-played golden games: identical trajectories
+    (trained weights: the value gaps are far above fp32 noise)."""
+    g = golden("games.npz")
+    eng.set_weights(*golden_weights(golden("model.npz"), "trained"))
+    eng.selfplay_init(3, first_id=5, id_stride=3, seed=int(g["seed"]), traj_cap=1024)
+    eng.selfplay_round()
+    rec, ply, gid = eng.selfplay_read()
+    for slot, name in enumerate(("trained5", "trained6", "trained7")):
+        pre, cho = eng.export_trajectory(slot)
+        gp = g[f"{name}.pre"]
+        same = min(len(pre), len(gp))
+        agree = (pre[:same, :29] == np.concatenate([gp, g[f"{name}.player"][:, None]], 1)[:same]).all(1)
+        first_diff = same if agree.all() else int(np.argmin(agree))
+        assert first_diff >= same - 1 or first_diff > 20, (name, first_diff)
+        if agree.all() and len(pre) == len(gp):
+            assert int(rec[slot, 31]) - 1 == int(g[f"{name}.winner"])
+            assert np.array_equal(pre[:, 29:31], g[f"{name}.dice"])
+
+
+def test_selfplay_step_restarts_and_rank_invariance(eng, golden):
+    """Slots sharded over 'ranks' play the same games as one big population (ids = first_id + slot, stride = global)."""
+    eng.set_weights(*golden_weights(golden("model.npz"), "trained"))
+    G = 64
+    eng.selfplay_init(G, first_id=0, id_stride=G, seed=SEED, first_mover=1)
+    tot = {"plies": 0, "games_finished": 0}
+    for _ in range(4):
+        st = eng.selfplay_step(40)
+        assert st["plies"] == G * 40
+        for k in tot:
+            tot[k] += st[k]
+    full = eng.selfplay_read()
+    assert tot["games_finished"] > 0 and (full[2] >= G).any()              # somebody restarted in place
+    halves = []
+    for r in range(2):
+        eng.selfplay_init(G // 2, first_id=r * G // 2, id_stride=G, seed=SEED, first_mover=1)
+        for _ in range(4):
+            eng.selfplay_step(40)
+        halves.append(eng.selfplay_read())
+    for k in range(3):
+        assert np.array_equal(full[k], np.concatenate([h[k] for h in halves]))
+
+
+# ------------------------------------------------------------------ TD(lambda)
+
+def td_tol(dref, wref):
+    return 1e-5 * np.max(np.abs(dref)) + np.spacing(np.float32(np.max(np.abs(wref))))
+
+
+def test_td_replay_host_golden(eng, golden):
+    """apply_td_updates (train.py:124-172) on the reference's own trajectories."""
+    g = golden("games.npz")
+    gm = golden("model.npz")
+    for name in g["names"]:
+        name = str(name)
+        w0 = golden_weights(gm, "rand" if name.startswith("rand") else "trained")
+        eng.set_weights(*w0)
+        rec = records_from(g[f"{name}.pre"], g[f"{name}.player"])
+        new, sq = eng.td_replay_host(rec, int(g[f"{name}.winner"]) == 0, float(g[f"{name}.lr"]), float(g[f"{name}.lam"]))
+        for a, b, k in zip(new, w0, ("W1", "b1", "w2", "b2")):
+            ref_new = g[f"{name}.new_{k}"].reshape(-1)
+            dref = ref_new - np.asarray(b).reshape(-1)
+            dgot = np.asarray(a).reshape(-1) - np.asarray(b).reshape(-1)
+            assert np.max(np.abs(dgot - dref)) <= td_tol(dref, ref_new), (name, k)
+        assert np.max(np.abs(np.sqrt(sq) - np.sqrt(g[f"{name}.losses"]))) <= 1e-5, name
+
+
+@pytest.mark.parametrize("tag", ["trained", "rand"])
+def test_td_round_delta_is_sum_of_per_game_replays(eng, orc, golden, tag):
+    import torch
+    w0 = golden_weights(golden("model.npz"), tag)
+    eng.set_weights(*w0)
+    n = 12
+    eng.selfplay_init(n, first_id=77, id_stride=n, seed=SEED, traj_cap=2048)
+    eng.selfplay_round()
+    rec, ply, gid = eng.selfplay_read()
+    delta = torch.zeros(25604, device="cuda", dtype=torch.float32)
+    st = eng.td_replay(0.1, 0.9, delta)
+    torch.cuda.synchronize()
+    assert st["td_steps"] == int(ply.sum()) and st["games_finished"] == n
+    got = delta.cpu().numpy()
+    flat0 = np.concatenate([np.asarray(a, np.float32).reshape(-1) for a in w0])
+    want = np.zeros(25601, np.float64)
+    sq_total = 0.0
+    for slot in range(n):
+        pre, _ = eng.export_trajectory(slot)
+        X = np.concatenate([orc.encode(pre[t:t + 1, :28].astype(np.int32), int(pre[t, 28])) for t in range(len(pre))])
+        new, sq = orc.td_replay(w0, X, rec[slot, 31] == 1, 0.1, 0.9)
+        want += np.concatenate([np.asarray(a, np.float32).reshape(-1) for a in new]).astype(np.float64) - flat0
+        sq_total += float(sq.sum())
+    for lo, hi, k in ((0, 25344, "W1"), (25344, 25472, "b1"), (25472, 25600, "w2"), (25600, 25601, "b2")):
+        tol = 1e-5 * np.max(np.abs(want[lo:hi])) + n * np.spacing(np.float32(np.max(np.abs(flat0[lo:hi]))))
+        assert np.max(np.abs(got[lo:hi] - want[lo:hi])) <= tol, k
+    assert not got[25601:].any()
+    assert abs(st["td_sq_error"] - sq_total) <= 1e-4 * max(sq_total, 1e-12) + 1e-9
+    # weights unchanged by the replay; apply_delta adds scale * delta
+    assert np.array_equal(np.concatenate([np.asarray(a).reshape(-1) for a in eng.get_weights()]), flat0)
+    eng.apply_delta(delta, 0.5)
+    after = np.concatenate([np.asarray(a).reshape(-1) for a in eng.get_weights()])
+    assert np.allclose(after, flat0 + 0.5 * got[:25601], rtol=0, atol=1e-7 * np.max(np.abs(flat0)) + 1e-9)
