@@ -29,6 +29,7 @@ struct bgx_engine {
     unsigned long long *stats = nullptr;     // 8 counters
     double *dstats = nullptr;                // TD: sum of squared errors
     uint32_t *uniq_tables = nullptr;
+    uint32_t *uniq_gens = nullptr;           // per-warp generation of the exact-dedup tables
     int uniq_grid = 0;
     // self-play population
     long long n_slots = 0, first_id = 0, id_stride = 0;
@@ -147,7 +148,7 @@ int bgx_destroy(bgx_engine *e)
     cudaDeviceSynchronize();
     for (int i = 0; i < bgx_engine::kScratch; i++) cudaFree(e->dbuf[i]);
     cudaFree(e->flat); cudaFree(e->table); cudaFree(e->wt); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats);
-    cudaFree(e->uniq_tables); cudaFree(e->slots); cudaFree(e->traj_pre); cudaFree(e->traj_chosen);
+    cudaFree(e->uniq_tables); cudaFree(e->uniq_gens); cudaFree(e->slots); cudaFree(e->traj_pre); cudaFree(e->traj_chosen);
     cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     delete e;
@@ -218,6 +219,8 @@ static int ensure_uniq_tables(bgx_engine *e)
     const size_t bytes = (size_t)e->uniq_grid * kGameWarps * kUniqBytesPerWarp;
     CU(cudaMalloc(&e->uniq_tables, bytes));
     CU(cudaMemsetAsync(e->uniq_tables, 0, bytes, e->stream));
+    CU(cudaMalloc(&e->uniq_gens, (size_t)e->uniq_grid * kGameWarps * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(e->uniq_gens, 0, (size_t)e->uniq_grid * kGameWarps * sizeof(uint32_t), e->stream));
     return BGX_OK;
 }
 
@@ -231,7 +234,7 @@ int bgx_enumerate_summary(bgx_engine *e, const int8_t *queries, int64_t n, int32
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     tick(e);
     k_enumerate_summary<<<e->uniq_grid, kGameThreads, 0, e->stream>>>(queries, n, n_seq, n_unique,
-                                                                       (unsigned long long *)digest, e->uniq_tables, e->counter);
+                                                                       (unsigned long long *)digest, e->uniq_tables, e->uniq_gens, e->counter);
     tock(e);
     e->launches++;
     CU(cudaGetLastError());

@@ -88,12 +88,12 @@ struct SummaryLeaf {
 __global__ void __launch_bounds__(kGameThreads, 1)
 k_enumerate_summary(const int8_t *__restrict__ queries, long long n, int32_t *__restrict__ n_seq,
                     int32_t *__restrict__ n_unique, unsigned long long *__restrict__ digest,
-                    uint32_t *__restrict__ tables, unsigned long long *counter)
+                    uint32_t *__restrict__ tables, uint32_t *__restrict__ gens, unsigned long long *counter)
 {
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     uint32_t *table = tables + (size_t)gwarp * (kUniqBytesPerWarp / 4);
-    uint32_t gen = 0;
+    uint32_t gen = gens[gwarp];                     // the table outlives the launch, so does its generation
     for (;;) {
         const long long q = claim(counter, lane);
         if (q >= n) break;
@@ -115,6 +115,7 @@ k_enumerate_summary(const int8_t *__restrict__ queries, long long n, int32_t *__
             digest[q] = leaf.digest;
         }
     }
+    if (lane == 0) gens[gwarp] = gen;
 }
 
 // ---- batched evaluateTurnSequences, materialised (game.cpp:193-222, bindings:27-39) ----
