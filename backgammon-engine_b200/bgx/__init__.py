@@ -5,5 +5,12 @@
 `bgx.synth`   seeded synthetic positions for the enumeration sweep
 `bgx.model`   TDLGammonModel with the reference's contract (model.py:31-222) + GPU fast paths
 """
-from . import lib  # noqa: F401
-from .lib import BgxError, FIRST_PARITY, FIRST_ROLLOFF  # noqa: F401
+import os as _os
+import sys as _sys
+
+_LIBDIR = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "lib")
+if _LIBDIR not in _sys.path:
+    _sys.path.append(_LIBDIR)      # where the compat module backgammon_env*.so is built (appended: explicit paths win)
+
+from . import lib  # noqa: E402,F401
+from .lib import BgxError, FIRST_PARITY, FIRST_ROLLOFF  # noqa: E402,F401

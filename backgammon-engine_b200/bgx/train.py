@@ -1,0 +1,118 @@
+"""Self-play and TD(lambda) training: the reference's train.py entry points on the compat API,
+plus the population trainer that runs whole rounds on the GPU.
+
+`play_game` / `apply_td_updates` keep the reference's signatures and semantics
+(train.py:64-121, 124-172) so its sequential and pool trainers can import them from here.
+`GpuTrainer` replaces the multiprocessing pool + sequential replay (train.py:305-354, 527-547):
+one round = every game of the population played to its end from one weight snapshot
+(k_selfplay), every trajectory replayed with exact online TD(lambda) from that snapshot
+(k_td_replay), the per-game weight changes summed, all-reduced over the ranks (NCCL) and
+applied.  Combining per-game updates by (scaled) summation instead of applying them one after
+the other is the one deliberate divergence from the reference.
+"""
+import numpy as np
+import torch
+
+import backgammon_env as bg
+
+from . import lib as L
+from .parallel import allreduce_delta, shard
+
+
+def play_game(model, game_idx, epsilon=0.0):
+    """One self-play game on a compat Game. Returns (winner, states, total_moves) like train.py:64-121."""
+    model.eval()
+    game = bg.Game(0)
+    white = bg.Player("White", bg.PlayerType.PLAYER1)
+    black = bg.Player("Black", bg.PlayerType.PLAYER2)
+    game.setPlayers(white, black)
+    while True:                                       # opening roll-off by dice sums (train.py:89-97)
+        a, b = sum(game.roll_dice()), sum(game.roll_dice())
+        if a != b:
+            break
+    game.setTurn(bg.PlayerType.PLAYER1 if a > b else bg.PlayerType.PLAYER2)
+    states, total_moves = [], 0
+    while True:
+        states.append(model.encode_state_np(game))    # pre-move encoding with the mover's flag
+        game.roll_dice()
+        model.make_move(game, game_idx, epsilon=epsilon)
+        over, winner = game.is_game_over()
+        if over:
+            return winner, states, total_moves
+        game.setTurn(bg.PlayerType.PLAYER2 if game.getTurn() == bg.PlayerType.PLAYER1 else bg.PlayerType.PLAYER1)
+        total_moves += 1
+
+
+def apply_td_updates(model, optimizer, states, player1_won):
+    """Online TD(lambda) over one recorded game (train.py:124-172): traces reset by the caller,
+    weights and model.eligibility_traces updated in place, returns the squared TD errors."""
+    device = next(model.parameters()).device
+    sq_errors = []
+
+    def step(value, td_error):
+        optimizer.zero_grad()
+        value.backward()
+        with torch.no_grad():
+            for name, p in model.named_parameters():
+                if p.requires_grad and p.grad is not None:
+                    model.eligibility_traces[name] = model.lambda_decay * model.eligibility_traces[name] + p.grad.data
+                    p.add_(model.learning_rate * td_error * model.eligibility_traces[name])
+
+    tensors = [torch.from_numpy(s).to(device).unsqueeze(0) for s in states]
+    for t in range(len(tensors) - 1):
+        model.eval()
+        with torch.no_grad():
+            v_next = model(tensors[t + 1])
+        model.train()
+        v = model(tensors[t])
+        delta = (v_next - v).item()
+        step(v, delta)
+        sq_errors.append(delta ** 2)
+    if tensors:
+        model.train()
+        v = model(tensors[-1])
+        step(v, (1.0 if player1_won else 0.0) - v.item())
+    return sq_errors
+
+
+class GpuTrainer:
+    """Round-structured self-play TD(lambda) on one GPU per process (rank = torch.distributed rank).
+
+    games_per_rank concurrent games; game ids are global (rank * games_per_rank + slot, stride
+    world * games_per_rank) so a run is invariant to how the population is sharded."""
+
+    def __init__(self, model, games_per_rank, device=0, seed=0x5EED2026, traj_cap=2048,
+                 first_mover=L.FIRST_ROLLOFF, delta_scale=None):
+        import torch.distributed as dist
+        self.dist = dist if dist.is_available() and dist.is_initialized() else None
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.model = model
+        self.games_per_rank = int(games_per_rank)
+        self.global_games = self.games_per_rank * self.world
+        # default: the MEAN of the per-game updates (mini-batch TD); the reference applies them in sequence
+        self.delta_scale = (1.0 / self.global_games) if delta_scale is None else float(delta_scale)
+        self.eng = model.engine(device)
+        self.eng.set_stream(torch.cuda.current_stream().cuda_stream)
+        first_id, n_slots, stride = shard(self.global_games, self.rank, self.world)
+        self.eng.selfplay_init(n_slots, first_id=first_id, id_stride=stride, seed=seed, first_mover=first_mover, traj_cap=traj_cap)
+        self.delta = torch.zeros(L.NPARAMS_PADDED, dtype=torch.float32, device=torch.device("cuda", device))
+        self.games_done = 0
+        self.rounds = 0
+
+    def round(self, epsilon=0.0):
+        """Play, replay, reduce, apply.  Returns the round's statistics (this rank's counts)."""
+        if self.rounds:
+            self.eng.selfplay_next_round()
+        self.model.update_learning_params(self.games_done + 1)               # schedule of model.py:69-73
+        play = self.eng.selfplay_round(epsilon)
+        td = self.eng.td_replay(self.model.learning_rate, self.model.lambda_decay, self.delta)
+        allreduce_delta(self.delta, self.dist)                               # the only cross-GPU traffic: 102,416 B
+        self.eng.apply_delta(self.delta, self.delta_scale)
+        self.games_done += self.global_games
+        self.rounds += 1
+        return {**play, "td_steps": td["td_steps"], "td_sq_error": td["td_sq_error"], "games": self.global_games}
+
+    def sync_model(self):
+        self.model.load_engine_weights()
+        return self.model
