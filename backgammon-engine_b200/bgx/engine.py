@@ -160,9 +160,11 @@ class BatchEngine:
 
     # ------------------------------------------------------------------ self-play population
     def selfplay_init(self, n_slots, first_id=0, id_stride=None, seed=0x5EED2026, first_mover=L.FIRST_ROLLOFF,
-                      traj_cap=0):
+                      traj_cap=0, record_chosen=False):
         self.n_slots = int(n_slots)
         self.traj_cap = int(traj_cap)
+        self.record_chosen = bool(record_chosen)
+        L.check(self._lib.bgx_selfplay_record_chosen(self._h, int(self.record_chosen)))
         L.check(self._lib.bgx_selfplay_init(self._h, int(n_slots), int(first_id), int(id_stride or n_slots),
                                             int(seed), int(first_mover), int(traj_cap)))
 
@@ -190,10 +192,11 @@ class BatchEngine:
         """-> pre int8[T,32] (pre-move records incl. dice), chosen int8[T,32] (afterstates)"""
         cap = max(self.traj_cap, 1)
         pre = np.zeros((cap, 32), np.int8)
-        cho = np.zeros((cap, 32), np.int8)
+        cho = np.zeros((cap, 32), np.int8) if self.record_chosen else None
         T = C.c_int32()
-        L.check(self._lib.bgx_export_trajectory(self._h, int(slot), cap, pre.ctypes.data, cho.ctypes.data, C.byref(T)))
-        return pre[: T.value], cho[: T.value]
+        L.check(self._lib.bgx_export_trajectory(self._h, int(slot), cap, pre.ctypes.data,
+                                                cho.ctypes.data if cho is not None else None, C.byref(T)))
+        return pre[: T.value], (cho[: T.value] if cho is not None else None)
 
     # ------------------------------------------------------------------ TD(lambda)
     def td_replay(self, lr, lam, delta, want_stats=True):

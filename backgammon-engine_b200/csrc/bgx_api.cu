@@ -35,6 +35,7 @@ struct bgx_engine {
     long long n_slots = 0, first_id = 0, id_stride = 0;
     uint32_t seed_lo = 0, seed_hi = 0;
     int first_mover = 0, traj_cap = 0;
+    bool record_chosen = false;
     int8_t *slots = nullptr, *traj_pre = nullptr, *traj_chosen = nullptr;
     int32_t *ply = nullptr;
     long long *game_id = nullptr;
@@ -450,7 +451,7 @@ int bgx_selfplay_init(bgx_engine *e, int64_t n_slots, int64_t first_id, int64_t 
     CU(cudaMalloc(&e->game_id, (size_t)n_slots * 8));
     if (traj_cap > 0) {
         CU(cudaMalloc(&e->traj_pre, (size_t)n_slots * traj_cap * 32));
-        CU(cudaMalloc(&e->traj_chosen, (size_t)n_slots * traj_cap * 32));
+        if (e->record_chosen) CU(cudaMalloc(&e->traj_chosen, (size_t)n_slots * traj_cap * 32));
     }
     e->n_slots = n_slots; e->first_id = first_id; e->id_stride = id_stride;
     e->seed_lo = (uint32_t)seed; e->seed_hi = (uint32_t)(seed >> 32);
@@ -459,6 +460,13 @@ int bgx_selfplay_init(bgx_engine *e, int64_t n_slots, int64_t first_id, int64_t 
                                                             e->seed_lo, e->seed_hi, first_mover);
     e->launches++;
     CU(cudaGetLastError());
+    return BGX_OK;
+}
+
+int bgx_selfplay_record_chosen(bgx_engine *e, int on)
+{
+    if (!e) { set_error("bgx_selfplay_record_chosen: null"); return BGX_E_INVALID; }
+    e->record_chosen = on != 0;
     return BGX_OK;
 }
 
@@ -540,7 +548,10 @@ int bgx_export_trajectory(bgx_engine *e, int64_t slot, int32_t cap, int8_t *pre,
     if (ply > cap) { set_error("bgx_export_trajectory: %d plies, cap %d", ply, cap); return BGX_E_CAPACITY; }
     if (ply == 0) return BGX_OK;
     if (pre) CU(cudaMemcpyAsync(pre, e->traj_pre + (size_t)slot * e->traj_cap * 32, (size_t)ply * 32, cudaMemcpyDeviceToHost, e->stream));
-    if (chosen) CU(cudaMemcpyAsync(chosen, e->traj_chosen + (size_t)slot * e->traj_cap * 32, (size_t)ply * 32, cudaMemcpyDeviceToHost, e->stream));
+    if (chosen) {
+        if (!e->traj_chosen) { set_error("bgx_export_trajectory: chosen afterstates were not recorded (bgx_selfplay_record_chosen)"); return BGX_E_STATE; }
+        CU(cudaMemcpyAsync(chosen, e->traj_chosen + (size_t)slot * e->traj_cap * 32, (size_t)ply * 32, cudaMemcpyDeviceToHost, e->stream));
+    }
     CU(cudaStreamSynchronize(e->stream));
     return BGX_OK;
 }

@@ -258,8 +258,43 @@ def run_ours(args):
     sampler.stop_flag.set()
     sampler.join(timeout=3)
 
+    # ---- one TD(lambda) round (BASELINE configs[3]/[4]): play to the end, replay, all-reduce, apply
+    td = None
+    if args.td_games > 0:
+        from bgx.lib import FIRST_ROLLOFF
+        from bgx.parallel import allreduce_delta, shard
+        first, n_slots, stride = shard(args.td_games * world, rank, world)
+        eng.selfplay_init(n_slots, first_id=first, id_stride=stride, seed=SEED + 1, first_mover=FIRST_ROLLOFF, traj_cap=2048)
+        delta = torch.zeros(25604, dtype=torch.float32, device=dev)
+        barrier()
+        e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        e0.record(stream)
+        play = eng.selfplay_round(0.0)
+        e1.record(stream)
+        tdst = eng.td_replay(0.1, 0.9, delta)
+        e2.record(stream)
+        allreduce_delta(delta, dist if world > 1 else None)
+        eng.apply_delta(delta, 1.0 / (args.td_games * world))
+        e3.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), e0.elapsed_time(e3)], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([play["plies"], tdst["td_steps"], play["games_finished"], play["truncated"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        ms, cnt = ms.tolist(), cnt.tolist()
+        td = {"games": int(args.td_games * world), "plies": int(cnt[0]), "td_steps": int(cnt[1]), "games_finished": int(cnt[2]),
+              "truncated": int(cnt[3]), "play_ms": ms[0], "td_replay_ms": ms[1], "allreduce_apply_ms": ms[2], "round_ms": ms[3],
+              "plies_per_sec_incl_update": cnt[0] / (ms[3] * 1e-3), "td_steps_per_sec": cnt[1] / (ms[1] * 1e-3),
+              "note": "one round: every game played to its end from one snapshot (k_selfplay), exact online TD(lambda) replay "
+                      "per game (k_td_replay), NCCL all-reduce of fp32[25604], apply"}
+
     if rank == 0:
         peaks, peak_src = peak_json()
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_selfplay"]["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
         k_ms = float(np.mean(kernel_ms))
         seq_per_launch = seqs / args.steps
         scored_per_launch = scored / args.steps
@@ -278,7 +313,7 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "k_selfplay",
+                             "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "kernel": "k_selfplay",
                              "kernel_ms": k_ms, "peak_source": peak_src,
                              "note": "algorithmic bytes = sequences enumerated per launch x 1,696 B (the materialised "
                                      "dataflow of SURVEY 8d); the fused kernel keeps features on chip, so its DRAM traffic is far lower"},
@@ -286,6 +321,8 @@ def run_ours(args):
                                   "frac": fp32_ach / fp32_peak,
                                   "note": "afterstates actually scored x 50,944 dense-equivalent FLOP; the kernel skips zero features"},
                 "wall_s_timed_region": wall}
+        if td:
+            line["td_round"] = td
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
@@ -309,6 +346,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU sample length per reference step")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--td-games", type=int, default=65536, help="games per GPU in the TD(lambda) round leg (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

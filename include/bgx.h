@@ -193,6 +193,9 @@ typedef struct bgx_stats {
  * traj_cap > 0 records every pre-move RECORD (train.py:105-106) for bgx_td_replay. */
 int bgx_selfplay_init(bgx_engine *e, int64_t n_slots, int64_t first_id, int64_t id_stride,
                       uint64_t seed, int first_mover, int32_t traj_cap);
+/* also log the chosen afterstate of every ply (needed by bgx_export_trajectory's `chosen`;
+ * off by default: it doubles the trajectory memory).  Call before bgx_selfplay_init. */
+int bgx_selfplay_record_chosen(bgx_engine *e, int on);
 /* every slot advances by n_plies plies; finished games restart in place with the next id */
 int bgx_selfplay_step(bgx_engine *e, int32_t n_plies, float epsilon, bgx_stats *out);
 /* every slot plays its current game to the end (or traj_cap), no restart: one "round" of

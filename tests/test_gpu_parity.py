@@ -262,7 +262,7 @@ def test_selfplay_round_trajectories(eng, orc, golden, tag):
     w = golden_weights(golden("model.npz"), tag)
     eng.set_weights(*w)
     n = 48
-    eng.selfplay_init(n, first_id=1000, id_stride=n, seed=SEED, traj_cap=2048)
+    eng.selfplay_init(n, first_id=1000, id_stride=n, seed=SEED, traj_cap=2048, record_chosen=True)
     st = eng.selfplay_round()
     rec, ply, gid = eng.selfplay_read()
     assert st["games_finished"] == n and st["truncated"] == 0
@@ -287,7 +287,7 @@ def test_selfplay_golden_game_ids(eng, golden):
     (trained weights: the value gaps are far above fp32 noise)."""
     g = golden("games.npz")
     eng.set_weights(*golden_weights(golden("model.npz"), "trained"))
-    eng.selfplay_init(3, first_id=5, id_stride=3, seed=int(g["seed"]), traj_cap=1024)
+    eng.selfplay_init(3, first_id=5, id_stride=3, seed=int(g["seed"]), traj_cap=1024, record_chosen=True)
     eng.selfplay_round()
     rec, ply, gid = eng.selfplay_read()
     for slot, name in enumerate(("trained5", "trained6", "trained7")):
