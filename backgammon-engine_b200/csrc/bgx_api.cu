@@ -134,7 +134,7 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaMalloc(&e->dstats, 2 * sizeof(double)));
     CU(cudaEventCreate(&e->ev0));
     CU(cudaEventCreate(&e->ev1));
-    CU(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, kGameSmem));
+    CU(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, kEvalSmem));
     CU(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kGameSmem));
     CU(cudaFuncSetAttribute(k_selfplay, cudaFuncAttributeMaxDynamicSharedMemorySize, kGameSmem));
     CU(cudaFuncSetAttribute(k_td_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
@@ -361,7 +361,7 @@ int bgx_evaluate(bgx_engine *e, const int8_t *records, int64_t n, float *V)
     if (!e->have_weights) { set_error("bgx_evaluate: weights not set"); return BGX_E_STATE; }
     if (n == 0) return BGX_OK;
     tick(e);
-    k_evaluate<<<game_grid(e), kGameThreads, kGameSmem, e->stream>>>(records, n, V, e->table, e->flat);
+    k_evaluate<<<game_grid(e), kGameThreads, kEvalSmem, e->stream>>>(records, n, V, e->table, e->flat);
     tock(e);
     e->launches++;
     CU(cudaGetLastError());
@@ -397,7 +397,7 @@ int bgx_select_moves(bgx_engine *e, const int8_t *queries, int64_t n, float epsi
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     tick(e);
     k_select<<<game_grid(e), kGameThreads, kGameSmem, e->stream>>>(queries, n, epsilon, (uint32_t)seed, (uint32_t)(seed >> 32),
-                                                                    out, e->table, e->flat, e->counter);
+                                                                    out, e->wt, e->flat, e->counter);
     tock(e);
     e->launches++;
     CU(cudaGetLastError());
@@ -496,7 +496,7 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
     tick(e);
-    k_selfplay<<<game_grid(e), kGameThreads, kGameSmem, e->stream>>>(p, e->table, e->flat);
+    k_selfplay<<<game_grid(e), kGameThreads, kGameSmem, e->stream>>>(p, e->wt, e->flat);
     tock(e);
     e->launches++;
     CU(cudaGetLastError());

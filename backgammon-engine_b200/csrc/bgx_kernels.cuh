@@ -2,13 +2,15 @@
 // the execution model; DESIGN.md for the roofline of each kernel.
 #pragma once
 #include "bgx_device.cuh"
+#include "bgx_ply.cuh"
 
 namespace bgx {
 
 constexpr int kGameWarps = 16;                     // warps per CTA in the warp-per-position kernels
 constexpr int kGameThreads = kGameWarps * 32;
-// dynamic shared memory of the kernels that score positions: table + per-warp caches + barrier
-constexpr int kGameSmem = kTableBytes + kGameWarps * kCacheBytesPerWarp + 16;
+// dynamic shared memory of the fused ply kernels: weight table + per-warp scratch + barrier
+constexpr int kGameSmem = kTableBytes + kGameWarps * kPlyScratchBytes + 16;
+constexpr int kEvalSmem = kTableBytes + 16;            // k_evaluate: table + barrier
 
 // exact-dedup table of the summary kernel: per warp, in global memory (L2 resident)
 constexpr int kUniqSlots = 4096;                   // 8 words each, probed as buckets of 4 slots
@@ -229,7 +231,7 @@ k_evaluate(const int8_t *__restrict__ records, long long n, float *__restrict__ 
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float *sT = reinterpret_cast<float *>(smem);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kGameWarps * kCacheBytesPerWarp);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes);
     stage_table(sT, T, bar);
     const int lane = threadIdx.x & 31;
     Evaluator ev;
@@ -274,19 +276,20 @@ __device__ __forceinline__ void store_choice(const SelectOut &o, long long q, co
 
 __global__ void __launch_bounds__(kGameThreads, 1)
 k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_t seed_lo, uint32_t seed_hi,
-         SelectOut out, const float *__restrict__ T, const float *__restrict__ flat, unsigned long long *counter)
+         SelectOut out, const float *__restrict__ Wt, const float *__restrict__ flat, unsigned long long *counter)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float *sT = reinterpret_cast<float *>(smem);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kGameWarps * kCacheBytesPerWarp);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kGameWarps * kPlyScratchBytes);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SeenCache cache;
-    cache.slots = reinterpret_cast<uint32_t *>(smem + kTableBytes + warp * kCacheBytesPerWarp);
+    PlyScratch &S = *reinterpret_cast<PlyScratch *>(smem + kTableBytes + warp * kPlyScratchBytes);
+    PlyCache cache;
+    cache.slots = S.cache;
     cache.gen = 0;
-    for (int i = lane; i < kCacheSlots * kCacheWords; i += 32) cache.slots[i] = 0;
-    stage_table(sT, T, bar);
-    Evaluator ev;
-    ev.T4 = reinterpret_cast<const float4 *>(sT);
+    for (int i = lane; i < kPlySlots * kPlyEntryWords; i += 32) S.cache[i] = 0;
+    stage_table(sT, Wt, bar);
+    PlyEvaluator ev;
+    ev.W4 = reinterpret_cast<const float4 *>(sT);
     ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, lane);
     for (;;) {
         const long long q = claim(counter, lane);
@@ -301,7 +304,7 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
             explore = (float)r.x[0] * 2.3283064365386963e-10f < epsilon;
             u = r.x[1];
         }
-        const Choice c = choose_ply(root, lane, player, d1, d2, ev, cache, explore, u);
+        const Choice c = choose_ply_fast(root, lane, player, d1, d2, ev, S, cache, explore, u);
         store_choice(out, q, c, lane, player);
     }
 }
@@ -324,19 +327,20 @@ struct SelfplayParams {
 };
 
 __global__ void __launch_bounds__(kGameThreads, 1)
-k_selfplay(SelfplayParams p, const float *__restrict__ T, const float *__restrict__ flat)
+k_selfplay(SelfplayParams p, const float *__restrict__ Wt, const float *__restrict__ flat)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float *sT = reinterpret_cast<float *>(smem);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kGameWarps * kCacheBytesPerWarp);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kGameWarps * kPlyScratchBytes);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SeenCache cache;
-    cache.slots = reinterpret_cast<uint32_t *>(smem + kTableBytes + warp * kCacheBytesPerWarp);
+    PlyScratch &S = *reinterpret_cast<PlyScratch *>(smem + kTableBytes + warp * kPlyScratchBytes);
+    PlyCache cache;
+    cache.slots = S.cache;
     cache.gen = 0;
-    for (int i = lane; i < kCacheSlots * kCacheWords; i += 32) cache.slots[i] = 0;
-    stage_table(sT, T, bar);
-    Evaluator ev;
-    ev.T4 = reinterpret_cast<const float4 *>(sT);
+    for (int i = lane; i < kPlySlots * kPlyEntryWords; i += 32) S.cache[i] = 0;
+    stage_table(sT, Wt, bar);
+    PlyEvaluator ev;
+    ev.W4 = reinterpret_cast<const float4 *>(sT);
     ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, lane);
 
     unsigned long long s_plies = 0, s_seq = 0, s_scored = 0, s_fin = 0, s_p1 = 0, s_trunc = 0;
@@ -373,7 +377,7 @@ k_selfplay(SelfplayParams p, const float *__restrict__ T, const float *__restric
                 explore = (float)e.x[0] * 2.3283064365386963e-10f < p.epsilon;
                 u = e.x[1];
             }
-            const Choice c = choose_ply(v, lane, player, d1, d2, ev, cache, explore, u);   // model.py:180-222
+            const Choice c = choose_ply_fast(v, lane, player, d1, d2, ev, S, cache, explore, u);   // model.py:180-222
             v = c.v;
             s_plies++;
             s_seq += (unsigned long long)c.n_seq;
