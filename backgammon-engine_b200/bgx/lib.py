@@ -25,7 +25,7 @@ class BgxError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("plies", C.c_int64), ("sequences", C.c_int64), ("scored", C.c_int64),
                 ("games_finished", C.c_int64), ("p1_wins", C.c_int64), ("truncated", C.c_int64),
-                ("td_steps", C.c_int64), ("td_sq_error", C.c_double)]
+                ("td_steps", C.c_int64), ("td_sq_error", C.c_double), ("tree_edges", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

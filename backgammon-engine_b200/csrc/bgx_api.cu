@@ -6,6 +6,7 @@
 #include "bgx_kernels.cuh"
 #include "bgx_td.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -42,6 +43,7 @@ struct bgx_engine {
     // TD
     float *td_partial = nullptr;             // [td_grid][25604] per-CTA delta accumulators
     int td_grid = 0;
+    int ply_warps = 16;                      // warps per CTA of the fused ply kernels
     // bookkeeping
     long long launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -135,8 +137,20 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaEventCreate(&e->ev0));
     CU(cudaEventCreate(&e->ev1));
     CU(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, kEvalSmem));
-    CU(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kGameSmem));
-    CU(cudaFuncSetAttribute(k_selfplay, cudaFuncAttributeMaxDynamicSharedMemorySize, kGameSmem));
+    {
+        const char *w = getenv("BGX_PLY_WARPS");       // tuning knob: 16 (default), 24 or 32 warps per CTA
+        e->ply_warps = w ? atoi(w) : 16;
+        if (e->ply_warps != 16 && e->ply_warps != 24 && e->ply_warps != 32) { set_error("BGX_PLY_WARPS must be 16, 24 or 32"); delete e; return BGX_E_INVALID; }
+    }
+#define BGX_SMEM_ATTR(W, S)                                                                                                    \
+    CU(cudaFuncSetAttribute(k_select<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));            \
+    CU(cudaFuncSetAttribute(k_select<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));             \
+    CU(cudaFuncSetAttribute(k_selfplay<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));          \
+    CU(cudaFuncSetAttribute(k_selfplay<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));
+    BGX_SMEM_ATTR(16, 128)
+    BGX_SMEM_ATTR(24, 64)
+    BGX_SMEM_ATTR(32, 32)
+#undef BGX_SMEM_ATTR
     CU(cudaFuncSetAttribute(k_td_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
     *out = e;
     return BGX_OK;
@@ -396,8 +410,14 @@ int bgx_select_moves(bgx_engine *e, const int8_t *queries, int64_t n, float epsi
     SelectOut out = {chosen, moves, moves_len, value, n_seq, n_scored};
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     tick(e);
-    k_select<<<game_grid(e), kGameThreads, kGameSmem, e->stream>>>(queries, n, epsilon, (uint32_t)seed, (uint32_t)(seed >> 32),
-                                                                    out, e->wt, e->flat, e->counter);
+#define BGX_LAUNCH_SELECT(W, S, X)                                                                              \
+    k_select<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(queries, n, epsilon, (uint32_t)seed, \
+                                                                             (uint32_t)(seed >> 32), out, e->wt, e->flat, e->counter)
+    const bool ex = epsilon > 0.f;
+    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 128, true); else BGX_LAUNCH_SELECT(16, 128, false); }
+    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 64, true); else BGX_LAUNCH_SELECT(24, 64, false); }
+    else { if (ex) BGX_LAUNCH_SELECT(32, 32, true); else BGX_LAUNCH_SELECT(32, 32, false); }
+#undef BGX_LAUNCH_SELECT
     tock(e);
     e->launches++;
     CU(cudaGetLastError());
@@ -496,7 +516,12 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
     tick(e);
-    k_selfplay<<<game_grid(e), kGameThreads, kGameSmem, e->stream>>>(p, e->wt, e->flat);
+#define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->wt, e->flat)
+    const bool ex = epsilon > 0.f;
+    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 128, true); else BGX_LAUNCH_SELFPLAY(16, 128, false); }
+    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 64, true); else BGX_LAUNCH_SELFPLAY(24, 64, false); }
+    else { if (ex) BGX_LAUNCH_SELFPLAY(32, 32, true); else BGX_LAUNCH_SELFPLAY(32, 32, false); }
+#undef BGX_LAUNCH_SELFPLAY
     tock(e);
     e->launches++;
     CU(cudaGetLastError());
@@ -507,6 +532,7 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
         std::memset(out, 0, sizeof *out);
         out->plies = (int64_t)h[0]; out->sequences = (int64_t)h[1]; out->scored = (int64_t)h[2];
         out->games_finished = (int64_t)h[3]; out->p1_wins = (int64_t)h[4]; out->truncated = (int64_t)h[5];
+        out->tree_edges = (int64_t)h[7];
     }
     return BGX_OK;
 }

@@ -265,6 +265,7 @@ struct Choice {
     float value;
     int n_seq;        // sequences enumerated (reference count)
     int n_scored;     // afterstates sent through the network
+    int n_visited;    // tree edges walked (moves applied)
     bool any;         // a sequence exists (N > 0)
 };
 
@@ -306,7 +307,7 @@ struct GreedyLeaf {
 
     __device__ __forceinline__ GreedyLeaf(const Evaluator &e, SeenCache &c, int ln, int pl) : ev(e), cache(c), lane(ln), player(pl)
     {
-        best.v = 0; best.moves = 0; best.value = 0.f; best.n_seq = 0; best.n_scored = 0; best.any = false;
+        best.v = 0; best.moves = 0; best.value = 0.f; best.n_seq = 0; best.n_scored = 0; best.n_visited = 0; best.any = false;
     }
     __device__ __forceinline__ void operator()(int v, uint64_t moves, int)
     {
@@ -345,7 +346,7 @@ __device__ __forceinline__ Choice choose_ply(int root, int lane, int player, int
         CountLeaf cnt;
         walk_turn(root, lane, player, d1, d2, cnt);
         Choice c;
-        c.v = root; c.moves = 0; c.value = __int_as_float(0x7fc00000); c.n_seq = cnt.n; c.n_scored = 0; c.any = cnt.n > 0;
+        c.v = root; c.moves = 0; c.value = __int_as_float(0x7fc00000); c.n_seq = cnt.n; c.n_scored = 0; c.n_visited = 0; c.any = cnt.n > 0;
         if (cnt.n > 0) {
             PickLeaf pick((int)mulhi32(u, (uint32_t)cnt.n));
             walk_turn(root, lane, player, d1, d2, pick);

@@ -9,7 +9,8 @@ namespace bgx {
 constexpr int kGameWarps = 16;                     // warps per CTA in the warp-per-position kernels
 constexpr int kGameThreads = kGameWarps * 32;
 // dynamic shared memory of the fused ply kernels: weight table + per-warp scratch + barrier
-constexpr int kGameSmem = kTableBytes + kGameWarps * kPlyScratchBytes + 16;
+template <int kWarps, int kSets>
+constexpr int ply_smem() { return kTableBytes + kWarps * (int)sizeof(PlyScratch<kSets>) + 16; }
 constexpr int kEvalSmem = kTableBytes + 16;            // k_evaluate: table + barrier
 
 // exact-dedup table of the summary kernel: per warp, in global memory (L2 resident)
@@ -274,19 +275,18 @@ __device__ __forceinline__ void store_choice(const SelectOut &o, long long q, co
     }
 }
 
-__global__ void __launch_bounds__(kGameThreads, 1)
+template <int kWarps, int kSets, bool kExplore>
+__global__ void __launch_bounds__(kWarps * 32, 1)
 k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_t seed_lo, uint32_t seed_hi,
          SelectOut out, const float *__restrict__ Wt, const float *__restrict__ flat, unsigned long long *counter)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float *sT = reinterpret_cast<float *>(smem);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kGameWarps * kPlyScratchBytes);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PlyScratch &S = *reinterpret_cast<PlyScratch *>(smem + kTableBytes + warp * kPlyScratchBytes);
-    PlyCache cache;
-    cache.slots = S.cache;
-    cache.gen = 0;
-    for (int i = lane; i < kPlySlots * kPlyEntryWords; i += 32) S.cache[i] = 0;
+    PlyScratch<kSets> &S = *reinterpret_cast<PlyScratch<kSets> *>(smem + kTableBytes + warp * sizeof(PlyScratch<kSets>));
+    PlyCache<kSets> cache;
+    cache.reset(S.cache, lane);
     stage_table(sT, Wt, bar);
     PlyEvaluator ev;
     ev.W4 = reinterpret_cast<const float4 *>(sT);
@@ -299,12 +299,12 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
         const int player = __shfl_sync(kFull, b, 28) ? 1 : 0, d1 = __shfl_sync(kFull, b, 29), d2 = __shfl_sync(kFull, b, 30);
         bool explore = false;
         uint32_t u = 0;
-        if (epsilon > 0.f) {
+        if (kExplore && epsilon > 0.f) {
             const Philox r = philox4x32_10(seed_lo, seed_hi, 0u, (uint32_t)q, (uint32_t)((unsigned long long)q >> 32), 2u);
             explore = (float)r.x[0] * 2.3283064365386963e-10f < epsilon;
             u = r.x[1];
         }
-        const Choice c = choose_ply_fast(root, lane, player, d1, d2, ev, S, cache, explore, u);
+        const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, player, d1, d2, ev, S, cache, explore, u);
         store_choice(out, q, c, lane, player);
     }
 }
@@ -323,27 +323,26 @@ struct SelfplayParams {
     int round_mode;         // 1: play the current game to its end, no restart
     float epsilon;
     unsigned long long *counter;
-    unsigned long long *stats;   // plies, sequences, scored, finished, p1 wins, truncated
+    unsigned long long *stats;   // plies, sequences, scored, finished, p1 wins, truncated, (td steps), tree edges
 };
 
-__global__ void __launch_bounds__(kGameThreads, 1)
+template <int kWarps, int kSets, bool kExplore>
+__global__ void __launch_bounds__(kWarps * 32, 1)
 k_selfplay(SelfplayParams p, const float *__restrict__ Wt, const float *__restrict__ flat)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float *sT = reinterpret_cast<float *>(smem);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kGameWarps * kPlyScratchBytes);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PlyScratch &S = *reinterpret_cast<PlyScratch *>(smem + kTableBytes + warp * kPlyScratchBytes);
-    PlyCache cache;
-    cache.slots = S.cache;
-    cache.gen = 0;
-    for (int i = lane; i < kPlySlots * kPlyEntryWords; i += 32) S.cache[i] = 0;
+    PlyScratch<kSets> &S = *reinterpret_cast<PlyScratch<kSets> *>(smem + kTableBytes + warp * sizeof(PlyScratch<kSets>));
+    PlyCache<kSets> cache;
+    cache.reset(S.cache, lane);
     stage_table(sT, Wt, bar);
     PlyEvaluator ev;
     ev.W4 = reinterpret_cast<const float4 *>(sT);
     ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, lane);
 
-    unsigned long long s_plies = 0, s_seq = 0, s_scored = 0, s_fin = 0, s_p1 = 0, s_trunc = 0;
+    unsigned long long s_plies = 0, s_seq = 0, s_scored = 0, s_fin = 0, s_p1 = 0, s_trunc = 0, s_visited = 0;
     for (;;) {
         const long long slot = claim(p.counter, lane);
         if (slot >= p.n_slots) break;
@@ -372,16 +371,17 @@ k_selfplay(SelfplayParams p, const float *__restrict__ Wt, const float *__restri
             }
             bool explore = false;
             uint32_t u = 0;
-            if (p.epsilon > 0.f) {
+            if (kExplore && p.epsilon > 0.f) {
                 const Philox e = philox4x32_10(p.seed_lo, p.seed_hi, (uint32_t)ply, (uint32_t)gid, (uint32_t)(gid >> 32), 2u);
                 explore = (float)e.x[0] * 2.3283064365386963e-10f < p.epsilon;
                 u = e.x[1];
             }
-            const Choice c = choose_ply_fast(v, lane, player, d1, d2, ev, S, cache, explore, u);   // model.py:180-222
+            const Choice c = choose_ply_fast<kSets, kExplore>(v, lane, player, d1, d2, ev, S, cache, explore, u);   // model.py:180-222
             v = c.v;
             s_plies++;
             s_seq += (unsigned long long)c.n_seq;
             s_scored += (unsigned long long)c.n_scored;
+            s_visited += (unsigned long long)c.n_visited;
             if (rec_traj && p.traj_chosen) {
                 int8_t *t = p.traj_chosen + ((size_t)slot * p.traj_cap + ply) * 32;
                 const int len = (int)(c.moves >> 40);
@@ -422,6 +422,7 @@ k_selfplay(SelfplayParams p, const float *__restrict__ Wt, const float *__restri
         atomicAdd(p.stats + 3, s_fin);
         atomicAdd(p.stats + 4, s_p1);
         atomicAdd(p.stats + 5, s_trunc);
+        atomicAdd(p.stats + 7, s_visited);
     }
 }
 

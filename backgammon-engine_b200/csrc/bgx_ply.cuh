@@ -24,19 +24,22 @@
 
 namespace bgx {
 
-constexpr int kPlySlots = 128;           // per-warp cache entries (6 words each)
 constexpr int kPlyEntryWords = 6;        // 4 magnitude planes (+depth tag), sign|generation, sub-tree count
 
-struct __align__(16) PlyScratch {        // one per warp, in shared memory
-    float4 zs[4][32];                    // hidden pre-activations of the node at each depth (lane's 4 units)
-    int sv[4][32];                       // node state at each depth (lane's element)
-    uint32_t lg[4];                      // origins still to try
+// Per-warp scratch in shared memory.  kSets two-way sets of 6-word entries; lane (way*8 + word)
+// owns word `word` of way `way` of every set, so no lane ever reads a word another lane wrote
+// and the walk needs no __syncwarp.  Depth 0 (the root) lives in registers; rows 0..2 hold
+// depths 1..3.
+template <int kSets>
+struct __align__(16) PlyScratch {
+    float4 zs[3][32];                    // hidden pre-activations of the nodes at depth 1..3 (lane's 4 units)
+    int sv[3][32];                       // node state at depth 1..3 (lane's element)
+    uint32_t lg[4];                      // origins still to try, per depth
     uint32_t ent[4];                     // N when the node was entered
     uint32_t mv[4];                      // move taken at each depth: origin | dest << 5
     uint32_t pad[4];
-    uint32_t cache[kPlySlots * kPlyEntryWords];
+    uint32_t cache[kSets * 12];          // two 6-word entries per set
 };
-constexpr int kPlyScratchBytes = (int)sizeof(PlyScratch);
 
 __device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
 
@@ -149,59 +152,84 @@ __device__ __forceinline__ int apply_with_delta(int v, int lane, int player, int
     return nv;
 }
 
+template <int kSets>
 struct PlyCache {
     uint32_t *slots;
     uint32_t gen;
 
+    __device__ __forceinline__ void reset(uint32_t *p, int lane)
+    {
+        slots = p;
+        gen = 0;
+        for (int i = lane; i < kSets * 12; i += 32) p[i] = 0;
+    }
     __device__ __forceinline__ void next_ply(int lane)
     {
         gen = (gen + 1) & 0xFFu;
         if (gen == 0) {
-            for (int i = lane; i < kPlySlots * kPlyEntryWords; i += 32) slots[i] = 0;
+            for (int i = lane; i < kSets * 12; i += 32) slots[i] = 0;
             gen = 1;
             __syncwarp();
         }
     }
-    // lane l (< 6) owns word l of every entry, so no lane ever reads a word another lane wrote
+    // what lane (way*8 + w) expects in word w of a matching entry
     __device__ __forceinline__ uint32_t word_of(const uint32_t k[5], int tag, int lane) const
     {
-        return lane == 0 ? (k[0] | ((uint32_t)tag << 28)) : lane == 1 ? k[1] : lane == 2 ? k[2] : lane == 3 ? k[3] : (k[4] | (gen << 24));
+        const int w = lane & 7;
+        return w == 0 ? (k[0] | ((uint32_t)tag << 28)) : w == 1 ? k[1] : w == 2 ? k[2] : w == 3 ? k[3] : (k[4] | (gen << 24));
     }
-    __device__ __forceinline__ uint32_t *entry(const uint32_t k[5], int tag) const
+    // probe both ways of the set with one LDS: bit 0 / bit 1 of the result = way 0 / way 1 matches
+    __device__ __forceinline__ uint32_t probe(const uint32_t k[5], int tag, int lane, uint32_t &h, uint32_t &got) const
     {
-        return slots + ((hash_planes(k) + (uint32_t)tag * 0x9E3779B1u) & (kPlySlots - 1)) * kPlyEntryWords;
+        h = hash_planes(k) + (uint32_t)tag * 0x9E3779B1u;
+        const uint32_t *set = slots + (h & (kSets - 1)) * 12;
+        got = (lane < 16 && (lane & 7) < 6) ? set[(lane >> 3) * 6 + (lane & 7)] : 0u;
+        const uint32_t same = __ballot_sync(kFull, (lane & 7) >= 5 || got == word_of(k, tag, lane));
+        return ((same & 0xFFu) == 0xFFu ? 1u : 0u) | ((same & 0xFF00u) == 0xFF00u ? 2u : 0u);
+    }
+    // victim: a way left over from an earlier ply if there is one, else pseudo-random
+    __device__ __forceinline__ void write(const uint32_t k[5], int tag, uint32_t h, uint32_t got, uint32_t count, int lane) const
+    {
+        const uint32_t stale = __ballot_sync(kFull, lane < 16 && (lane & 7) == 4 && (got >> 24) != gen);
+        const int way = (stale & 0x10u) ? 0 : (stale & 0x1000u) ? 1 : (int)((h >> 20) & 1u);
+        uint32_t *e = slots + (h & (kSets - 1)) * 12 + way * 6;
+        const int w = lane & 7;
+        if ((lane >> 3) == way) {
+            if (w < 5) e[w] = word_of(k, tag, lane);
+            else if (w == 5) e[5] = count;
+        }
     }
     // scored-afterstate set (tag 0): true if this exact state was scored earlier in this ply
     __device__ __forceinline__ bool seen_or_insert(const uint32_t k[5], int lane) const
     {
-        uint32_t *e = entry(k, 0);
-        const uint32_t mine = word_of(k, 0, lane);
-        const bool same = lane >= 5 || e[lane] == mine;
-        const bool seen = __all_sync(kFull, same);
-        if (!seen && lane < 5) e[lane] = mine;
-        return seen;
+        uint32_t h, got;
+        if (probe(k, 0, lane, h, got)) return true;
+        write(k, 0, h, got, 0u, lane);
+        return false;
     }
     // memo of interior nodes (tag = depth): sub-tree sequence count, or -1
     __device__ __forceinline__ int lookup(const uint32_t k[5], int tag, int lane) const
     {
-        uint32_t *e = entry(k, tag);
-        const uint32_t mine = word_of(k, tag, lane);
-        uint32_t got = 0;
-        if (lane < 6) got = e[lane];
-        const bool hitall = __all_sync(kFull, lane >= 5 || got == mine);
-        const int cnt = (int)__shfl_sync(kFull, got, 5);
-        return hitall ? cnt : -1;
+        uint32_t h, got;
+        const uint32_t hit = probe(k, tag, lane, h, got);
+        const int cnt = (int)__shfl_sync(kFull, got, (hit & 1u) ? 5 : 13);
+        return hit ? cnt : -1;
     }
     __device__ __forceinline__ void store(const uint32_t k[5], int tag, int count, int lane) const
     {
-        uint32_t *e = entry(k, tag);
-        if (lane < 5) e[lane] = word_of(k, tag, lane);
-        else if (lane == 5) e[5] = (uint32_t)count;
+        uint32_t h, got;
+        const uint32_t hit = probe(k, tag, lane, h, got);   // refresh in place if it is still there
+        if (hit) {
+            if (lane == ((hit & 1u) ? 5 : 13)) slots[(h & (kSets - 1)) * 12 + (lane >> 3) * 6 + 5] = (uint32_t)count;
+        } else {
+            write(k, tag, h, got, (uint32_t)count, lane);
+        }
     }
 };
 
+template <int kSets>
 __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int d1, int d2, const PlyEvaluator &ev,
-                                             PlyScratch &S, PlyCache &cache)
+                                             PlyScratch<kSets> &S, PlyCache<kSets> &cache)
 {
     cache.next_ply(lane);
     const float4 zroot = ev.preactivation(root, lane, player);
@@ -209,7 +237,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
     const int maxlen = dbl ? 4 : 2;
     const int npass = dbl ? 1 : 2;
     Choice best;
-    best.v = root; best.moves = 0; best.value = __int_as_float(0x7fc00000); best.n_seq = 0; best.n_scored = 0; best.any = false;
+    best.v = root; best.moves = 0; best.value = __int_as_float(0x7fc00000); best.n_seq = 0; best.n_scored = 0; best.n_visited = 0; best.any = false;
     int best_len = 0;
     uint32_t best_mv0 = 0, best_mv1 = 0, best_mv2 = 0, best_mv3 = 0;
 
@@ -234,7 +262,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
                         uint32_t k[5];
                         key_planes(cur, k);
                         if (!cache.seen_or_insert(k, lane)) {
-                            const float4 z = depth == 0 ? zroot : md.apply(S.zs[depth - 1][lane], ev.W4, lane, player);
+                            const float4 z = depth == 0 ? zroot : md.apply(depth == 1 ? zroot : S.zs[depth - 2][lane], ev.W4, lane, player);
                             const float val = ev.finish(z);
                             best.n_scored++;
                             if (!best.any || (player == 0 ? val > best.value : val < best.value)) {
@@ -257,8 +285,10 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
                         continue;
                     }
                 }
-                S.zs[depth][lane] = depth == 0 ? zroot : md.apply(S.zs[depth - 1][lane], ev.W4, lane, player);
-                S.sv[depth][lane] = cur;
+                if (depth > 0) {
+                    S.zs[depth - 1][lane] = md.apply(depth == 1 ? zroot : S.zs[depth - 2][lane], ev.W4, lane, player);
+                    S.sv[depth - 1][lane] = cur;
+                }
                 S.lg[depth] = legal;
                 S.ent[depth] = (uint32_t)best.n_seq;
             }
@@ -266,7 +296,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
             if (rest == 0) {                                       // all children done
                 if (dbl && depth >= 2) {
                     uint32_t k[5];
-                    key_planes(S.sv[depth][lane], k);
+                    key_planes(S.sv[depth - 1][lane], k);
                     cache.store(k, depth, best.n_seq - (int)S.ent[depth], lane);
                 }
                 if (depth == 0) break;
@@ -276,7 +306,8 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
             const int o = lowest_bit(rest);
             S.lg[depth] = rest & (rest - 1);
             const int d = destination(player, o, (depth & 1) ? dieB : dieA);
-            cur = apply_with_delta(S.sv[depth][lane], lane, player, o, d, md);
+            cur = apply_with_delta(depth == 0 ? root : S.sv[depth - 1][lane], lane, player, o, d, md);
+            best.n_visited++;
             S.mv[depth] = (uint32_t)(o | (d << 5));
             depth++;
             entering = true;
@@ -293,15 +324,16 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
     return best;
 }
 
-// greedy or exploring ply
+// greedy or exploring ply; kExplore = false compiles the epsilon path out (smaller, fewer registers)
+template <int kSets, bool kExplore>
 __device__ __forceinline__ Choice choose_ply_fast(int root, int lane, int player, int d1, int d2, const PlyEvaluator &ev,
-                                                  PlyScratch &S, PlyCache &cache, bool explore, uint32_t u)
+                                                  PlyScratch<kSets> &S, PlyCache<kSets> &cache, bool explore, uint32_t u)
 {
-    if (explore) {
+    if (kExplore && explore) {
         CountLeaf cnt;
         walk_turn(root, lane, player, d1, d2, cnt);
         Choice c;
-        c.v = root; c.moves = 0; c.value = __int_as_float(0x7fc00000); c.n_seq = cnt.n; c.n_scored = 0; c.any = cnt.n > 0;
+        c.v = root; c.moves = 0; c.value = __int_as_float(0x7fc00000); c.n_seq = cnt.n; c.n_scored = 0; c.n_visited = 0; c.any = cnt.n > 0;
         if (cnt.n > 0) {
             PickLeaf pick((int)mulhi32(u, (uint32_t)cnt.n));
             walk_turn(root, lane, player, d1, d2, pick);
@@ -310,7 +342,7 @@ __device__ __forceinline__ Choice choose_ply_fast(int root, int lane, int player
         }
         return c;
     }
-    return greedy_ply(root, lane, player, d1, d2, ev, S, cache);
+    return greedy_ply<kSets>(root, lane, player, d1, d2, ev, S, cache);
 }
 
 } // namespace bgx

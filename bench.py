@@ -202,7 +202,7 @@ def run_ours(args):
     sampler.start()
     launches0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms, plies, seqs, scored = [], 0, 0, 0
+    kernel_ms, plies, seqs, scored, edges = [], 0, 0, 0, 0
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)                       # L2 flush between timed iterations (not timed)
@@ -210,7 +210,7 @@ def run_ours(args):
         st = eng.selfplay_step(PLIES_PER_STEP)      # reads the 64-byte stats block back: one sync per step
         ev[k][1].record(stream)
         kernel_ms.append(eng.last_kernel_ms())
-        plies += st["plies"]; seqs += st["sequences"]; scored += st["scored"]
+        plies += st["plies"]; seqs += st["sequences"]; scored += st["scored"]; edges += st["tree_edges"]
     barrier()
     wall = time.perf_counter() - t_wall0
     launches = eng.launch_count() - launches0
@@ -307,6 +307,7 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world),
                 "sequences_per_sec": seqs_all / total_s, "afterstates_scored_per_sec": scored_all / total_s,
                 "sequences_per_ply": seqs_all / plies_all, "scored_per_ply": scored_all / plies_all,
+                "tree_edges_per_ply_rank0": edges / max(plies, 1), "ply_warps_per_cta": int(os.environ.get("BGX_PLY_WARPS", "16")),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 32, "d2h_bytes_per_step": G * 36,
                         "note": "one step = one ply for all 65,536 games through bgx_select_moves_host; "
                                 f"{e2e_steps} timed plies incl. the numpy host loop"},

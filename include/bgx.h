@@ -179,6 +179,7 @@ typedef struct bgx_stats {
     int64_t truncated;        /* games that hit traj_cap before ending */
     int64_t td_steps;         /* TD(lambda) steps replayed (bgx_td_replay) */
     double td_sq_error;       /* sum of td_error^2 over the non-terminal steps (train.py:162) */
+    int64_t tree_edges;       /* moves applied while walking the turn trees (work actually done; <= what the reference walks) */
 } bgx_stats;
 
 /* first-mover rule */
