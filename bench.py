@@ -103,7 +103,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def port_baseline(w, seconds):
@@ -231,8 +231,9 @@ def run_ours(args):
                "value": torch.zeros(G, dtype=torch.float32).pin_memory().numpy(),
                "moves": None, "moves_len": None, "n_seq": None, "n_scored": None}
     q = q_pin.numpy()
-    q[:, :24] = START_BOARD
-    q[:, 28] = (np.arange(G) + rank * G) % 2
+    rec, _, _ = eng.selfplay_read()          # continue the (desynchronised) games of the population from the host
+    q[:] = rec
+    q[:, 31] = 0
     rng = np.random.default_rng(SEED + rank)
     e2e_plies = 0
     for it in range(-2, e2e_steps):                 # 2 untimed warm-up plies
@@ -332,10 +333,20 @@ def run_ours(args):
                 line["cpu_baseline"] = ref["cpu_baseline"]
             except Exception as exc:                 # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {exc}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def emit(line):
+    """The one JSON line goes to the REAL stdout; everything else any library prints (NCCL's version
+    banner, warnings) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
