@@ -147,8 +147,8 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaFuncSetAttribute(k_select<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));             \
     CU(cudaFuncSetAttribute(k_selfplay<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));          \
     CU(cudaFuncSetAttribute(k_selfplay<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));
-    BGX_SMEM_ATTR(16, 128)
-    BGX_SMEM_ATTR(24, 64)
+    BGX_SMEM_ATTR(16, 96)
+    BGX_SMEM_ATTR(24, 48)
     BGX_SMEM_ATTR(32, 32)
 #undef BGX_SMEM_ATTR
     CU(cudaFuncSetAttribute(k_td_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
@@ -414,8 +414,8 @@ int bgx_select_moves(bgx_engine *e, const int8_t *queries, int64_t n, float epsi
     k_select<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(queries, n, epsilon, (uint32_t)seed, \
                                                                              (uint32_t)(seed >> 32), out, e->wt, e->flat, e->counter)
     const bool ex = epsilon > 0.f;
-    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 128, true); else BGX_LAUNCH_SELECT(16, 128, false); }
-    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 64, true); else BGX_LAUNCH_SELECT(24, 64, false); }
+    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 96, true); else BGX_LAUNCH_SELECT(16, 96, false); }
+    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 48, true); else BGX_LAUNCH_SELECT(24, 48, false); }
     else { if (ex) BGX_LAUNCH_SELECT(32, 32, true); else BGX_LAUNCH_SELECT(32, 32, false); }
 #undef BGX_LAUNCH_SELECT
     tock(e);
@@ -518,8 +518,8 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
     tick(e);
 #define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->wt, e->flat)
     const bool ex = epsilon > 0.f;
-    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 128, true); else BGX_LAUNCH_SELFPLAY(16, 128, false); }
-    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 64, true); else BGX_LAUNCH_SELFPLAY(24, 64, false); }
+    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 96, true); else BGX_LAUNCH_SELFPLAY(16, 96, false); }
+    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 48, true); else BGX_LAUNCH_SELFPLAY(24, 48, false); }
     else { if (ex) BGX_LAUNCH_SELFPLAY(32, 32, true); else BGX_LAUNCH_SELFPLAY(32, 32, false); }
 #undef BGX_LAUNCH_SELFPLAY
     tock(e);

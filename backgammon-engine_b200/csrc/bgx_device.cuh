@@ -21,9 +21,6 @@ constexpr int kFeatures = 198;
 constexpr int kHidden = 128;
 constexpr int kTableFloats = kFeatures * kHidden;                 // 25 344
 constexpr int kTableBytes = kTableFloats * 4;                     // 101 376
-constexpr int kCacheSlots = 256;                                  // per-warp dedup cache (direct mapped)
-constexpr int kCacheWords = 5;                                    // 4 magnitude planes + sign|generation
-constexpr int kCacheBytesPerWarp = kCacheSlots * kCacheWords * 4; // 5 120
 
 // status byte (record byte 31) of a self-play slot
 enum { kRunning = 0, kP1Won = 1, kP2Won = 2, kTruncated = 3 };
@@ -269,59 +266,6 @@ struct Choice {
     bool any;         // a sequence exists (N > 0)
 };
 
-// per-warp direct-mapped cache of afterstates already scored in THIS ply.  A miss only
-// costs a repeated evaluation, a hit is an exact 160-bit match (plus the 8-bit ply
-// generation stored in the unused top byte of the sign plane), so the arg-best is exact:
-// duplicates score identically and the strict comparison keeps the first occurrence,
-// which is torch.argmax/argmin's tie-break (model.py:212-213).
-struct SeenCache {
-    uint32_t *slots;   // shared memory, kCacheSlots * kCacheWords
-    uint32_t gen;
-
-    __device__ __forceinline__ void next_ply(int lane)
-    {
-        gen = (gen + 1) & 0xFFu;
-        if (gen == 0) {
-            for (int i = lane; i < kCacheSlots * kCacheWords; i += 32) slots[i] = 0;
-            gen = 1;
-            __syncwarp();
-        }
-    }
-    __device__ __forceinline__ bool test_and_set(const uint32_t k[5], int lane)
-    {
-        uint32_t *e = slots + (hash_planes(k) & (kCacheSlots - 1)) * kCacheWords;
-        const uint32_t mine = lane == 0 ? k[0] : lane == 1 ? k[1] : lane == 2 ? k[2] : lane == 3 ? k[3] : (k[4] | (gen << 24));
-        const bool same = lane >= kCacheWords || e[lane] == mine;
-        const bool seen = __all_sync(kFull, same);
-        if (!seen && lane < kCacheWords) e[lane] = mine;
-        __syncwarp();
-        return seen;
-    }
-};
-
-struct GreedyLeaf {
-    const Evaluator &ev;
-    SeenCache &cache;
-    int lane, player;
-    Choice best;
-
-    __device__ __forceinline__ GreedyLeaf(const Evaluator &e, SeenCache &c, int ln, int pl) : ev(e), cache(c), lane(ln), player(pl)
-    {
-        best.v = 0; best.moves = 0; best.value = 0.f; best.n_seq = 0; best.n_scored = 0; best.n_visited = 0; best.any = false;
-    }
-    __device__ __forceinline__ void operator()(int v, uint64_t moves, int)
-    {
-        best.n_seq++;
-        uint32_t k[5];
-        key_planes(v, k);
-        if (cache.test_and_set(k, lane)) return;
-        const float val = ev.value(v, lane);
-        best.n_scored++;
-        const bool better = !best.any || (player == 0 ? val > best.value : val < best.value);
-        if (better) { best.v = v; best.moves = moves; best.value = val; best.any = true; }
-    }
-};
-
 struct CountLeaf {
     int n = 0;
     __device__ __forceinline__ void operator()(int, uint64_t, int) { n++; }
@@ -337,31 +281,6 @@ struct PickLeaf {
         n++;
     }
 };
-
-// explore: take sequence floor(u * N / 2^32) instead of the arg-best (model.py:205-206)
-__device__ __forceinline__ Choice choose_ply(int root, int lane, int player, int d1, int d2, Evaluator &ev,
-                                             SeenCache &cache, bool explore, uint32_t u)
-{
-    if (explore) {
-        CountLeaf cnt;
-        walk_turn(root, lane, player, d1, d2, cnt);
-        Choice c;
-        c.v = root; c.moves = 0; c.value = __int_as_float(0x7fc00000); c.n_seq = cnt.n; c.n_scored = 0; c.n_visited = 0; c.any = cnt.n > 0;
-        if (cnt.n > 0) {
-            PickLeaf pick((int)mulhi32(u, (uint32_t)cnt.n));
-            walk_turn(root, lane, player, d1, d2, pick);
-            c.v = pick.v;
-            c.moves = pick.moves;
-        }
-        return c;
-    }
-    cache.next_ply(lane);
-    ev.begin(player, lane);
-    GreedyLeaf leaf(ev, cache, lane, player);
-    walk_turn(root, lane, player, d1, d2, leaf);
-    if (!leaf.best.any) { leaf.best.v = root; leaf.best.value = __int_as_float(0x7fc00000); }
-    return leaf.best;
-}
 
 // opening position (cppsrc/game.cpp:251) for this lane
 __device__ __forceinline__ int start_value(int lane)

@@ -17,19 +17,18 @@
 //     at depth >= 2 are remembered with the number of sequences below them; meeting one again
 //     adds that count to N and skips the whole sub-tree: all its afterstates were already
 //     scored earlier in reference order, so the first-index arg-best is unchanged and N stays
-//     exact.  The memo shares the per-warp direct-mapped cache with the scored-afterstate
-//     set; it is lossy in the safe direction only (a miss re-walks, never mis-counts).
+//     exact.  The memo shares the per-warp two-way cache with the scored-afterstate set; it is
+//     lossy in the safe direction only (a miss re-walks, never mis-counts).
 #pragma once
 #include "bgx_device.cuh"
 
 namespace bgx {
 
-constexpr int kPlyEntryWords = 6;        // 4 magnitude planes (+depth tag), sign|generation, sub-tree count
+constexpr int kPlyEntryBytes = 32;       // one byte per lane: 28 state bytes, node tag, ply generation, sub-tree count, spare
 
-// Per-warp scratch in shared memory.  kSets two-way sets of 6-word entries; lane (way*8 + word)
-// owns word `word` of way `way` of every set, so no lane ever reads a word another lane wrote
-// and the walk needs no __syncwarp.  Depth 0 (the root) lives in registers; rows 0..2 hold
-// depths 1..3.
+// Per-warp scratch in shared memory.  The cache is kSets two-way sets of 32-byte entries; lane l
+// owns byte l of both ways of every set: it alone reads and writes that byte, so the walk needs
+// no __syncwarp.  Depth 0 (the root) lives in registers; rows 0..2 hold depths 1..3.
 template <int kSets>
 struct __align__(16) PlyScratch {
     float4 zs[3][32];                    // hidden pre-activations of the nodes at depth 1..3 (lane's 4 units)
@@ -38,7 +37,7 @@ struct __align__(16) PlyScratch {
     uint32_t ent[4];                     // N when the node was entered
     uint32_t mv[4];                      // move taken at each depth: origin | dest << 5
     uint32_t pad[4];
-    uint32_t cache[kSets * 12];          // two 6-word entries per set
+    uint8_t cache[kSets * 2 * kPlyEntryBytes];
 };
 
 __device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
@@ -152,78 +151,92 @@ __device__ __forceinline__ int apply_with_delta(int v, int lane, int player, int
     return nv;
 }
 
+// The per-warp cache of one ply.  Two kinds of entries share it:
+//   tag 0      an afterstate that was already scored in this ply (the exact-duplicate filter)
+//   tag 2, 3   an interior node of a double at that depth, with the number of sequences below it
+// An entry is the position itself, one byte per lane, so a probe is one byte load per way, one
+// compare and one vote; the set index comes from a single warp-wide integer reduction
+// (REDUX.SUM) of value x per-lane multiplier.  A hit is an exact match of all 28 state bytes,
+// the tag and the ply generation, so the cache can only lose time, never exactness.
 template <int kSets>
 struct PlyCache {
-    uint32_t *slots;
-    uint32_t gen;
+    uint8_t *slots;
+    uint32_t gen;        // 1..255, bumped per ply; stale entries are the preferred victims
+    uint32_t kmul;       // this lane's hash multiplier
 
-    __device__ __forceinline__ void reset(uint32_t *p, int lane)
+    struct Probe {
+        uint32_t off;    // byte offset of the set
+        uint32_t m0, m1; // per-lane equality masks of way 0 / way 1
+        uint32_t h, got0, got1;
+        __device__ __forceinline__ bool hit() const { return m0 == kFull || m1 == kFull; }
+    };
+
+    __device__ __forceinline__ void reset(uint8_t *p, int lane)
     {
         slots = p;
         gen = 0;
-        for (int i = lane; i < kSets * 12; i += 32) p[i] = 0;
+        kmul = (0x9E3779B1u * (uint32_t)(2 * lane + 1)) ^ (0x85EBCA77u >> (lane & 7));
+        uint32_t *w = reinterpret_cast<uint32_t *>(p);
+        for (int i = lane; i < kSets * 2 * kPlyEntryBytes / 4; i += 32) w[i] = 0;
     }
     __device__ __forceinline__ void next_ply(int lane)
     {
         gen = (gen + 1) & 0xFFu;
         if (gen == 0) {
-            for (int i = lane; i < kSets * 12; i += 32) slots[i] = 0;
+            uint32_t *w = reinterpret_cast<uint32_t *>(slots);
+            for (int i = lane; i < kSets * 2 * kPlyEntryBytes / 4; i += 32) w[i] = 0;
             gen = 1;
             __syncwarp();
         }
     }
-    // what lane (way*8 + w) expects in word w of a matching entry
-    __device__ __forceinline__ uint32_t word_of(const uint32_t k[5], int tag, int lane) const
+    // what this lane's byte of a matching entry holds (lanes 30, 31 match anything)
+    __device__ __forceinline__ uint32_t byte_of(int v, int tag, int lane) const
     {
-        const int w = lane & 7;
-        return w == 0 ? (k[0] | ((uint32_t)tag << 28)) : w == 1 ? k[1] : w == 2 ? k[2] : w == 3 ? k[3] : (k[4] | (gen << 24));
+        const uint32_t meta = lane == 28 ? (uint32_t)tag : gen;
+        return lane < 28 ? ((uint32_t)v & 0xFFu) : meta;
     }
-    // probe both ways of the set with one LDS: bit 0 / bit 1 of the result = way 0 / way 1 matches
-    __device__ __forceinline__ uint32_t probe(const uint32_t k[5], int tag, int lane, uint32_t &h, uint32_t &got) const
+    __device__ __forceinline__ Probe probe(int v, int tag, int lane) const
     {
-        h = hash_planes(k) + (uint32_t)tag * 0x9E3779B1u;
-        const uint32_t *set = slots + (h & (kSets - 1)) * 12;
-        got = (lane < 16 && (lane & 7) < 6) ? set[(lane >> 3) * 6 + (lane & 7)] : 0u;
-        const uint32_t same = __ballot_sync(kFull, (lane & 7) >= 5 || got == word_of(k, tag, lane));
-        return ((same & 0xFFu) == 0xFFu ? 1u : 0u) | ((same & 0xFF00u) == 0xFF00u ? 2u : 0u);
+        Probe p;
+        uint32_t h = __reduce_add_sync(kFull, (uint32_t)(v + 16) * kmul) + (uint32_t)tag * 0x9E3779B1u;
+        h ^= h >> 15;
+        p.h = h;
+        p.off = (((h & 0xFFFFu) * (uint32_t)kSets) >> 16) * (2 * kPlyEntryBytes);
+        const uint8_t *e = slots + p.off + lane;
+        p.got0 = e[0];
+        p.got1 = e[kPlyEntryBytes];
+        const uint32_t mine = byte_of(v, tag, lane);
+        p.m0 = __ballot_sync(kFull, lane >= 30 || p.got0 == mine);
+        p.m1 = __ballot_sync(kFull, lane >= 30 || p.got1 == mine);
+        return p;
     }
-    // victim: a way left over from an earlier ply if there is one, else pseudo-random
-    __device__ __forceinline__ void write(const uint32_t k[5], int tag, uint32_t h, uint32_t got, uint32_t count, int lane) const
+    // victim: the matching way if there is one, else a way left over from an earlier ply, else pseudo-random
+    __device__ __forceinline__ void write(const Probe &p, int v, int tag, int count, int lane) const
     {
-        const uint32_t stale = __ballot_sync(kFull, lane < 16 && (lane & 7) == 4 && (got >> 24) != gen);
-        const int way = (stale & 0x10u) ? 0 : (stale & 0x1000u) ? 1 : (int)((h >> 20) & 1u);
-        uint32_t *e = slots + (h & (kSets - 1)) * 12 + way * 6;
-        const int w = lane & 7;
-        if ((lane >> 3) == way) {
-            if (w < 5) e[w] = word_of(k, tag, lane);
-            else if (w == 5) e[5] = count;
-        }
+        const int way = p.m0 == kFull ? 0 : p.m1 == kFull ? 1 : !((p.m0 >> 29) & 1u) ? 0 : !((p.m1 >> 29) & 1u) ? 1 : (int)((p.h >> 20) & 1u);
+        const uint32_t mine = lane == 30 ? (uint32_t)count : byte_of(v, tag, lane);
+        slots[p.off + way * kPlyEntryBytes + lane] = (uint8_t)mine;
     }
     // scored-afterstate set (tag 0): true if this exact state was scored earlier in this ply
-    __device__ __forceinline__ bool seen_or_insert(const uint32_t k[5], int lane) const
+    __device__ __forceinline__ bool seen_or_insert(int v, int lane) const
     {
-        uint32_t h, got;
-        if (probe(k, 0, lane, h, got)) return true;
-        write(k, 0, h, got, 0u, lane);
+        const Probe p = probe(v, 0, lane);
+        if (p.hit()) return true;
+        write(p, v, 0, 0, lane);
         return false;
     }
-    // memo of interior nodes (tag = depth): sub-tree sequence count, or -1
-    __device__ __forceinline__ int lookup(const uint32_t k[5], int tag, int lane) const
+    // memo of interior nodes (tag = depth): sub-tree sequence count (<= 225), or -1
+    __device__ __forceinline__ int lookup(int v, int tag, int lane) const
     {
-        uint32_t h, got;
-        const uint32_t hit = probe(k, tag, lane, h, got);
-        const int cnt = (int)__shfl_sync(kFull, got, (hit & 1u) ? 5 : 13);
-        return hit ? cnt : -1;
+        const Probe p = probe(v, tag, lane);
+        const int cnt = (int)__shfl_sync(kFull, p.m0 == kFull ? p.got0 : p.got1, 30);
+        return p.hit() ? cnt : -1;
     }
-    __device__ __forceinline__ void store(const uint32_t k[5], int tag, int count, int lane) const
+    __device__ __forceinline__ void store(int v, int tag, int count, int lane) const
     {
-        uint32_t h, got;
-        const uint32_t hit = probe(k, tag, lane, h, got);   // refresh in place if it is still there
-        if (hit) {
-            if (lane == ((hit & 1u) ? 5 : 13)) slots[(h & (kSets - 1)) * 12 + (lane >> 3) * 6 + 5] = (uint32_t)count;
-        } else {
-            write(k, tag, h, got, (uint32_t)count, lane);
-        }
+        if (count > 255) return;                      // cannot happen (<= 15 x 15 sequences below depth 2); never mis-count
+        const Probe p = probe(v, tag, lane);
+        write(p, v, tag, count, lane);
     }
 };
 
@@ -259,9 +272,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
                 if (legal == 0) {
                     if (dbl || depth > 0) {                       // a sequence ends here
                         best.n_seq++;
-                        uint32_t k[5];
-                        key_planes(cur, k);
-                        if (!cache.seen_or_insert(k, lane)) {
+                        if (!cache.seen_or_insert(cur, lane)) {
                             const float4 z = depth == 0 ? zroot : md.apply(depth == 1 ? zroot : S.zs[depth - 2][lane], ev.W4, lane, player);
                             const float val = ev.finish(z);
                             best.n_scored++;
@@ -276,9 +287,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
                     continue;
                 }
                 if (dbl && depth >= 2) {                           // same position, same dice left: seen before?
-                    uint32_t k[5];
-                    key_planes(cur, k);
-                    const int below = cache.lookup(k, depth, lane);
+                    const int below = cache.lookup(cur, depth, lane);
                     if (below >= 0) {
                         best.n_seq += below;
                         depth--;
@@ -295,9 +304,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
             const uint32_t rest = S.lg[depth];
             if (rest == 0) {                                       // all children done
                 if (dbl && depth >= 2) {
-                    uint32_t k[5];
-                    key_planes(S.sv[depth - 1][lane], k);
-                    cache.store(k, depth, best.n_seq - (int)S.ent[depth], lane);
+                    cache.store(S.sv[depth - 1][lane], depth, best.n_seq - (int)S.ent[depth], lane);
                 }
                 if (depth == 0) break;
                 depth--;
