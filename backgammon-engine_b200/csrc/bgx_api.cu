@@ -147,9 +147,9 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaFuncSetAttribute(k_select<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));             \
     CU(cudaFuncSetAttribute(k_selfplay<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));          \
     CU(cudaFuncSetAttribute(k_selfplay<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));
-    BGX_SMEM_ATTR(16, 96)
-    BGX_SMEM_ATTR(24, 48)
-    BGX_SMEM_ATTR(32, 32)
+    BGX_SMEM_ATTR(16, 126)
+    BGX_SMEM_ATTR(24, 84)
+    BGX_SMEM_ATTR(32, 62)
 #undef BGX_SMEM_ATTR
     CU(cudaFuncSetAttribute(k_td_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
     *out = e;
@@ -414,9 +414,9 @@ int bgx_select_moves(bgx_engine *e, const int8_t *queries, int64_t n, float epsi
     k_select<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(queries, n, epsilon, (uint32_t)seed, \
                                                                              (uint32_t)(seed >> 32), out, e->wt, e->flat, e->counter)
     const bool ex = epsilon > 0.f;
-    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 96, true); else BGX_LAUNCH_SELECT(16, 96, false); }
-    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 48, true); else BGX_LAUNCH_SELECT(24, 48, false); }
-    else { if (ex) BGX_LAUNCH_SELECT(32, 32, true); else BGX_LAUNCH_SELECT(32, 32, false); }
+    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 126, true); else BGX_LAUNCH_SELECT(16, 126, false); }
+    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 84, true); else BGX_LAUNCH_SELECT(24, 84, false); }
+    else { if (ex) BGX_LAUNCH_SELECT(32, 62, true); else BGX_LAUNCH_SELECT(32, 62, false); }
 #undef BGX_LAUNCH_SELECT
     tock(e);
     e->launches++;
@@ -518,9 +518,9 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
     tick(e);
 #define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->wt, e->flat)
     const bool ex = epsilon > 0.f;
-    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 96, true); else BGX_LAUNCH_SELFPLAY(16, 96, false); }
-    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 48, true); else BGX_LAUNCH_SELFPLAY(24, 48, false); }
-    else { if (ex) BGX_LAUNCH_SELFPLAY(32, 32, true); else BGX_LAUNCH_SELFPLAY(32, 32, false); }
+    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 126, true); else BGX_LAUNCH_SELFPLAY(16, 126, false); }
+    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 84, true); else BGX_LAUNCH_SELFPLAY(24, 84, false); }
+    else { if (ex) BGX_LAUNCH_SELFPLAY(32, 62, true); else BGX_LAUNCH_SELFPLAY(32, 62, false); }
 #undef BGX_LAUNCH_SELFPLAY
     tock(e);
     e->launches++;

@@ -284,9 +284,8 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
     float *sT = reinterpret_cast<float *>(smem);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PlyScratch<kSets> &S = *reinterpret_cast<PlyScratch<kSets> *>(smem + kTableBytes + warp * sizeof(PlyScratch<kSets>));
     PlyCache<kSets> cache;
-    cache.reset(S.cache, lane);
+    cache.reset(reinterpret_cast<PlyScratch<kSets> *>(smem + kTableBytes)[warp].cache, lane);
     stage_table(sT, Wt, bar);
     PlyEvaluator ev;
     ev.W4 = reinterpret_cast<const float4 *>(sT);
@@ -304,7 +303,7 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
             explore = (float)r.x[0] * 2.3283064365386963e-10f < epsilon;
             u = r.x[1];
         }
-        const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, player, d1, d2, ev, S, cache, explore, u);
+        const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, player, d1, d2, ev, cache, explore, u);
         store_choice(out, q, c, lane, player);
     }
 }
@@ -334,9 +333,8 @@ k_selfplay(SelfplayParams p, const float *__restrict__ Wt, const float *__restri
     float *sT = reinterpret_cast<float *>(smem);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PlyScratch<kSets> &S = *reinterpret_cast<PlyScratch<kSets> *>(smem + kTableBytes + warp * sizeof(PlyScratch<kSets>));
     PlyCache<kSets> cache;
-    cache.reset(S.cache, lane);
+    cache.reset(reinterpret_cast<PlyScratch<kSets> *>(smem + kTableBytes)[warp].cache, lane);
     stage_table(sT, Wt, bar);
     PlyEvaluator ev;
     ev.W4 = reinterpret_cast<const float4 *>(sT);
@@ -376,7 +374,7 @@ k_selfplay(SelfplayParams p, const float *__restrict__ Wt, const float *__restri
                 explore = (float)e.x[0] * 2.3283064365386963e-10f < p.epsilon;
                 u = e.x[1];
             }
-            const Choice c = choose_ply_fast<kSets, kExplore>(v, lane, player, d1, d2, ev, S, cache, explore, u);   // model.py:180-222
+            const Choice c = choose_ply_fast<kSets, kExplore>(v, lane, player, d1, d2, ev, cache, explore, u);   // model.py:180-222
             v = c.v;
             s_plies++;
             s_seq += (unsigned long long)c.n_seq;

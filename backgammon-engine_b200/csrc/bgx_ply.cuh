@@ -1,17 +1,18 @@
-// bgx_ply.cuh — the greedy ply of the fused self-play path, second generation.
+// bgx_ply.cuh — the greedy ply of the fused self-play path.
 //
-// Same contract as choose_ply() in bgx_device.cuh (make_move, model.py:180-222: enumerate
-// in reference order, score every distinct afterstate, first-index arg-best), three changes
-// in how the work is done, all driven by the ncu capture profiles/r1a:
+// Contract: make_move (model.py:180-222) — enumerate the legal turn sequences in reference
+// order, score every distinct afterstate with the 198-128-1 net, first-index arg-best.
+// How the work is done (each step driven by an ncu capture, see profiles/):
 //
 //  1. DELTA EVALUATION.  The hidden pre-activation z = W1 x + b1 of a node is kept per tree
 //     depth; a move changes 2-4 features (one checker leaves a stack, one joins a stack, a
-//     hit also flips the blot and the enemy bar), so z(child) = z(parent) + sum of 2-4 rows
-//     of the raw feature-major weight table.  Scoring a new afterstate costs 2-4 LDS.128 +
-//     the sigmoid epilogue instead of a walk over all ~16 occupied points.
-//  2. TREE STACK IN SHARED MEMORY.  Per-depth node state / z / remaining-origin masks live in
-//     a per-warp scratch block indexed by depth; every word is only ever touched by one lane
-//     (or written with identical values by all), so the walk needs no __syncwarp.
+//     hit also flips the blot and the enemy bar), so z(child) = z(parent) + 2-4 rows of the
+//     raw feature-major weight table.  Scoring a new afterstate costs 2-4 LDS.128 + the
+//     sigmoid epilogue instead of a walk over all ~16 occupied points.
+//  2. DEPTH-SPECIALISED WALK IN REGISTERS.  The turn tree is walked by a fully inlined
+//     template recursion (one instance per depth), so node state, node z and the origins
+//     still to try are registers, not a stack in memory, and work is lazy: a child is only
+//     applied and probed in the cache; everything else happens for new afterstates only.
 //  3. MEMOISED DOUBLES.  In a double, the same position is reached at the same depth through
 //     many move orders (start 3-3: 536 sequences, 73 distinct afterstates).  Interior nodes
 //     at depth >= 2 are remembered with the number of sequences below them; meeting one again
@@ -19,6 +20,8 @@
 //     scored earlier in reference order, so the first-index arg-best is unchanged and N stays
 //     exact.  The memo shares the per-warp two-way cache with the scored-afterstate set; it is
 //     lossy in the safe direction only (a miss re-walks, never mis-counts).
+//  4. BYTE-PER-LANE CACHE.  An entry is the position itself, lane l owning byte l; the set
+//     index is one REDUX.SUM.  A probe is one byte load per way, one compare, one vote.
 #pragma once
 #include "bgx_device.cuh"
 
@@ -26,17 +29,11 @@ namespace bgx {
 
 constexpr int kPlyEntryBytes = 32;       // one byte per lane: 28 state bytes, node tag, ply generation, sub-tree count, spare
 
-// Per-warp scratch in shared memory.  The cache is kSets two-way sets of 32-byte entries; lane l
+// Per-warp scratch in shared memory: the ply cache, kSets two-way sets of 32-byte entries.  Lane l
 // owns byte l of both ways of every set: it alone reads and writes that byte, so the walk needs
-// no __syncwarp.  Depth 0 (the root) lives in registers; rows 0..2 hold depths 1..3.
+// no __syncwarp.
 template <int kSets>
 struct __align__(16) PlyScratch {
-    float4 zs[3][32];                    // hidden pre-activations of the nodes at depth 1..3 (lane's 4 units)
-    int sv[3][32];                       // node state at depth 1..3 (lane's element)
-    uint32_t lg[4];                      // origins still to try, per depth
-    uint32_t ent[4];                     // N when the node was entered
-    uint32_t mv[4];                      // move taken at each depth: origin | dest << 5
-    uint32_t pad[4];
     uint8_t cache[kSets * 2 * kPlyEntryBytes];
 };
 
@@ -94,62 +91,11 @@ struct PlyEvaluator {
     }
 };
 
-// what the last move changed, in table rows (warp-uniform)
-struct MoveDelta {
-    int row_src, row_dst, row_opp;
-    float c_src, c_dst;
-    bool hit;
-    __device__ __forceinline__ float4 apply(float4 z, const float4 *W4, int lane, int player) const
-    {
-        PlyEvaluator::axpy(z, c_src, W4[row_src * 32 + lane]);
-        PlyEvaluator::axpy(z, c_dst, W4[row_dst * 32 + lane]);
-        if (hit) {
-            PlyEvaluator::axpy(z, -1.0f, W4[row_opp * 32 + lane]);
-            PlyEvaluator::axpy(z, 0.5f, W4[(195 - player) * 32 + lane]);   // the enemy's bar feature
-        }
-        return z;
-    }
-};
-
-// apply a generated move on the lanes and describe it as table rows (game.cpp:624-659)
-__device__ __forceinline__ int apply_with_delta(int v, int lane, int player, int o, int d, MoveDelta &md)
-{
-    const int m = player ? -1 : 1;
-    const int c_me = player ? 4 : 0;
-    const bool from_bar = (o == 0) | (o == 25);
-    const bool off = (d == 0) | (d == 25);
-    const int src = from_bar ? 24 + player : o - 1;
-    const int dst = off ? 26 + player : d - 1;
-    const int sval = __shfl_sync(kFull, v, src);
-    const int dval = __shfl_sync(kFull, v, dst);
-    const bool hit = !off && dval == -m;
-    if (from_bar) {
-        md.row_src = 194 + player;
-        md.c_src = -0.5f;
-    } else {
-        const int n = sval < 0 ? -sval : sval;
-        md.row_src = 8 * src + c_me + (n < 4 ? n : 4) - 1;
-        md.c_src = n >= 4 ? -0.5f : -1.0f;
-    }
-    if (off) {
-        md.row_dst = 196 + player;
-        md.c_dst = off_feature(dval + 1) - off_feature(dval);
-    } else if (hit) {
-        md.row_dst = 8 * dst + c_me;
-        md.c_dst = 1.0f;
-        md.row_opp = 8 * dst + (4 - c_me);
-    } else {
-        const int k = (dval < 0 ? -dval : dval) + 1;
-        md.row_dst = 8 * dst + c_me + (k < 4 ? k : 4) - 1;
-        md.c_dst = k >= 4 ? 0.5f : 1.0f;
-    }
-    md.hit = hit;
-    int nv = v;
-    if (lane == src) nv -= from_bar ? 1 : m;
-    if (lane == dst) nv = off ? nv + 1 : (hit ? m : nv + m);
-    if (hit && lane == 25 - player) nv += 1;
-    return nv;
-}
+// off/15.0 for off = 0..16 (model.py:143-144: float64 divide, stored as float32); [16] pads the k+1 read
+__device__ __constant__ float kOffFeature[17] = {
+    (float)(0 / 15.0), (float)(1 / 15.0), (float)(2 / 15.0), (float)(3 / 15.0), (float)(4 / 15.0), (float)(5 / 15.0),
+    (float)(6 / 15.0), (float)(7 / 15.0), (float)(8 / 15.0), (float)(9 / 15.0), (float)(10 / 15.0), (float)(11 / 15.0),
+    (float)(12 / 15.0), (float)(13 / 15.0), (float)(14 / 15.0), (float)(15 / 15.0), (float)(16 / 15.0)};
 
 // The per-warp cache of one ply.  Two kinds of entries share it:
 //   tag 0      an afterstate that was already scored in this ply (the exact-duplicate filter)
@@ -240,101 +186,219 @@ struct PlyCache {
     }
 };
 
+// ---- the walk ----------------------------------------------------------------------------
+// One template instance per tree depth (the recursion is fully inlined), so the per-depth
+// state of the walk - node state, node pre-activation, origins still to try - lives in
+// registers and every level knows at compile time which die it plays and whether its children
+// can have children.  Work is done as late as possible: a child is first only APPLIED (one
+// shuffle for the landing point, three predicated adds) and probed in the cache; the rows its
+// move changes in the network input, its pre-activation and its value are computed only for
+// afterstates that were not scored yet in this ply and for interior nodes.
 template <int kSets>
-__device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int d1, int d2, const PlyEvaluator &ev,
-                                             PlyScratch<kSets> &S, PlyCache<kSets> &cache)
-{
-    cache.next_ply(lane);
-    const float4 zroot = ev.preactivation(root, lane, player);
-    const bool dbl = d1 == d2;
-    const int maxlen = dbl ? 4 : 2;
-    const int npass = dbl ? 1 : 2;
-    Choice best;
-    best.v = root; best.moves = 0; best.value = __int_as_float(0x7fc00000); best.n_seq = 0; best.n_scored = 0; best.n_visited = 0; best.any = false;
-    int best_len = 0;
-    uint32_t best_mv0 = 0, best_mv1 = 0, best_mv2 = 0, best_mv3 = 0;
+struct PlyWalk {
+    const PlyEvaluator &ev;
+    const PlyCache<kSets> &cache;
+    int lane, player;
+    int unit;             // what one checker of the mover adds to this lane: +-1 on points, +1 on bar/off lanes
+    int c_me;             // feature block of the mover inside a point's 8 features (0 or 4)
+    int dieA, dieB;       // die of even / odd depths
+    uint32_t root_only;   // restricts the root's origins (all ones: no restriction)
+    float4 zroot;
+    // result
+    float best_key;       // value, negated for PLAYER2 (who minimises): always maximised, strict > keeps the first
+    int best_v;
+    uint32_t best_path;   // origins 5 bits each, length << 20
+    int n_seq, n_scored, n_visited;
 
-    for (int pass = 0; pass < npass; pass++) {
-        const int dieA = pass ? d2 : d1, dieB = pass ? d1 : d2;
-        int depth = 0, cur = root;
-        bool entering = true;
-        MoveDelta md;
-        md.row_src = md.row_dst = md.row_opp = 0; md.c_src = md.c_dst = 0.f; md.hit = false;
-        for (;;) {
-            if (entering) {
-                entering = false;
-                uint32_t legal = 0;
-                if (depth < maxlen) {
-                    bool on_bar;
-                    const Masks mk = masks_on_lanes(cur, player, on_bar);
-                    legal = legal_origins(player, (depth & 1) ? dieB : dieA, mk, on_bar ? 1 : 0);
-                }
-                if (legal == 0) {
-                    if (dbl || depth > 0) {                       // a sequence ends here
-                        best.n_seq++;
-                        if (!cache.seen_or_insert(cur, lane)) {
-                            const float4 z = depth == 0 ? zroot : md.apply(depth == 1 ? zroot : S.zs[depth - 2][lane], ev.W4, lane, player);
-                            const float val = ev.finish(z);
-                            best.n_scored++;
-                            if (!best.any || (player == 0 ? val > best.value : val < best.value)) {
-                                best.any = true; best.value = val; best.v = cur; best_len = depth;
-                                best_mv0 = S.mv[0]; best_mv1 = S.mv[1]; best_mv2 = S.mv[2]; best_mv3 = S.mv[3];
-                            }
-                        }
-                    }
-                    if (depth == 0) break;
-                    depth--;
-                    continue;
-                }
-                if (dbl && depth >= 2) {                           // same position, same dice left: seen before?
-                    const int below = cache.lookup(cur, depth, lane);
-                    if (below >= 0) {
-                        best.n_seq += below;
-                        depth--;
-                        continue;
-                    }
-                }
-                if (depth > 0) {
-                    S.zs[depth - 1][lane] = md.apply(depth == 1 ? zroot : S.zs[depth - 2][lane], ev.W4, lane, player);
-                    S.sv[depth - 1][lane] = cur;
-                }
-                S.lg[depth] = legal;
-                S.ent[depth] = (uint32_t)best.n_seq;
+    __device__ __forceinline__ PlyWalk(const PlyEvaluator &e, const PlyCache<kSets> &c, int ln, int pl)
+        : ev(e), cache(c), lane(ln), player(pl)
+    {
+        unit = ln < 24 ? (pl ? -1 : 1) : 1;
+        c_me = pl ? 4 : 0;
+        root_only = kFull;
+        best_key = __int_as_float(0xff800000);          // -inf
+        best_v = 0; best_path = 0;
+        n_seq = n_scored = n_visited = 0;
+    }
+
+    // legal origins of the mover on state v (bgx_core.h legal_origins) from two ballots
+    __device__ __forceinline__ uint32_t legal_here(int v, int die) const
+    {
+        const int rel = lane < 24 ? v * unit : v;                         // mover-relative count; bar/off lanes as they are
+        const uint32_t own = __ballot_sync(kFull, rel > 0);
+        const uint32_t blk = __ballot_sync(kFull, rel < -1) & 0xFFFFFFu;  // points the mover cannot land on
+        const uint32_t occ = (own & 0xFFFFFFu) << 1, wall = blk << 1;
+        const bool on_bar = (own >> (24 + player)) & 1u;
+        if (player == 0) {
+            if (on_bar) return ((wall >> die) & 1u) ? 0u : 1u;
+            uint32_t legal = occ & ((~wall & kPoints) >> die);
+            if (occ != 0 && (occ & kP1Outside) == 0) {
+                legal |= occ & (1u << (25 - die));
+                const int hi = highest_bit(occ);
+                if (hi + die > 25) legal |= 1u << hi;
             }
-            const uint32_t rest = S.lg[depth];
-            if (rest == 0) {                                       // all children done
-                if (dbl && depth >= 2) {
-                    cache.store(S.sv[depth - 1][lane], depth, best.n_seq - (int)S.ent[depth], lane);
-                }
-                if (depth == 0) break;
-                depth--;
-                continue;
+            return legal;
+        }
+        if (on_bar) return ((wall >> (25 - die)) & 1u) ? 0u : (1u << 25);
+        uint32_t legal = occ & ((~wall & kPoints) << die) & kPoints;
+        if (occ != 0 && (occ & kP2Outside) == 0) {
+            legal |= occ & (1u << die);
+            const uint32_t any = (__ballot_sync(kFull, v != 0) & 0xFFFFFFu) << 1;   // either colour
+            const int hi = highest_bit(any & kP2Window);
+            if (hi < die && ((occ >> hi) & 1u)) legal |= 1u << hi;
+        }
+        return legal;
+    }
+
+    // lanes of the origin / destination codes
+    __device__ __forceinline__ int src_lane(int o) const { return (o == (player ? 25 : 0)) ? 24 + player : o - 1; }
+    __device__ __forceinline__ int dst_lane(int d) const { return (d == (player ? 0 : 25)) ? 26 + player : d - 1; }
+
+    // the child state (game.cpp:624-659); dval = what stood on the landing lane
+    __device__ __forceinline__ int apply(int v, int o, int d, int &dval) const
+    {
+        const int src = src_lane(o), dst = dst_lane(d);
+        dval = __shfl_sync(kFull, v, dst);
+        const bool hit = dst < 24 && dval * unit_of_points() == -1;
+        int t = lane == dst ? (hit ? 2 * unit : unit) : 0;
+        t -= lane == src ? unit : 0;
+        t += (hit && lane == 25 - player) ? 1 : 0;
+        return v + t;
+    }
+    __device__ __forceinline__ int unit_of_points() const { return player ? -1 : 1; }
+
+    // pre-activation of the child reached from (vpar, zpar) by o -> d: 2 rows, 4 after a hit
+    __device__ __forceinline__ float4 child_z(const float4 &zpar, int vpar, int o, int d, int dval) const
+    {
+        const int src = src_lane(o), dst = dst_lane(d);
+        const int sval = __shfl_sync(kFull, vpar, src);
+        const float4 *W4 = ev.W4 + lane;
+        float4 z = zpar;
+        int row;
+        float c;
+        if (src >= 24) { row = 194 + player; c = -0.5f; }
+        else {
+            const int n = sval < 0 ? -sval : sval;
+            row = 8 * src + c_me + (n < 4 ? n : 4) - 1;
+            c = n >= 4 ? -0.5f : -1.0f;
+        }
+        PlyEvaluator::axpy(z, c, W4[row * 32]);
+        if (dst >= 24) {
+            row = 196 + player;
+            c = kOffFeature[dval + 1] - kOffFeature[dval];
+        } else if (dval * unit_of_points() == -1) {                          // a hit
+            PlyEvaluator::axpy(z, -1.0f, W4[(8 * dst + 4 - c_me) * 32]);   // the blot leaves ...
+            PlyEvaluator::axpy(z, 0.5f, W4[(195 - player) * 32]);          // ... for the enemy's bar
+            row = 8 * dst + c_me;
+            c = 1.0f;
+        } else {
+            const int k = (dval < 0 ? -dval : dval) + 1;
+            row = 8 * dst + c_me + (k < 4 ? k : 4) - 1;
+            c = k >= 4 ? 0.5f : 1.0f;
+        }
+        PlyEvaluator::axpy(z, c, W4[row * 32]);
+        return z;
+    }
+
+    // a legal turn sequence ends on v (reference order); score it unless this exact state was scored before
+    template <int D>
+    __device__ __forceinline__ void leaf(int v, const float4 &zpar, int vpar, int o, int d, int dval, uint32_t path)
+    {
+        n_seq++;
+        const typename PlyCache<kSets>::Probe pr = cache.probe(v, 0, lane);
+        if (pr.hit()) return;
+        cache.write(pr, v, 0, 0, lane);
+        const float4 z = D == 0 ? zroot : child_z(zpar, vpar, o, d, dval);
+        const float val = ev.finish(z);
+        n_scored++;
+        const float key = player ? -val : val;
+        if (key > best_key) { best_key = key; best_v = v; best_path = path | ((uint32_t)D << 20); }
+    }
+
+    template <int D, bool kDbl>
+    __device__ __forceinline__ void visit(int v, const float4 &zpar, int vpar, int o, int d, int dval, uint32_t path)
+    {
+        constexpr int kMax = kDbl ? 4 : 2;
+        uint32_t legal = 0;
+        if constexpr (D < kMax) {
+            legal = legal_here(v, (D & 1) ? dieB : dieA);
+            if (D == 0) legal &= root_only;
+        }
+        if (legal == 0) {
+            // a node without a move ends the sequence (game.cpp:117-121, 148-151); the root of a
+            // non-double pass emits nothing
+            if (kDbl || D > 0) leaf<D>(v, zpar, vpar, o, d, dval, path);
+            return;
+        }
+        if constexpr (D < kMax) {
+            if constexpr (kDbl && D >= 2) {                  // same position, same dice left: seen before?
+                const int below = cache.lookup(v, D, lane);
+                if (below >= 0) { n_seq += below; return; }
             }
-            const int o = lowest_bit(rest);
-            S.lg[depth] = rest & (rest - 1);
-            const int d = destination(player, o, (depth & 1) ? dieB : dieA);
-            cur = apply_with_delta(depth == 0 ? root : S.sv[depth - 1][lane], lane, player, o, d, md);
-            best.n_visited++;
-            S.mv[depth] = (uint32_t)(o | (d << 5));
-            depth++;
-            entering = true;
+            const float4 z = D == 0 ? zroot : child_z(zpar, vpar, o, d, dval);
+            const int entered = n_seq;
+            const int die = (D & 1) ? dieB : dieA;
+            do {
+                const int oc = lowest_bit(legal);
+                legal &= legal - 1;
+                const int dc = destination(player, oc, die);
+                int dv;
+                const int child = apply(v, oc, dc, dv);
+                n_visited++;
+                visit<D + 1, kDbl>(child, z, v, oc, dc, dv, path | ((uint32_t)oc << (5 * D)));
+            } while (legal);
+            if constexpr (kDbl && D >= 2) cache.store(v, D, n_seq - entered, lane);
         }
     }
-    if (best.any) {
-        uint64_t mv = (uint64_t)best_len << 40;
-        if (best_len > 0) mv |= (uint64_t)best_mv0;
-        if (best_len > 1) mv |= (uint64_t)best_mv1 << 10;
-        if (best_len > 2) mv |= (uint64_t)best_mv2 << 20;
-        if (best_len > 3) mv |= (uint64_t)best_mv3 << 30;
-        best.moves = mv;
+};
+
+// root_only: bit mask over the root's origin codes (work splitting of big doubles); kFull = the whole turn
+template <int kSets>
+__device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int d1, int d2, const PlyEvaluator &ev,
+                                             PlyCache<kSets> &cache, uint32_t root_only = kFull)
+{
+    cache.next_ply(lane);
+    PlyWalk<kSets> w(ev, cache, lane, player);
+    w.root_only = root_only;
+    w.zroot = ev.preactivation(root, lane, player);
+    uint32_t best_pass = 0;
+    if (d1 == d2) {
+        w.dieA = w.dieB = d1;
+        w.template visit<0, true>(root, w.zroot, root, 0, 0, 0, 0u);
+    } else {
+        float key1 = 0.f;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {          // game.cpp:143-188: d1 first, then d2 first
+            w.dieA = pass ? d2 : d1;
+            w.dieB = pass ? d1 : d2;
+            if (pass) key1 = w.best_key;
+            w.template visit<0, false>(root, w.zroot, root, 0, 0, 0, 0u);
+        }
+        best_pass = w.best_key > key1 ? 1u : 0u;
     }
+    Choice best;
+    best.any = w.n_seq > 0;
+    best.v = best.any ? w.best_v : root;
+    best.value = best.any ? (player ? -w.best_key : w.best_key) : __int_as_float(0x7fc00000);
+    best.n_seq = w.n_seq; best.n_scored = w.n_scored; best.n_visited = w.n_visited;
+    uint64_t mv = 0;
+    if (best.any) {
+        const int len = (int)(w.best_path >> 20);
+        mv = (uint64_t)len << 40;
+        for (int j = 0; j < len; j++) {
+            const int o = (int)((w.best_path >> (5 * j)) & 31u);
+            const int die = ((j & 1) != (int)best_pass) ? d2 : d1;
+            mv |= pack_move(o, destination(player, o, die), j);
+        }
+    }
+    best.moves = mv;
     return best;
 }
 
 // greedy or exploring ply; kExplore = false compiles the epsilon path out (smaller, fewer registers)
 template <int kSets, bool kExplore>
 __device__ __forceinline__ Choice choose_ply_fast(int root, int lane, int player, int d1, int d2, const PlyEvaluator &ev,
-                                                  PlyScratch<kSets> &S, PlyCache<kSets> &cache, bool explore, uint32_t u)
+                                                  PlyCache<kSets> &cache, bool explore, uint32_t u)
 {
     if (kExplore && explore) {
         CountLeaf cnt;
@@ -349,7 +413,7 @@ __device__ __forceinline__ Choice choose_ply_fast(int root, int lane, int player
         }
         return c;
     }
-    return greedy_ply<kSets>(root, lane, player, d1, d2, ev, S, cache);
+    return greedy_ply<kSets>(root, lane, player, d1, d2, ev, cache);
 }
 
 } // namespace bgx
