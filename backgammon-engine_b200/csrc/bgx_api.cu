@@ -29,6 +29,7 @@ struct bgx_engine {
     unsigned long long *counter = nullptr;   // work queue
     unsigned long long *stats = nullptr;     // 8 counters
     double *dstats = nullptr;                // TD: sum of squared errors
+    StealResult *steal = nullptr;            // [CTA][warp][16] sub-tree results of shared doubles (bgx_ply.cuh)
     uint32_t *uniq_tables = nullptr;
     uint32_t *uniq_gens = nullptr;           // per-warp generation of the exact-dedup tables
     int uniq_grid = 0;
@@ -134,6 +135,7 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaMalloc(&e->counter, sizeof(unsigned long long)));
     CU(cudaMalloc(&e->stats, 8 * sizeof(unsigned long long)));
     CU(cudaMalloc(&e->dstats, 2 * sizeof(double)));
+    CU(cudaMalloc(&e->steal, (size_t)e->sm_count * 32 * kStealMaxResults * sizeof(StealResult)));
     CU(cudaEventCreate(&e->ev0));
     CU(cudaEventCreate(&e->ev1));
     CU(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, kEvalSmem));
@@ -162,7 +164,7 @@ int bgx_destroy(bgx_engine *e)
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < bgx_engine::kScratch; i++) cudaFree(e->dbuf[i]);
-    cudaFree(e->flat); cudaFree(e->table); cudaFree(e->wt); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats);
+    cudaFree(e->flat); cudaFree(e->table); cudaFree(e->wt); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats); cudaFree(e->steal);
     cudaFree(e->uniq_tables); cudaFree(e->uniq_gens); cudaFree(e->slots); cudaFree(e->traj_pre); cudaFree(e->traj_chosen);
     cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
@@ -412,7 +414,7 @@ int bgx_select_moves(bgx_engine *e, const int8_t *queries, int64_t n, float epsi
     tick(e);
 #define BGX_LAUNCH_SELECT(W, S, X)                                                                              \
     k_select<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(queries, n, epsilon, (uint32_t)seed, \
-                                                                             (uint32_t)(seed >> 32), out, e->wt, e->flat, e->counter)
+                                                                             (uint32_t)(seed >> 32), out, e->wt, e->flat, e->counter, e->steal)
     const bool ex = epsilon > 0.f;
     if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 126, true); else BGX_LAUNCH_SELECT(16, 126, false); }
     else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 84, true); else BGX_LAUNCH_SELECT(24, 84, false); }
@@ -516,7 +518,7 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
     tick(e);
-#define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->wt, e->flat)
+#define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->wt, e->flat, e->steal)
     const bool ex = epsilon > 0.f;
     if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 126, true); else BGX_LAUNCH_SELFPLAY(16, 126, false); }
     else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 84, true); else BGX_LAUNCH_SELFPLAY(24, 84, false); }

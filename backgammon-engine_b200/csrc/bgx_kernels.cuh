@@ -10,7 +10,7 @@ constexpr int kGameWarps = 16;                     // warps per CTA in the warp-
 constexpr int kGameThreads = kGameWarps * 32;
 // dynamic shared memory of the fused ply kernels: weight table + per-warp scratch + barrier
 template <int kWarps, int kSets>
-constexpr int ply_smem() { return kTableBytes + kWarps * (int)sizeof(PlyScratch<kSets>) + 16; }
+constexpr int ply_smem() { return kTableBytes + kWarps * (int)sizeof(PlyScratch<kSets>) + (int)sizeof(StealShared<kWarps>) + 16; }
 constexpr int kEvalSmem = kTableBytes + 16;            // k_evaluate: table + barrier
 
 // exact-dedup table of the summary kernel: per warp, in global memory (L2 resident)
@@ -275,36 +275,83 @@ __device__ __forceinline__ void store_choice(const SelectOut &o, long long q, co
     }
 }
 
+// shared-memory carve-up of the fused ply kernels: weight table | per-warp caches | sharing slots | barrier
+template <int kWarps, int kSets>
+struct PlySmem {
+    float *table;
+    PlyScratch<kSets> *scratch;
+    StealShared<kWarps> *share;
+    uint64_t *bar;
+    __device__ __forceinline__ explicit PlySmem(unsigned char *smem)
+    {
+        table = reinterpret_cast<float *>(smem);
+        scratch = reinterpret_cast<PlyScratch<kSets> *>(smem + kTableBytes);
+        share = reinterpret_cast<StealShared<kWarps> *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>));
+        bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>) + sizeof(StealShared<kWarps>));
+    }
+    // every thread calls this before stage_table(), whose __syncthreads publishes it
+    __device__ __forceinline__ void init_share() const
+    {
+        if (threadIdx.x < kWarps) {
+            share->slot[threadIdx.x].legal0 = 0;
+            share->slot[threadIdx.x].pending = 0;
+            share->slot[threadIdx.x].nres = 0;
+        }
+        if (threadIdx.x == 0) share->active = kWarps;
+    }
+};
+
 template <int kWarps, int kSets, bool kExplore>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_t seed_lo, uint32_t seed_hi,
-         SelectOut out, const float *__restrict__ Wt, const float *__restrict__ flat, unsigned long long *counter)
+         SelectOut out, const float *__restrict__ Wt, const float *__restrict__ flat, unsigned long long *counter,
+         StealResult *__restrict__ steal)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    float *sT = reinterpret_cast<float *>(smem);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>));
+    const PlySmem<kWarps, kSets> sm(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     PlyCache<kSets> cache;
-    cache.reset(reinterpret_cast<PlyScratch<kSets> *>(smem + kTableBytes)[warp].cache, lane);
-    stage_table(sT, Wt, bar);
+    cache.reset(sm.scratch[warp].cache, lane);
+    sm.init_share();
+    stage_table(sm.table, Wt, sm.bar);
     PlyEvaluator ev;
-    ev.W4 = reinterpret_cast<const float4 *>(sT);
+    ev.W4 = reinterpret_cast<const float4 *>(sm.table);
     ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, lane);
+    StealSlot *mine = &sm.share->slot[warp];
+    StealResult *cta_results = steal + (size_t)blockIdx.x * kWarps * kStealMaxResults;
+    StealResult *my_results = cta_results + warp * kStealMaxResults;
+    bool helping = false;
     for (;;) {
-        const long long q = claim(counter, lane);
-        if (q >= n) break;
-        const int b = load_record_byte(queries + q * 32, lane);
-        const int root = lane < 28 ? b : 0;
-        const int player = __shfl_sync(kFull, b, 28) ? 1 : 0, d1 = __shfl_sync(kFull, b, 29), d2 = __shfl_sync(kFull, b, 30);
+        int root = 0, player = 0, d1 = 0, d2 = 0, vw = 0;
+        uint32_t only = kFull, u = 0;
+        long long q = 0;
         bool explore = false;
-        uint32_t u = 0;
-        if (kExplore && epsilon > 0.f) {
-            const Philox r = philox4x32_10(seed_lo, seed_hi, 0u, (uint32_t)q, (uint32_t)((unsigned long long)q >> 32), 2u);
-            explore = (float)r.x[0] * 2.3283064365386963e-10f < epsilon;
-            u = r.x[1];
+        if (!helping) {
+            q = claim(counter, lane);
+            if (q >= n) {                                   // queue empty: help the owners of big doubles
+                helping = true;
+                if (lane == 0) atomicSub(&sm.share->active, 1);
+                continue;
+            }
+            const int b = load_record_byte(queries + q * 32, lane);
+            root = lane < 28 ? b : 0;
+            player = __shfl_sync(kFull, b, 28) ? 1 : 0; d1 = __shfl_sync(kFull, b, 29); d2 = __shfl_sync(kFull, b, 30);
+            if (kExplore && epsilon > 0.f) {
+                const Philox r = philox4x32_10(seed_lo, seed_hi, 0u, (uint32_t)q, (uint32_t)((unsigned long long)q >> 32), 2u);
+                explore = (float)r.x[0] * 2.3283064365386963e-10f < epsilon;
+                u = r.x[1];
+            }
+        } else {
+            bool done;
+            only = take_child<kWarps>(sm.share, lane, vw, root, player, d1, done);
+            if (done) break;
+            if (only == 0) continue;
+            d2 = d1;
         }
-        const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, player, d1, d2, ev, cache, explore, u);
-        store_choice(out, q, c, lane, player);
+        const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, player, d1, d2, ev, cache, explore, u, only,
+                                                          helping ? nullptr : mine, my_results);
+        if (helping) deliver_child<kWarps>(sm.share, cta_results, vw, only, c, lane);
+        else store_choice(out, q, c, lane, player);
     }
 }
 
@@ -327,54 +374,86 @@ struct SelfplayParams {
 
 template <int kWarps, int kSets, bool kExplore>
 __global__ void __launch_bounds__(kWarps * 32, 1)
-k_selfplay(SelfplayParams p, const float *__restrict__ Wt, const float *__restrict__ flat)
+k_selfplay(SelfplayParams p, const float *__restrict__ Wt, const float *__restrict__ flat, StealResult *__restrict__ steal)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    float *sT = reinterpret_cast<float *>(smem);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>));
+    const PlySmem<kWarps, kSets> sm(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     PlyCache<kSets> cache;
-    cache.reset(reinterpret_cast<PlyScratch<kSets> *>(smem + kTableBytes)[warp].cache, lane);
-    stage_table(sT, Wt, bar);
+    cache.reset(sm.scratch[warp].cache, lane);
+    sm.init_share();
+    stage_table(sm.table, Wt, sm.bar);
     PlyEvaluator ev;
-    ev.W4 = reinterpret_cast<const float4 *>(sT);
+    ev.W4 = reinterpret_cast<const float4 *>(sm.table);
     ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, lane);
+    StealSlot *mine = &sm.share->slot[warp];
+    StealResult *cta_results = steal + (size_t)blockIdx.x * kWarps * kStealMaxResults;
+    StealResult *my_results = cta_results + warp * kStealMaxResults;
 
     unsigned long long s_plies = 0, s_seq = 0, s_scored = 0, s_fin = 0, s_p1 = 0, s_trunc = 0, s_visited = 0;
+    const int budget = p.round_mode ? 0x7fffffff : p.n_plies;
+    bool helping = false, seated = false;
+    long long slot = 0;
+    int v = 0, player = 0, status = kRunning, ply = 0, step = 0;
+    unsigned long long gid = 0;
+    // one iteration = one ply: of the slot this warp is seated at, or (queue empty) of a sub-tree taken from a neighbour
     for (;;) {
-        const long long slot = claim(p.counter, lane);
-        if (slot >= p.n_slots) break;
-        int8_t *rec = p.slots + slot * 32;
-        const int b = load_record_byte(rec, lane);
-        int v = lane < 28 ? b : 0;
-        int player = __shfl_sync(kFull, b, 28) ? 1 : 0;
-        int status = __shfl_sync(kFull, b, 31);
-        int ply = p.ply[slot];
-        unsigned long long gid = (unsigned long long)p.game_id[slot];
-        if (p.round_mode && status != kRunning) continue;
-        const int budget = p.round_mode ? 0x7fffffff : p.n_plies;
-        for (int step = 0; step < budget; step++) {
+        int root = 0, mover = 0, d1 = 0, d2 = 0, vw = 0;
+        uint32_t only = kFull, u = 0;
+        bool explore = false, rec_traj = false;
+        if (!helping) {
+            if (!seated) {
+                slot = claim(p.counter, lane);
+                if (slot >= p.n_slots) {
+                    helping = true;
+                    if (lane == 0) atomicSub(&sm.share->active, 1);
+                    continue;
+                }
+                const int b = load_record_byte(p.slots + slot * 32, lane);
+                v = lane < 28 ? b : 0;
+                player = __shfl_sync(kFull, b, 28) ? 1 : 0;
+                status = __shfl_sync(kFull, b, 31);
+                ply = p.ply[slot];
+                gid = (unsigned long long)p.game_id[slot];
+                if (p.round_mode && status != kRunning) continue;
+                step = 0;
+                seated = true;
+            }
             if (p.round_mode && p.traj_cap > 0 && ply >= p.traj_cap) {   // the log is full: give the game up
                 status = kTruncated;
                 s_trunc++;
-                break;
+                seated = false;
+            } else {
+                const Philox r = philox4x32_10(p.seed_lo, p.seed_hi, (uint32_t)ply, (uint32_t)gid, (uint32_t)(gid >> 32), 0u);
+                d1 = die_of(r.x[0]); d2 = die_of(r.x[1]);
+                rec_traj = p.traj_pre != nullptr && ply < p.traj_cap && status == kRunning;
+                if (rec_traj) {
+                    int8_t *t = p.traj_pre + ((size_t)slot * p.traj_cap + ply) * 32;
+                    const int out = lane < 28 ? v : (lane == 28 ? player : (lane == 29 ? d1 : (lane == 30 ? d2 : 0)));
+                    t[lane] = (int8_t)out;                           // train.py:105-106
+                }
+                if (kExplore && p.epsilon > 0.f) {
+                    const Philox e = philox4x32_10(p.seed_lo, p.seed_hi, (uint32_t)ply, (uint32_t)gid, (uint32_t)(gid >> 32), 2u);
+                    explore = (float)e.x[0] * 2.3283064365386963e-10f < p.epsilon;
+                    u = e.x[1];
+                }
+                root = v;
+                mover = player;
             }
-            const Philox r = philox4x32_10(p.seed_lo, p.seed_hi, (uint32_t)ply, (uint32_t)gid, (uint32_t)(gid >> 32), 0u);
-            const int d1 = die_of(r.x[0]), d2 = die_of(r.x[1]);
-            const bool rec_traj = p.traj_pre != nullptr && ply < p.traj_cap && status == kRunning;
-            if (rec_traj) {
-                int8_t *t = p.traj_pre + ((size_t)slot * p.traj_cap + ply) * 32;
-                const int out = lane < 28 ? v : (lane == 28 ? player : (lane == 29 ? d1 : (lane == 30 ? d2 : 0)));
-                t[lane] = (int8_t)out;                               // train.py:105-106
+        } else {
+            bool done;
+            only = take_child<kWarps>(sm.share, lane, vw, root, mover, d1, done);
+            if (done) break;
+            if (only == 0) continue;
+            d2 = d1;
+        }
+        if (helping || seated) {
+            const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, mover, d1, d2, ev, cache, explore, u, only,
+                                                              helping ? nullptr : mine, my_results);   // model.py:180-222
+            if (helping) {
+                deliver_child<kWarps>(sm.share, cta_results, vw, only, c, lane);
+                continue;
             }
-            bool explore = false;
-            uint32_t u = 0;
-            if (kExplore && p.epsilon > 0.f) {
-                const Philox e = philox4x32_10(p.seed_lo, p.seed_hi, (uint32_t)ply, (uint32_t)gid, (uint32_t)(gid >> 32), 2u);
-                explore = (float)e.x[0] * 2.3283064365386963e-10f < p.epsilon;
-                u = e.x[1];
-            }
-            const Choice c = choose_ply_fast<kSets, kExplore>(v, lane, player, d1, d2, ev, cache, explore, u);   // model.py:180-222
             v = c.v;
             s_plies++;
             s_seq += (unsigned long long)c.n_seq;
@@ -390,27 +469,32 @@ k_selfplay(SelfplayParams p, const float *__restrict__ Wt, const float *__restri
             const int off1 = __shfl_sync(kFull, v, 26), off2 = __shfl_sync(kFull, v, 27);
             const int winner = off1 == 15 ? 0 : (off2 == 15 ? 1 : -1);
             ply++;
+            step++;
             if (winner >= 0) {
                 s_fin++;
                 s_p1 += winner == 0;
                 if (p.round_mode) {
                     status = winner == 0 ? kP1Won : kP2Won;
-                    break;
+                    seated = false;
+                } else {
+                    gid += (unsigned long long)p.id_stride;          // restart in place
+                    v = start_value(lane);
+                    player = first_mover_of(p.seed_lo, p.seed_hi, gid, p.first_mover);
+                    ply = 0;
+                    status = kRunning;
                 }
-                gid += (unsigned long long)p.id_stride;              // restart in place
-                v = start_value(lane);
-                player = first_mover_of(p.seed_lo, p.seed_hi, gid, p.first_mover);
-                ply = 0;
-                status = kRunning;
             } else {
                 player ^= 1;                                         // train.py:119-120
             }
+            if (step >= budget) seated = false;
         }
-        const int out = lane < 28 ? v : (lane == 28 ? player : (lane == 31 ? status : 0));
-        rec[lane] = (int8_t)out;
-        if (lane == 0) {
-            p.ply[slot] = ply;
-            p.game_id[slot] = (long long)gid;
+        if (!seated) {                                               // leave the slot: write it back
+            const int out = lane < 28 ? v : (lane == 28 ? player : (lane == 31 ? status : 0));
+            p.slots[slot * 32 + lane] = (int8_t)out;
+            if (lane == 0) {
+                p.ply[slot] = ply;
+                p.game_id[slot] = (long long)gid;
+            }
         }
     }
     if (lane == 0) {

@@ -37,7 +37,15 @@ struct __align__(16) PlyScratch {
     uint8_t cache[kSets * 2 * kPlyEntryBytes];
 };
 
-__device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+// 1 / (1 + 2^(-z log2 e)) on the SFU: ex2.approx + rcp.approx (flush-to-zero: 2^x underflows to 0 exactly
+// where 1 + 2^x rounds to 1 anyway), ~3e-7 relative error, 4 instructions
+__device__ __forceinline__ float fast_sigmoid(float z)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
 
 struct PlyEvaluator {
     const float4 *W4;    // shared memory, raw feature-major table Wt[198][32] float4
@@ -352,19 +360,113 @@ struct PlyWalk {
     }
 };
 
-// root_only: bit mask over the root's origin codes (work splitting of big doubles); kFull = the whole turn
+// ---- sharing the sub-trees of a big double inside the CTA --------------------------------
+// A double with many first moves has a turn tree of up to ~12 k sequences: walked by one warp
+// it is the tail of every launch.  The owner of such a ply PUBLISHES the origins of its root in
+// its shared-memory slot and pops them lowest first; warps of the same CTA that have run out of
+// queue work pop the highest one, walk that sub-tree with their own cache and deliver the result;
+// the owner merges.  Exactness: every root child is walked by exactly one warp in reference
+// order, the merge prefers the better value and, on equal values, the lower root origin, which
+// is the reference's first-index rule (model.py:212-213); N is the sum of the parts.
+constexpr int kStealMinChildren = 4;     // root origins from which a double is worth publishing
+constexpr int kStealMaxResults = 16;     // >= the 15 origins a root can have
+
+struct StealSlot {                       // shared memory, one per warp
+    uint32_t legal0;                     // root origins nobody has taken yet (0: nothing to take)
+    int32_t pending;                     // taken sub-trees still being walked by helpers
+    uint32_t nres;                       // results delivered for the current ply
+    uint32_t meta;                       // player | die << 8
+    int8_t root[32];
+};
+
+struct __align__(16) StealResult {       // global memory, [CTA][warp][kStealMaxResults]
+    float value;
+    int32_t any, n_seq, n_scored, n_visited, origin;
+    unsigned long long moves;
+    int8_t v[32];
+};
+
+template <int kWarps>
+struct StealShared {
+    StealSlot slot[kWarps];
+    int32_t active;                      // warps that still own queue work
+    int32_t pad[3];
+};
+
+__device__ __forceinline__ Choice finish_choice(const uint32_t best_path, float best_key, int best_v, int n_seq, int n_scored,
+                                                int n_visited, int root, int player, int d1, int d2, uint32_t best_pass)
+{
+    Choice best;
+    best.any = n_seq > 0;
+    best.v = best.any ? best_v : root;
+    best.value = best.any ? (player ? -best_key : best_key) : __int_as_float(0x7fc00000);
+    best.n_seq = n_seq; best.n_scored = n_scored; best.n_visited = n_visited;
+    uint64_t mv = 0;
+    if (best.any) {
+        const int len = (int)(best_path >> 20);
+        mv = (uint64_t)len << 40;
+        for (int j = 0; j < len; j++) {
+            const int o = (int)((best_path >> (5 * j)) & 31u);
+            const int die = ((j & 1) != (int)best_pass) ? d2 : d1;
+            mv |= pack_move(o, destination(player, o, die), j);
+        }
+    }
+    best.moves = mv;
+    return best;
+}
+
+// root_only: bit mask over the root's origin codes (a helper walks one stolen child); kFull = the whole turn.
+// slot/results: the caller's sharing slot (nullptr: never publish).
 template <int kSets>
 __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int d1, int d2, const PlyEvaluator &ev,
-                                             PlyCache<kSets> &cache, uint32_t root_only = kFull)
+                                             PlyCache<kSets> &cache, uint32_t root_only = kFull,
+                                             StealSlot *slot = nullptr, StealResult *results = nullptr)
 {
     cache.next_ply(lane);
     PlyWalk<kSets> w(ev, cache, lane, player);
     w.root_only = root_only;
     w.zroot = ev.preactivation(root, lane, player);
     uint32_t best_pass = 0;
+    bool shared = false;
     if (d1 == d2) {
         w.dieA = w.dieB = d1;
-        w.template visit<0, true>(root, w.zroot, root, 0, 0, 0, 0u);
+        uint32_t legal = w.legal_here(root, d1) & root_only;
+        if (legal == 0) {
+            w.template leaf<0>(root, w.zroot, root, 0, 0, 0, 0u);        // no move at all: the empty sequence
+        } else {
+            shared = slot != nullptr && __popc(legal) >= kStealMinChildren;
+            if (shared) {                                                // publish the root's origins
+                slot->root[lane] = (int8_t)root;
+                if (lane == 0) { slot->meta = (uint32_t)player | ((uint32_t)d1 << 8); slot->nres = 0; }
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) atomicExch(&slot->legal0, legal);
+            }
+            for (;;) {
+                uint32_t bit = 0;
+                if (shared) {                                            // pop the lowest origin still there
+                    if (lane == 0) {
+                        for (;;) {
+                            const uint32_t old = *(volatile uint32_t *)&slot->legal0;
+                            if (old == 0) break;
+                            const uint32_t low = old & (0u - old);
+                            if (atomicAnd(&slot->legal0, ~low) & low) { bit = low; break; }
+                        }
+                    }
+                    bit = __shfl_sync(kFull, bit, 0);
+                } else {
+                    bit = legal & (0u - legal);
+                    legal &= legal - 1;
+                }
+                if (bit == 0) break;
+                const int oc = lowest_bit(bit);
+                const int dc = destination(player, oc, d1);
+                int dv;
+                const int child = w.apply(root, oc, dc, dv);
+                w.n_visited++;
+                w.template visit<1, true>(child, w.zroot, root, oc, dc, dv, (uint32_t)oc);
+            }
+        }
     } else {
         float key1 = 0.f;
 #pragma unroll 1
@@ -376,29 +478,94 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
         }
         best_pass = w.best_key > key1 ? 1u : 0u;
     }
-    Choice best;
-    best.any = w.n_seq > 0;
-    best.v = best.any ? w.best_v : root;
-    best.value = best.any ? (player ? -w.best_key : w.best_key) : __int_as_float(0x7fc00000);
-    best.n_seq = w.n_seq; best.n_scored = w.n_scored; best.n_visited = w.n_visited;
-    uint64_t mv = 0;
-    if (best.any) {
-        const int len = (int)(w.best_path >> 20);
-        mv = (uint64_t)len << 40;
-        for (int j = 0; j < len; j++) {
-            const int o = (int)((w.best_path >> (5 * j)) & 31u);
-            const int die = ((j & 1) != (int)best_pass) ? d2 : d1;
-            mv |= pack_move(o, destination(player, o, die), j);
+    Choice best = finish_choice(w.best_path, w.best_key, w.best_v, w.n_seq, w.n_scored, w.n_visited, root, player, d1, d2, best_pass);
+    if (shared) {
+        // wait for the helpers, then merge their sub-trees: better value, then lower root origin
+        while (*(volatile int32_t *)&slot->pending != 0) __nanosleep(64);
+        __threadfence_block();
+        const int n = (int)*(volatile uint32_t *)&slot->nres;
+        int best_origin = best.any ? (int)(best.moves & 31u) : 99;
+        for (int i = 0; i < n; i++) {
+            const StealResult *r = results + i;
+            const int any = __ldcg(&r->any);
+            best.n_seq += __ldcg(&r->n_seq);
+            best.n_scored += __ldcg(&r->n_scored);
+            best.n_visited += __ldcg(&r->n_visited);
+            if (!any) continue;
+            const float val = __ldcg(&r->value);
+            const int org = __ldcg(&r->origin);
+            const bool better = !best.any || (player ? val < best.value : val > best.value) || (val == best.value && org < best_origin);
+            if (better) {
+                best.any = true; best.value = val; best_origin = org;
+                best.moves = __ldcg(&r->moves);
+                best.v = (int)__ldcg(reinterpret_cast<const signed char *>(r->v) + lane);
+            }
         }
     }
-    best.moves = mv;
     return best;
+}
+
+// What a warp does once the work queue is empty: help the owners of published doubles in its CTA
+// until no warp of the CTA owns queue work any more.  take_child() returns the origin bit it took
+// from warp `vw` (filling root / player / die), 0 when there is nothing to take right now, and
+// sets `done` once every warp of the CTA has left the queue.
+template <int kWarps>
+__device__ __forceinline__ uint32_t take_child(StealShared<kWarps> *sh, int lane, int &vw, int &root, int &player, int &die, bool &done)
+{
+    done = false;
+    const uint32_t avail = lane < kWarps ? *(volatile uint32_t *)&sh->slot[lane].legal0 : 0u;
+    const uint32_t m = __ballot_sync(kFull, avail != 0);
+    if (m == 0) {
+        done = __shfl_sync(kFull, *(volatile int32_t *)&sh->active, 0) <= 0;
+        if (!done) __nanosleep(200);
+        return 0u;
+    }
+    vw = lowest_bit(m);
+    StealSlot *vs = &sh->slot[vw];
+    uint32_t bit = 0;
+    if (lane == 0) {
+        const uint32_t old = *(volatile uint32_t *)&vs->legal0;
+        if (old) {
+            const uint32_t high = 1u << highest_bit(old);
+            atomicAdd(&vs->pending, 1);                           // before the take: the owner cannot finish under us
+            if (atomicCAS(&vs->legal0, old, old & ~high) == old) bit = high;
+            else atomicSub(&vs->pending, 1);
+        }
+    }
+    bit = __shfl_sync(kFull, bit, 0);
+    if (bit == 0) return 0u;
+    __threadfence_block();
+    const int b = (int)*(volatile int8_t *)&vs->root[lane];
+    const uint32_t meta = *(volatile uint32_t *)&vs->meta;
+    root = lane < 28 ? b : 0;
+    player = (int)(meta & 1u);
+    die = (int)(meta >> 8);
+    return bit;
+}
+
+template <int kWarps>
+__device__ __forceinline__ void deliver_child(StealShared<kWarps> *sh, StealResult *cta_results, int vw, uint32_t bit, const Choice &c, int lane)
+{
+    StealSlot *vs = &sh->slot[vw];
+    uint32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(&vs->nres, 1u);
+    idx = __shfl_sync(kFull, idx, 0);
+    StealResult *r = cta_results + vw * kStealMaxResults + idx;
+    r->v[lane] = (int8_t)c.v;
+    if (lane == 0) {
+        r->value = c.value; r->any = c.any ? 1 : 0; r->n_seq = c.n_seq; r->n_scored = c.n_scored;
+        r->n_visited = c.n_visited; r->origin = lowest_bit(bit); r->moves = c.moves;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicSub(&vs->pending, 1);
 }
 
 // greedy or exploring ply; kExplore = false compiles the epsilon path out (smaller, fewer registers)
 template <int kSets, bool kExplore>
 __device__ __forceinline__ Choice choose_ply_fast(int root, int lane, int player, int d1, int d2, const PlyEvaluator &ev,
-                                                  PlyCache<kSets> &cache, bool explore, uint32_t u)
+                                                  PlyCache<kSets> &cache, bool explore, uint32_t u,
+                                                  uint32_t root_only = kFull, StealSlot *slot = nullptr, StealResult *results = nullptr)
 {
     if (kExplore && explore) {
         CountLeaf cnt;
@@ -413,7 +580,7 @@ __device__ __forceinline__ Choice choose_ply_fast(int root, int lane, int player
         }
         return c;
     }
-    return greedy_ply<kSets>(root, lane, player, d1, d2, ev, cache);
+    return greedy_ply<kSets>(root, lane, player, d1, d2, ev, cache, root_only, slot, results);
 }
 
 } // namespace bgx
