@@ -152,6 +152,17 @@ class BatchEngine:
                                                 L.ptr(o["value"]), L.ptr(o["n_seq"]), L.ptr(o["n_scored"])))
         return o
 
+    def select_moves_host_async(self, lane, queries, out, epsilon=0.0, seed=0):
+        """Queue one batch on `lane` (0..3) and return; `out` maps output names to preallocated
+        (ideally pinned) numpy arrays, missing names are not computed.  wait(lane) completes it."""
+        q = _records(queries)
+        L.check(self._lib.bgx_select_moves_host_async(self._h, int(lane), q.ctypes.data, q.shape[0], float(epsilon), int(seed),
+                                                      L.ptr(out.get("chosen")), L.ptr(out.get("moves")), L.ptr(out.get("moves_len")),
+                                                      L.ptr(out.get("value")), L.ptr(out.get("n_seq")), L.ptr(out.get("n_scored"))))
+
+    def wait(self, lane):
+        L.check(self._lib.bgx_lane_wait(self._h, int(lane)))
+
     def select_moves(self, queries, epsilon=0.0, seed=0, chosen=None, moves=None, moves_len=None, value=None,
                      n_seq=None, n_scored=None):
         L.check(self._lib.bgx_select_moves(self._h, L.ptr(queries), queries.shape[0], float(epsilon), int(seed),

@@ -61,6 +61,8 @@ _SIGNATURES = {
     "bgx_evaluate_host": (C.c_int, [_vp, _vp, _i64, _vp]),
     "bgx_select_moves": (C.c_int, [_vp, _vp, _i64, C.c_float, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bgx_select_moves_host": (C.c_int, [_vp, _vp, _i64, C.c_float, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bgx_select_moves_host_async": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_float, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bgx_lane_wait": (C.c_int, [_vp, C.c_int]),
     # section 4
     "bgx_selfplay_init": (C.c_int, [_vp, _i64, _i64, _i64, C.c_uint64, C.c_int, C.c_int32]),
     "bgx_selfplay_record_chosen": (C.c_int, [_vp, C.c_int]),

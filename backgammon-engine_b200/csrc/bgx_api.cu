@@ -12,6 +12,19 @@
 
 using namespace bgx;
 
+// an asynchronous lane of the batched make_move path: its own stream, work-queue counter,
+// sharing buffer and staging buffers, so that two batches can be in flight at once
+struct bgx_lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    unsigned long long *counter = nullptr;
+    StealResult *steal = nullptr;
+    void *buf[7] = {};
+    size_t cap[7] = {};
+    bool busy = false;
+};
+constexpr int kLanes = BGX_ASYNC_LANES;
+
 struct bgx_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -19,8 +32,9 @@ struct bgx_engine {
     size_t global_mem = 0;
     // model
     float *flat = nullptr;        // [25604] state_dict order
-    float *table = nullptr;       // [198][128] feature-major cumulative table
     float *wt = nullptr;          // [198][128] W1 transposed (TD kernel)
+    int32_t *fixed = nullptr;     // [198][128] W1 transposed in fixed point (ply kernels, k_evaluate)
+    float *aux = nullptr;         // [4] derived scalars: [0] fixed-point scale S, [1] 1/S
     bool have_weights = false;
     // scratch
     static constexpr int kScratch = 12;
@@ -47,8 +61,9 @@ struct bgx_engine {
     int ply_warps = 16;                      // warps per CTA of the fused ply kernels
     // bookkeeping
     long long launches = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
     bool timed = false;
+    bgx_lane lanes[kLanes];
 };
 
 #define CU(call)                                                                              \
@@ -130,14 +145,17 @@ int bgx_create(int device, bgx_engine **out)
     cudaDeviceGetAttribute(&e->clock_khz, cudaDevAttrClockRate, device);
     CU(cudaMalloc(&e->flat, BGX_NPARAMS_PADDED * sizeof(float)));
     CU(cudaMemset(e->flat, 0, BGX_NPARAMS_PADDED * sizeof(float)));
-    CU(cudaMalloc(&e->table, kTableBytes));
     CU(cudaMalloc(&e->wt, kTableBytes));
+    CU(cudaMalloc(&e->fixed, kTableBytes));
+    CU(cudaMalloc(&e->aux, 4 * sizeof(float)));
+    CU(cudaMemset(e->aux, 0, 4 * sizeof(float)));
     CU(cudaMalloc(&e->counter, sizeof(unsigned long long)));
     CU(cudaMalloc(&e->stats, 8 * sizeof(unsigned long long)));
     CU(cudaMalloc(&e->dstats, 2 * sizeof(double)));
     CU(cudaMalloc(&e->steal, (size_t)e->sm_count * 32 * kStealMaxResults * sizeof(StealResult)));
     CU(cudaEventCreate(&e->ev0));
     CU(cudaEventCreate(&e->ev1));
+    CU(cudaEventCreateWithFlags(&e->ev_sync, cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, kEvalSmem));
     {
         const char *w = getenv("BGX_PLY_WARPS");       // tuning knob: 16 (default), 24 or 32 warps per CTA
@@ -164,10 +182,16 @@ int bgx_destroy(bgx_engine *e)
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < bgx_engine::kScratch; i++) cudaFree(e->dbuf[i]);
-    cudaFree(e->flat); cudaFree(e->table); cudaFree(e->wt); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats); cudaFree(e->steal);
+    cudaFree(e->flat); cudaFree(e->wt); cudaFree(e->fixed); cudaFree(e->aux); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats); cudaFree(e->steal);
     cudaFree(e->uniq_tables); cudaFree(e->uniq_gens); cudaFree(e->slots); cudaFree(e->traj_pre); cudaFree(e->traj_chosen);
     cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial);
-    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_sync);
+    for (bgx_lane &l : e->lanes) {
+        if (l.stream) cudaStreamDestroy(l.stream);
+        if (l.done) cudaEventDestroy(l.done);
+        cudaFree(l.counter); cudaFree(l.steal);
+        for (void *b : l.buf) cudaFree(b);
+    }
     delete e;
     return BGX_OK;
 }
@@ -188,8 +212,10 @@ int bgx_synchronize(bgx_engine *e)
 
 static int rebuild_table(bgx_engine *e)
 {
-    k_build_table<<<(kTableFloats + 255) / 256, 256, 0, e->stream>>>(e->flat, e->table, e->wt);
-    e->launches++;
+    k_build_table<<<(kTableFloats + 255) / 256, 256, 0, e->stream>>>(e->flat, e->wt);
+    k_fixed_scale<<<1, kHidden, 0, e->stream>>>(e->flat, e->aux);
+    k_build_fixed<<<(kTableFloats + 255) / 256, 256, 0, e->stream>>>(e->flat, e->aux, e->fixed);
+    e->launches += 3;
     CU(cudaGetLastError());
     return BGX_OK;
 }
@@ -377,7 +403,7 @@ int bgx_evaluate(bgx_engine *e, const int8_t *records, int64_t n, float *V)
     if (!e->have_weights) { set_error("bgx_evaluate: weights not set"); return BGX_E_STATE; }
     if (n == 0) return BGX_OK;
     tick(e);
-    k_evaluate<<<game_grid(e), kGameThreads, kEvalSmem, e->stream>>>(records, n, V, e->table, e->flat);
+    k_evaluate<<<game_grid(e), kGameThreads, kEvalSmem, e->stream>>>(records, n, V, e->fixed, e->flat, e->aux);
     tock(e);
     e->launches++;
     CU(cudaGetLastError());
@@ -402,6 +428,23 @@ int bgx_evaluate_host(bgx_engine *e, const int8_t *records, int64_t n, float *V)
 
 // ------------------------------------------------------------------------ batched make_move
 
+static int launch_select(bgx_engine *e, cudaStream_t stream, unsigned long long *counter, StealResult *steal,
+                         const int8_t *queries, int64_t n, float epsilon, uint64_t seed, const SelectOut &out)
+{
+    CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+#define BGX_LAUNCH_SELECT(W, S, X)                                                                          \
+    k_select<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), stream>>>(queries, n, epsilon, (uint32_t)seed, \
+                                                                          (uint32_t)(seed >> 32), out, e->fixed, e->flat, e->aux, counter, steal)
+    const bool ex = epsilon > 0.f;
+    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 126, true); else BGX_LAUNCH_SELECT(16, 126, false); }
+    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 84, true); else BGX_LAUNCH_SELECT(24, 84, false); }
+    else { if (ex) BGX_LAUNCH_SELECT(32, 62, true); else BGX_LAUNCH_SELECT(32, 62, false); }
+#undef BGX_LAUNCH_SELECT
+    e->launches++;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
 int bgx_select_moves(bgx_engine *e, const int8_t *queries, int64_t n, float epsilon, uint64_t seed,
                      int8_t *chosen, int8_t *moves, int8_t *moves_len, float *value, int32_t *n_seq, int32_t *n_scored)
 {
@@ -409,21 +452,11 @@ int bgx_select_moves(bgx_engine *e, const int8_t *queries, int64_t n, float epsi
     NEED(queries && n >= 0, "bad argument");
     if (!e->have_weights) { set_error("bgx_select_moves: weights not set"); return BGX_E_STATE; }
     if (n == 0) return BGX_OK;
-    SelectOut out = {chosen, moves, moves_len, value, n_seq, n_scored};
-    CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
+    const SelectOut out = {chosen, moves, moves_len, value, n_seq, n_scored};
     tick(e);
-#define BGX_LAUNCH_SELECT(W, S, X)                                                                              \
-    k_select<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(queries, n, epsilon, (uint32_t)seed, \
-                                                                             (uint32_t)(seed >> 32), out, e->wt, e->flat, e->counter, e->steal)
-    const bool ex = epsilon > 0.f;
-    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 126, true); else BGX_LAUNCH_SELECT(16, 126, false); }
-    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 84, true); else BGX_LAUNCH_SELECT(24, 84, false); }
-    else { if (ex) BGX_LAUNCH_SELECT(32, 62, true); else BGX_LAUNCH_SELECT(32, 62, false); }
-#undef BGX_LAUNCH_SELECT
+    const int rc = launch_select(e, e->stream, e->counter, e->steal, queries, n, epsilon, seed, out);
     tock(e);
-    e->launches++;
-    CU(cudaGetLastError());
-    return BGX_OK;
+    return rc;
 }
 
 int bgx_select_moves_host(bgx_engine *e, const int8_t *queries, int64_t n, float epsilon, uint64_t seed,
@@ -453,6 +486,77 @@ int bgx_select_moves_host(bgx_engine *e, const int8_t *queries, int64_t n, float
     if (n_seq) CU(cudaMemcpyAsync(n_seq, dn, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
     if (n_scored) CU(cudaMemcpyAsync(n_scored, ds, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    return BGX_OK;
+}
+
+// Asynchronous form of bgx_select_moves_host: the copies and the kernel are queued on lane `lane`'s own
+// stream and the call returns; bgx_lane_wait blocks until that lane's results are in the host buffers.
+// Two lanes in flight let the host advance one half of a population while the GPU plays the other.
+static int lane_scratch(bgx_lane &l, int i, size_t bytes, void **out)
+{
+    if (l.cap[i] < bytes) {
+        if (l.buf[i]) CU(cudaFree(l.buf[i]));
+        l.buf[i] = nullptr;
+        l.cap[i] = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        CU(cudaMalloc(&l.buf[i], want));
+        l.cap[i] = want;
+    }
+    *out = l.buf[i];
+    return BGX_OK;
+}
+
+int bgx_select_moves_host_async(bgx_engine *e, int lane, const int8_t *queries, int64_t n, float epsilon, uint64_t seed,
+                                int8_t *chosen, int8_t *moves, int8_t *moves_len, float *value, int32_t *n_seq, int32_t *n_scored)
+{
+    USE(e);
+    NEED(lane >= 0 && lane < kLanes, "lane out of range");
+    NEED(queries && n >= 0, "bad argument");
+    if (!e->have_weights) { set_error("bgx_select_moves_host_async: weights not set"); return BGX_E_STATE; }
+    bgx_lane &l = e->lanes[lane];
+    if (l.busy) { set_error("bgx_select_moves_host_async: lane %d has a batch in flight (bgx_lane_wait first)", lane); return BGX_E_STATE; }
+    if (!l.stream) {
+        CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        CU(cudaMalloc(&l.counter, sizeof(unsigned long long)));
+        CU(cudaMalloc(&l.steal, (size_t)e->sm_count * 32 * kStealMaxResults * sizeof(StealResult)));
+    }
+    if (n == 0) return BGX_OK;
+    void *dq, *dc, *dm, *dl, *dv, *dn, *ds;
+    int rc;
+    if ((rc = lane_scratch(l, 0, (size_t)n * 32, &dq))) return rc;
+    if ((rc = lane_scratch(l, 1, (size_t)n * 32, &dc))) return rc;
+    if ((rc = lane_scratch(l, 2, (size_t)n * 8, &dm))) return rc;
+    if ((rc = lane_scratch(l, 3, (size_t)n, &dl))) return rc;
+    if ((rc = lane_scratch(l, 4, (size_t)n * 4, &dv))) return rc;
+    if ((rc = lane_scratch(l, 5, (size_t)n * 4, &dn))) return rc;
+    if ((rc = lane_scratch(l, 6, (size_t)n * 4, &ds))) return rc;
+    // weights set on the engine's stream before this call are visible to the lane
+    CU(cudaEventRecord(e->ev_sync, e->stream));
+    CU(cudaStreamWaitEvent(l.stream, e->ev_sync, 0));
+    CU(cudaMemcpyAsync(dq, queries, (size_t)n * 32, cudaMemcpyHostToDevice, l.stream));
+    const SelectOut out = {chosen ? (int8_t *)dc : nullptr, moves ? (int8_t *)dm : nullptr, moves_len ? (int8_t *)dl : nullptr,
+                           value ? (float *)dv : nullptr, n_seq ? (int32_t *)dn : nullptr, n_scored ? (int32_t *)ds : nullptr};
+    if ((rc = launch_select(e, l.stream, l.counter, l.steal, (const int8_t *)dq, n, epsilon, seed, out))) return rc;
+    if (chosen) CU(cudaMemcpyAsync(chosen, dc, (size_t)n * 32, cudaMemcpyDeviceToHost, l.stream));
+    if (moves) CU(cudaMemcpyAsync(moves, dm, (size_t)n * 8, cudaMemcpyDeviceToHost, l.stream));
+    if (moves_len) CU(cudaMemcpyAsync(moves_len, dl, (size_t)n, cudaMemcpyDeviceToHost, l.stream));
+    if (value) CU(cudaMemcpyAsync(value, dv, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
+    if (n_seq) CU(cudaMemcpyAsync(n_seq, dn, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
+    if (n_scored) CU(cudaMemcpyAsync(n_scored, ds, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
+    CU(cudaEventRecord(l.done, l.stream));
+    l.busy = true;
+    return BGX_OK;
+}
+
+int bgx_lane_wait(bgx_engine *e, int lane)
+{
+    USE(e);
+    NEED(lane >= 0 && lane < kLanes, "lane out of range");
+    bgx_lane &l = e->lanes[lane];
+    if (!l.busy) return BGX_OK;
+    CU(cudaEventSynchronize(l.done));
+    l.busy = false;
     return BGX_OK;
 }
 
@@ -518,7 +622,7 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
     tick(e);
-#define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->wt, e->flat, e->steal)
+#define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->fixed, e->flat, e->aux, e->steal)
     const bool ex = epsilon > 0.f;
     if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 126, true); else BGX_LAUNCH_SELFPLAY(16, 126, false); }
     else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 84, true); else BGX_LAUNCH_SELFPLAY(24, 84, false); }

@@ -152,75 +152,9 @@ __device__ __forceinline__ void walk_turn(int root, int lane, int player, int d1
     }
 }
 
-// ------------------------------------------------------------------------------------
-// the evaluator: V = sigmoid(w2 . sigmoid(W1 x + b1) + b2)         model.py:63-67
-// with x generated on the fly from the lanes (model.py:111-144); X never exists in memory
-// ------------------------------------------------------------------------------------
-// Shared-memory table T[198][128] (feature-major = W1 transposed) with the three unit
-// features of every (point, colour) pre-accumulated: row 8i+c+k (k=0,1,2) holds
-// W1[:,8i+c] + ... + W1[:,8i+c+k], row 8i+c+3 holds the raw slope column.  A point with n
-// checkers then costs one row (n<=3) or two (n>3): T[base+min(n,3)-1] + (n-3)/2 * T[base+3].
-// Lane l owns hidden units 4l..4l+3, so a row is one conflict-free LDS.128 per lane.
-
 __device__ __forceinline__ float sigmoid_f32(float z) { return 1.0f / (1.0f + expf(-z)); }
 
 __device__ __forceinline__ float off_feature(int k) { return __fdiv_rn((float)k, 15.0f); } // == (float)(k/15.0), k<=15
-
-struct Evaluator {
-    const float4 *T4;   // shared memory, [198][32] float4
-    float4 b1, w2;      // this lane's 4 hidden units
-    float b2;
-    float4 z0;          // b1 + T[192 + mover]: constant over the candidates of one ply
-
-    __device__ __forceinline__ void load_params(const float *b1g, const float *w2g, const float *b2g, int lane)
-    {
-        b1 = reinterpret_cast<const float4 *>(b1g)[lane];
-        w2 = reinterpret_cast<const float4 *>(w2g)[lane];
-        b2 = b2g[0];
-    }
-    // `turn` is the flag of features 192/193: the MOVER for afterstates
-    __device__ __forceinline__ void begin(int turn, int lane)
-    {
-        const float4 t = T4[(192 + turn) * 32 + lane];
-        z0 = make_float4(b1.x + t.x, b1.y + t.y, b1.z + t.z, b1.w + t.w);
-    }
-    __device__ __forceinline__ float value(int v, int lane) const
-    {
-        // every lane describes its own point: row of the cumulative unit features | extra<<8
-        const int n = v < 0 ? -v : v;
-        const int row = 8 * lane + (v > 0 ? 0 : 4) + (n < 3 ? n : 3) - 1;
-        const int packed = row | ((n > 3 ? n - 3 : 0) << 8);
-        uint32_t occ = __ballot_sync(kFull, lane < 24 && v != 0);
-        uint32_t side = __ballot_sync(kFull, lane >= 24 && v != 0);   // bar / borne-off lanes
-        float4 z = z0;
-        while (occ) {
-            const int i = lowest_bit(occ);
-            occ &= occ - 1;
-            const int p = __shfl_sync(kFull, packed, i);
-            const int r = p & 0xFF;
-            const float4 t = T4[r * 32 + lane];
-            z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w;
-            const int extra = p >> 8;
-            if (extra) {
-                const float s = (float)extra * 0.5f;
-                const float4 u = T4[(r | 3) * 32 + lane];
-                z.x += s * u.x; z.y += s * u.y; z.z += s * u.z; z.w += s * u.w;
-            }
-        }
-        while (side) {
-            const int i = lowest_bit(side);
-            side &= side - 1;
-            const int c = __shfl_sync(kFull, v, i);
-            const float s = i < 26 ? (float)c * 0.5f : off_feature(c);
-            const float4 u = T4[(170 + i) * 32 + lane];               // rows 194..197
-            z.x += s * u.x; z.y += s * u.y; z.z += s * u.z; z.w += s * u.w;
-        }
-        float y = w2.x * sigmoid_f32(z.x) + w2.y * sigmoid_f32(z.y) + w2.z * sigmoid_f32(z.z) + w2.w * sigmoid_f32(z.w);
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) y += __shfl_xor_sync(kFull, y, s);
-        return sigmoid_f32(y + b2);
-    }
-};
 
 // ------------------------------------------------------------------------------------
 // shared-memory staging of the weight table: one TMA bulk copy per CTA
@@ -228,7 +162,7 @@ struct Evaluator {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Every thread of the CTA must call this; returns once the table is visible.
-__device__ __forceinline__ void stage_table(float *dst_smem, const float *src_gmem, uint64_t *bar)
+__device__ __forceinline__ void stage_table(void *dst_smem, const void *src_gmem, uint64_t *bar)
 {
     const uint32_t b = smem_u32(bar);
     if (threadIdx.x == 0) {

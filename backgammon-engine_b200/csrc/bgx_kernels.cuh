@@ -18,22 +18,60 @@ constexpr int kUniqSlots = 4096;                   // 8 words each, probed as bu
 constexpr int kUniqWords = 8;
 constexpr size_t kUniqBytesPerWarp = (size_t)kUniqSlots * kUniqWords * 4;   // 128 KiB
 
-// ---- weights: state_dict order -> feature-major cumulative table -----------------------
+// ---- weights: state_dict order -> the tables the kernels read ------------------------------
 // flat = [W1[128][198] | b1[128] | w2[128] | b2[1]]  (model.py:36-37)
-__global__ void k_build_table(const float *__restrict__ flat, float *__restrict__ T, float *__restrict__ Wt)
+// Wt[198][128]: W1 transposed (feature-major), fp32, for the TD kernel
+__global__ void k_build_table(const float *__restrict__ flat, float *__restrict__ Wt)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= kTableFloats) return;
     const int f = idx / kHidden, j = idx % kHidden;
+    Wt[idx] = flat[j * kFeatures + f];
+}
+
+// aux[0] = S, aux[1] = 1/S: the fixed-point scale of the ply evaluator (bgx_ply.cuh).  Thread j bounds
+// |z_j| over every position: |b1_j| + per point the largest contribution any stack of either colour can make
+// (up to 15 checkers: three unit features and a slope of up to 6) + both bars at 7.5 + both borne-off
+// features at 1 + the larger turn flag.  S = the largest power of two with max_j bound_j * S <= 2^30.
+__global__ void k_fixed_scale(const float *__restrict__ flat, float *__restrict__ aux)
+{
+    __shared__ float red[kHidden / 32];
+    const int j = threadIdx.x;
     const float *w = flat + j * kFeatures;
-    float s = w[f];
-    Wt[idx] = s;                                   // plain transpose, for the TD kernel
-    if (f < 192 && (f & 3) != 3) {
-        const int base = f & ~3;
-        s = w[base];
-        for (int t = base + 1; t <= f; t++) s += w[t];
+    float bound = fabsf(flat[kTableFloats + j]);
+    for (int i = 0; i < 24; i++) {
+        float worst = 0.f;
+        for (int c = 0; c < 2; c++) {
+            const float *u = w + 8 * i + 4 * c;
+            const float s1 = u[0], s2 = s1 + u[1], s3 = s2 + u[2];
+            worst = fmaxf(worst, fmaxf(fabsf(s1), fabsf(s2)));
+            worst = fmaxf(worst, fabsf(s3) + 6.f * fabsf(u[3]));
+        }
+        bound += worst;
     }
-    T[idx] = s;
+    bound += fmaxf(fabsf(w[192]), fabsf(w[193])) + 7.5f * (fabsf(w[194]) + fabsf(w[195])) + fabsf(w[196]) + fabsf(w[197]);
+    for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(kFull, bound, o));
+    if ((j & 31) == 0) red[j >> 5] = bound;
+    __syncthreads();
+    if (j == 0) {
+        for (int k = 1; k < kHidden / 32; k++) bound = fmaxf(bound, red[k]);
+        int e = 30 - (ilogbf(fmaxf(bound, 1e-30f)) + 1);      // bound < 2^(ilogb+1)  =>  bound * 2^e < 2^30
+        e = e > 60 ? 60 : (e < -60 ? -60 : e);
+        aux[0] = ldexpf(1.f, e);
+        aux[1] = ldexpf(1.f, -e);
+        aux[2] = bound;
+    }
+}
+
+// Ti[198][128]: the fixed-point table of the ply evaluator (layout in bgx_ply.cuh)
+__global__ void k_build_fixed(const float *__restrict__ flat, const float *__restrict__ aux, int32_t *__restrict__ Ti)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kTableFloats) return;
+    const int f = idx / kHidden, j = idx % kHidden;
+    const float w = flat[j * kFeatures + f], S = aux[0];
+    const bool half = (f < 192 && (f & 3) == 3) || f == 194 || f == 195;
+    Ti[idx] = f >= 196 ? __float_as_int(w) : __float2int_rn(w * (half ? 0.5f * S : S));
 }
 
 // a warp-wide work queue: lane 0 claims, everybody learns
@@ -228,22 +266,21 @@ k_encode(const int8_t *__restrict__ records, long long n, float *__restrict__ X)
 // ---- forward(_encode_states_np(states, turn)) (model.py:63-67): records -> V ------------
 __global__ void __launch_bounds__(kGameThreads, 1)
 k_evaluate(const int8_t *__restrict__ records, long long n, float *__restrict__ V,
-           const float *__restrict__ T, const float *__restrict__ flat)
+           const int32_t *__restrict__ Ti, const float *__restrict__ flat, const float *__restrict__ aux)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    float *sT = reinterpret_cast<float *>(smem);
+    int32_t *sT = reinterpret_cast<int32_t *>(smem);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes);
-    stage_table(sT, T, bar);
+    stage_table(sT, Ti, bar);
     const int lane = threadIdx.x & 31;
-    Evaluator ev;
-    ev.T4 = reinterpret_cast<const float4 *>(sT);
-    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, lane);
+    PlyEvaluator ev;
+    ev.T4 = reinterpret_cast<const int4 *>(sT);
+    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, aux, lane);
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += warps) {
         const int b = load_record_byte(records + q * 32, lane);
         const int v = lane < 28 ? b : 0;
-        ev.begin(__shfl_sync(kFull, b, 28) ? 1 : 0, lane);
-        const float val = ev.value(v, lane);
+        const float val = ev.finish(ev.preactivation(v, lane, __shfl_sync(kFull, b, 28) ? 1 : 0));
         if (lane == 0) V[q] = val;
     }
 }
@@ -278,13 +315,13 @@ __device__ __forceinline__ void store_choice(const SelectOut &o, long long q, co
 // shared-memory carve-up of the fused ply kernels: weight table | per-warp caches | sharing slots | barrier
 template <int kWarps, int kSets>
 struct PlySmem {
-    float *table;
+    int32_t *table;
     PlyScratch<kSets> *scratch;
     StealShared<kWarps> *share;
     uint64_t *bar;
     __device__ __forceinline__ explicit PlySmem(unsigned char *smem)
     {
-        table = reinterpret_cast<float *>(smem);
+        table = reinterpret_cast<int32_t *>(smem);
         scratch = reinterpret_cast<PlyScratch<kSets> *>(smem + kTableBytes);
         share = reinterpret_cast<StealShared<kWarps> *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>));
         bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>) + sizeof(StealShared<kWarps>));
@@ -304,8 +341,8 @@ struct PlySmem {
 template <int kWarps, int kSets, bool kExplore>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_t seed_lo, uint32_t seed_hi,
-         SelectOut out, const float *__restrict__ Wt, const float *__restrict__ flat, unsigned long long *counter,
-         StealResult *__restrict__ steal)
+         SelectOut out, const int32_t *__restrict__ Ti, const float *__restrict__ flat, const float *__restrict__ aux,
+         unsigned long long *counter, StealResult *__restrict__ steal)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const PlySmem<kWarps, kSets> sm(smem);
@@ -313,10 +350,10 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
     PlyCache<kSets> cache;
     cache.reset(sm.scratch[warp].cache, lane);
     sm.init_share();
-    stage_table(sm.table, Wt, sm.bar);
+    stage_table(sm.table, Ti, sm.bar);
     PlyEvaluator ev;
-    ev.W4 = reinterpret_cast<const float4 *>(sm.table);
-    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, lane);
+    ev.T4 = reinterpret_cast<const int4 *>(sm.table);
+    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, aux, lane);
     StealSlot *mine = &sm.share->slot[warp];
     StealResult *cta_results = steal + (size_t)blockIdx.x * kWarps * kStealMaxResults;
     StealResult *my_results = cta_results + warp * kStealMaxResults;
@@ -374,7 +411,8 @@ struct SelfplayParams {
 
 template <int kWarps, int kSets, bool kExplore>
 __global__ void __launch_bounds__(kWarps * 32, 1)
-k_selfplay(SelfplayParams p, const float *__restrict__ Wt, const float *__restrict__ flat, StealResult *__restrict__ steal)
+k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__restrict__ flat, const float *__restrict__ aux,
+           StealResult *__restrict__ steal)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const PlySmem<kWarps, kSets> sm(smem);
@@ -382,10 +420,10 @@ k_selfplay(SelfplayParams p, const float *__restrict__ Wt, const float *__restri
     PlyCache<kSets> cache;
     cache.reset(sm.scratch[warp].cache, lane);
     sm.init_share();
-    stage_table(sm.table, Wt, sm.bar);
+    stage_table(sm.table, Ti, sm.bar);
     PlyEvaluator ev;
-    ev.W4 = reinterpret_cast<const float4 *>(sm.table);
-    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, lane);
+    ev.T4 = reinterpret_cast<const int4 *>(sm.table);
+    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, aux, lane);
     StealSlot *mine = &sm.share->slot[warp];
     StealResult *cta_results = steal + (size_t)blockIdx.x * kWarps * kStealMaxResults;
     StealResult *my_results = cta_results + warp * kStealMaxResults;

@@ -4,11 +4,12 @@
 // order, score every distinct afterstate with the 198-128-1 net, first-index arg-best.
 // How the work is done (each step driven by an ncu capture, see profiles/):
 //
-//  1. DELTA EVALUATION.  The hidden pre-activation z = W1 x + b1 of a node is kept per tree
-//     depth; a move changes 2-4 features (one checker leaves a stack, one joins a stack, a
-//     hit also flips the blot and the enemy bar), so z(child) = z(parent) + 2-4 rows of the
-//     raw feature-major weight table.  Scoring a new afterstate costs 2-4 LDS.128 + the
-//     sigmoid epilogue instead of a walk over all ~16 occupied points.
+//  1. DELTA EVALUATION IN FIXED POINT.  The hidden pre-activation z = W1 x + b1 of a node is kept
+//     per tree depth; a move changes 2-4 features (one checker leaves a stack, one joins a stack,
+//     a hit also flips the blot and the enemy bar), so z(child) = z(parent) +- 2-4 rows of the
+//     feature-major weight table: 2-4 LDS.128 + the sigmoid epilogue instead of a walk over all
+//     ~16 occupied points.  z is int32 fixed point, which makes it independent of the path (see
+//     PlyEvaluator): an afterstate's value is a pure function of the afterstate.
 //  2. DEPTH-SPECIALISED WALK IN REGISTERS.  The turn tree is walked by a fully inlined
 //     template recursion (one instance per depth), so node state, node z and the origins
 //     still to try are registers, not a stack in memory, and work is lazy: a child is only
@@ -47,63 +48,89 @@ __device__ __forceinline__ float fast_sigmoid(float z)
     return r;
 }
 
-struct PlyEvaluator {
-    const float4 *W4;    // shared memory, raw feature-major table Wt[198][32] float4
-    float4 b1, w2;
-    float b2;
-
-    __device__ __forceinline__ void load_params(const float *b1g, const float *w2g, const float *b2g, int lane)
-    {
-        b1 = reinterpret_cast<const float4 *>(b1g)[lane];
-        w2 = reinterpret_cast<const float4 *>(w2g)[lane];
-        b2 = b2g[0];
-    }
-    __device__ __forceinline__ static void axpy(float4 &z, float a, const float4 &t)
-    {
-        z.x = fmaf(a, t.x, z.x); z.y = fmaf(a, t.y, z.y); z.z = fmaf(a, t.z, z.z); z.w = fmaf(a, t.w, z.w);
-    }
-    // full pre-activation of a position (once per ply, for the root), features in ascending order
-    __device__ __forceinline__ float4 preactivation(int v, int lane, int turn) const
-    {
-        const int n = v < 0 ? -v : v;
-        const int packed = (8 * lane + (v > 0 ? 0 : 4)) | (n << 8);
-        uint32_t occ = __ballot_sync(kFull, lane < 24 && v != 0);
-        uint32_t side = __ballot_sync(kFull, lane >= 24 && v != 0);
-        float4 z = b1;
-        while (occ) {
-            const int i = lowest_bit(occ);
-            occ &= occ - 1;
-            const int p = __shfl_sync(kFull, packed, i);
-            const int base = p & 0xFF, cnt = p >> 8;
-            const float4 *row = W4 + base * 32 + lane;
-            axpy(z, 1.0f, row[0]);
-            if (cnt >= 2) axpy(z, 1.0f, row[32]);
-            if (cnt >= 3) axpy(z, 1.0f, row[64]);
-            if (cnt >= 4) axpy(z, (float)(cnt - 3) * 0.5f, row[96]);
-        }
-        axpy(z, 1.0f, W4[(192 + turn) * 32 + lane]);
-        while (side) {
-            const int i = lowest_bit(side);
-            side &= side - 1;
-            const int c = __shfl_sync(kFull, v, i);
-            axpy(z, i < 26 ? (float)c * 0.5f : off_feature(c), W4[(170 + i) * 32 + lane]);
-        }
-        return z;
-    }
-    __device__ __forceinline__ float finish(const float4 &z) const
-    {
-        float y = w2.x * fast_sigmoid(z.x) + w2.y * fast_sigmoid(z.y) + w2.z * fast_sigmoid(z.z) + w2.w * fast_sigmoid(z.w);
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) y += __shfl_xor_sync(kFull, y, s);
-        return fast_sigmoid(y + b2);
-    }
-};
-
 // off/15.0 for off = 0..16 (model.py:143-144: float64 divide, stored as float32); [16] pads the k+1 read
 __device__ __constant__ float kOffFeature[17] = {
     (float)(0 / 15.0), (float)(1 / 15.0), (float)(2 / 15.0), (float)(3 / 15.0), (float)(4 / 15.0), (float)(5 / 15.0),
     (float)(6 / 15.0), (float)(7 / 15.0), (float)(8 / 15.0), (float)(9 / 15.0), (float)(10 / 15.0), (float)(11 / 15.0),
     (float)(12 / 15.0), (float)(13 / 15.0), (float)(14 / 15.0), (float)(15 / 15.0), (float)(16 / 15.0)};
+
+// ---- the evaluator of the ply kernels: hidden pre-activations in FIXED POINT ---------------
+// z = b1 + W1 x is accumulated in int32 with a per-network power-of-two scale S (k_fixed_scale:
+// the largest S with |z| S < 2^30 for every reachable position).  Integer addition is associative,
+// so the z of a position is the same whichever path of the turn tree led to it, whichever warp
+// walked it and whatever the caches held: the value of an afterstate is a pure function of the
+// afterstate, duplicates score bit-identically, and the strict first-index arg-best is reproducible
+// bit for bit.  (Float accumulation along the tree path differed in the last bits from path to
+// path, which made near-ties between distinct afterstates depend on timing.)  Resolution: 2^-30
+// of the largest possible |z|, finer than fp32's own rounding of a sum of that size.
+// Table Ti[198][128] (k_build_fixed), per feature row f:
+//   unit features (f < 192, f % 4 != 3), turn flags 192/193     round(W1[:,f] S)
+//   slope features (f % 4 == 3): (n-3)/2 grows by 1/2 per checker   round(W1[:,f] S / 2), coefficient +-1
+//   bar features 194/195: n/2                                       round(W1[:,f] S / 2), coefficient +-1
+//   borne-off features 196/197: k/15 is not a multiple of a step    the fp32 weight itself (bit pattern);
+//                                                                   contribution round(fl(k/15) W1 S), a function of k
+struct PlyEvaluator {
+    const int4 *T4;      // shared memory, fixed-point table Ti[198][32] int4
+    int4 b1;             // round(b1 S), this lane's 4 hidden units
+    float4 w2;
+    float b2, scale, inv_scale;
+
+    __device__ __forceinline__ void load_params(const float *b1g, const float *w2g, const float *b2g, const float *aux, int lane)
+    {
+        scale = aux[0];
+        inv_scale = aux[1];
+        const float4 b = reinterpret_cast<const float4 *>(b1g)[lane];
+        b1 = make_int4(__float2int_rn(b.x * scale), __float2int_rn(b.y * scale), __float2int_rn(b.z * scale), __float2int_rn(b.w * scale));
+        w2 = reinterpret_cast<const float4 *>(w2g)[lane];
+        b2 = b2g[0];
+    }
+    __device__ __forceinline__ static void add(int4 &z, const int4 &t) { z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w; }
+    __device__ __forceinline__ static void sub(int4 &z, const int4 &t) { z.x -= t.x; z.y -= t.y; z.z -= t.z; z.w -= t.w; }
+    __device__ __forceinline__ static void addn(int4 &z, int n, const int4 &t) { z.x += n * t.x; z.y += n * t.y; z.z += n * t.z; z.w += n * t.w; }
+    // contribution of k borne-off checkers of `player` (row 196 + player holds the fp32 weights)
+    __device__ __forceinline__ int4 off_term(int k, int player, int lane) const
+    {
+        const int4 w = T4[(196 + player) * 32 + lane];
+        const float f = kOffFeature[k] * scale;
+        return make_int4(__float2int_rn(__int_as_float(w.x) * f), __float2int_rn(__int_as_float(w.y) * f),
+                         __float2int_rn(__int_as_float(w.z) * f), __float2int_rn(__int_as_float(w.w) * f));
+    }
+    // pre-activation of a position from scratch (the root of a ply; k_evaluate)
+    __device__ __forceinline__ int4 preactivation(int v, int lane, int turn) const
+    {
+        const int n = v < 0 ? -v : v;
+        const int packed = (8 * lane + (v > 0 ? 0 : 4)) | (n << 8);
+        uint32_t occ = __ballot_sync(kFull, lane < 24 && v != 0);
+        int4 z = b1;
+        while (occ) {
+            const int i = lowest_bit(occ);
+            occ &= occ - 1;
+            const int p = __shfl_sync(kFull, packed, i);
+            const int base = p & 0xFF, cnt = p >> 8;
+            const int4 *row = T4 + base * 32 + lane;
+            add(z, row[0]);
+            if (cnt >= 2) add(z, row[32]);
+            if (cnt >= 3) add(z, row[64]);
+            if (cnt >= 4) addn(z, cnt - 3, row[96]);
+        }
+        add(z, T4[(192 + turn) * 32 + lane]);
+        const int bar1 = __shfl_sync(kFull, v, 24), bar2 = __shfl_sync(kFull, v, 25);
+        const int off1 = __shfl_sync(kFull, v, 26), off2 = __shfl_sync(kFull, v, 27);
+        if (bar1) addn(z, bar1, T4[194 * 32 + lane]);
+        if (bar2) addn(z, bar2, T4[195 * 32 + lane]);
+        if (off1) add(z, off_term(off1, 0, lane));
+        if (off2) add(z, off_term(off2, 1, lane));
+        return z;
+    }
+    __device__ __forceinline__ float finish(const int4 &zi) const
+    {
+        const float zx = (float)zi.x * inv_scale, zy = (float)zi.y * inv_scale, zz = (float)zi.z * inv_scale, zw = (float)zi.w * inv_scale;
+        float y = w2.x * fast_sigmoid(zx) + w2.y * fast_sigmoid(zy) + w2.z * fast_sigmoid(zz) + w2.w * fast_sigmoid(zw);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) y += __shfl_xor_sync(kFull, y, s);
+        return fast_sigmoid(y + b2);
+    }
+};
 
 // The per-warp cache of one ply.  Two kinds of entries share it:
 //   tag 0      an afterstate that was already scored in this ply (the exact-duplicate filter)
@@ -211,7 +238,7 @@ struct PlyWalk {
     int c_me;             // feature block of the mover inside a point's 8 features (0 or 4)
     int dieA, dieB;       // die of even / odd depths
     uint32_t root_only;   // restricts the root's origins (all ones: no restriction)
-    float4 zroot;
+    int4 zroot;
     // result
     float best_key;       // value, negated for PLAYER2 (who minimises): always maximised, strict > keeps the first
     int best_v;
@@ -276,47 +303,41 @@ struct PlyWalk {
     __device__ __forceinline__ int unit_of_points() const { return player ? -1 : 1; }
 
     // pre-activation of the child reached from (vpar, zpar) by o -> d: 2 rows, 4 after a hit
-    __device__ __forceinline__ float4 child_z(const float4 &zpar, int vpar, int o, int d, int dval) const
+    __device__ __forceinline__ int4 child_z(const int4 &zpar, int vpar, int o, int d, int dval) const
     {
         const int src = src_lane(o), dst = dst_lane(d);
         const int sval = __shfl_sync(kFull, vpar, src);
-        const float4 *W4 = ev.W4 + lane;
-        float4 z = zpar;
-        int row;
-        float c;
-        if (src >= 24) { row = 194 + player; c = -0.5f; }
-        else {
+        const int4 *T4 = ev.T4 + lane;
+        int4 z = zpar;
+        if (src >= 24) {
+            PlyEvaluator::sub(z, T4[(194 + player) * 32]);                  // one checker less on the bar
+        } else {
             const int n = sval < 0 ? -sval : sval;
-            row = 8 * src + c_me + (n < 4 ? n : 4) - 1;
-            c = n >= 4 ? -0.5f : -1.0f;
+            PlyEvaluator::sub(z, T4[(8 * src + c_me + (n < 4 ? n : 4) - 1) * 32]);
         }
-        PlyEvaluator::axpy(z, c, W4[row * 32]);
         if (dst >= 24) {
-            row = 196 + player;
-            c = kOffFeature[dval + 1] - kOffFeature[dval];
+            PlyEvaluator::add(z, ev.off_term(dval + 1, player, lane));
+            PlyEvaluator::sub(z, ev.off_term(dval, player, lane));
         } else if (dval * unit_of_points() == -1) {                          // a hit
-            PlyEvaluator::axpy(z, -1.0f, W4[(8 * dst + 4 - c_me) * 32]);   // the blot leaves ...
-            PlyEvaluator::axpy(z, 0.5f, W4[(195 - player) * 32]);          // ... for the enemy's bar
-            row = 8 * dst + c_me;
-            c = 1.0f;
+            PlyEvaluator::sub(z, T4[(8 * dst + 4 - c_me) * 32]);            // the blot leaves ...
+            PlyEvaluator::add(z, T4[(195 - player) * 32]);                  // ... for the enemy's bar
+            PlyEvaluator::add(z, T4[(8 * dst + c_me) * 32]);
         } else {
             const int k = (dval < 0 ? -dval : dval) + 1;
-            row = 8 * dst + c_me + (k < 4 ? k : 4) - 1;
-            c = k >= 4 ? 0.5f : 1.0f;
+            PlyEvaluator::add(z, T4[(8 * dst + c_me + (k < 4 ? k : 4) - 1) * 32]);
         }
-        PlyEvaluator::axpy(z, c, W4[row * 32]);
         return z;
     }
 
     // a legal turn sequence ends on v (reference order); score it unless this exact state was scored before
     template <int D>
-    __device__ __forceinline__ void leaf(int v, const float4 &zpar, int vpar, int o, int d, int dval, uint32_t path)
+    __device__ __forceinline__ void leaf(int v, const int4 &zpar, int vpar, int o, int d, int dval, uint32_t path)
     {
         n_seq++;
         const typename PlyCache<kSets>::Probe pr = cache.probe(v, 0, lane);
         if (pr.hit()) return;
         cache.write(pr, v, 0, 0, lane);
-        const float4 z = D == 0 ? zroot : child_z(zpar, vpar, o, d, dval);
+        const int4 z = D == 0 ? zroot : child_z(zpar, vpar, o, d, dval);
         const float val = ev.finish(z);
         n_scored++;
         const float key = player ? -val : val;
@@ -324,7 +345,7 @@ struct PlyWalk {
     }
 
     template <int D, bool kDbl>
-    __device__ __forceinline__ void visit(int v, const float4 &zpar, int vpar, int o, int d, int dval, uint32_t path)
+    __device__ __forceinline__ void visit(int v, const int4 &zpar, int vpar, int o, int d, int dval, uint32_t path)
     {
         constexpr int kMax = kDbl ? 4 : 2;
         uint32_t legal = 0;
@@ -343,7 +364,7 @@ struct PlyWalk {
                 const int below = cache.lookup(v, D, lane);
                 if (below >= 0) { n_seq += below; return; }
             }
-            const float4 z = D == 0 ? zroot : child_z(zpar, vpar, o, d, dval);
+            const int4 z = D == 0 ? zroot : child_z(zpar, vpar, o, d, dval);
             const int entered = n_seq;
             const int die = (D & 1) ? dieB : dieA;
             do {

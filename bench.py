@@ -224,34 +224,53 @@ def run_ours(args):
     plies_all, seqs_all, scored_all = (float(x) for x in counts.tolist())
     value = plies_all / total_s
 
-    # ---- end to end: host-driven self-play through bgx_select_moves_host, pinned buffers
+    # ---- end to end: host-driven self-play through the batched make_move C-ABI call, pinned host buffers.
+    # The population is split into two halves, each on its own asynchronous lane: while the GPU plays
+    # one half (H2D of its records, k_select, D2H of the chosen afterstates) the host advances the other
+    # (game over?, restart, flip the mover, next dice) - the loop of train.py:99-121 for 65,536 games.
     e2e_steps = max(2, min(args.steps, 8)) * PLIES_PER_STEP
     q_pin = torch.zeros((G, 32), dtype=torch.int8).pin_memory()
-    out_pin = {"chosen": torch.zeros((G, 32), dtype=torch.int8).pin_memory().numpy(),
-               "value": torch.zeros(G, dtype=torch.float32).pin_memory().numpy(),
-               "moves": None, "moves_len": None, "n_seq": None, "n_scored": None}
-    q = q_pin.numpy()
+    ch_pin = torch.zeros((G, 32), dtype=torch.int8).pin_memory()
+    val_pin = torch.zeros(G, dtype=torch.float32).pin_memory()
+    q, ch, val = q_pin.numpy(), ch_pin.numpy(), val_pin.numpy()
     rec, _, _ = eng.selfplay_read()          # continue the (desynchronised) games of the population from the host
     q[:] = rec
     q[:, 31] = 0
     rng = np.random.default_rng(SEED + rank)
+    halves = [(0, G // 2), (G // 2, G)]
+
+    def submit(h):
+        lo, hi = halves[h]
+        q[lo:hi, 29:31] = rng.integers(1, 7, (hi - lo, 2), dtype=np.int8)
+        eng.select_moves_host_async(h, q[lo:hi], {"chosen": ch[lo:hi], "value": val[lo:hi]})
+
+    def advance(h):
+        lo, hi = halves[h]
+        eng.wait(h)
+        c = ch[lo:hi]
+        over = (c[:, 26] == 15) | (c[:, 27] == 15)
+        q[lo:hi, :28] = c[:, :28]
+        q[lo:hi, 28] ^= 1
+        if over.any():
+            idx = np.flatnonzero(over) + lo
+            q[idx, :24] = START_BOARD
+            q[idx, 24:28] = 0
+        return hi - lo
+
+    submit(0)
+    submit(1)
     e2e_plies = 0
     for it in range(-2, e2e_steps):                 # 2 untimed warm-up plies
         if it == 0:
-            barrier()
+            barrier()                               # drains nothing of ours: the lanes are non-blocking streams
             t0 = time.perf_counter()
-        q[:, 29:31] = rng.integers(1, 7, (G, 2), dtype=np.int8)
-        o = eng.select_moves_host(q, out=dict(out_pin))
-        ch = o["chosen"]
-        over = (ch[:, 26] == 15) | (ch[:, 27] == 15)
-        q[:, :28] = ch[:, :28]
-        q[:, 28] ^= 1
-        if over.any():
-            q[over, :24] = START_BOARD
-            q[over, 24:28] = 0
-        if it >= 0:
-            e2e_plies += G
-    torch.cuda.synchronize()
+        for h in (0, 1):
+            n_adv = advance(h)
+            submit(h)
+            if it >= 0:
+                e2e_plies += n_adv
+    eng.wait(0)
+    eng.wait(1)
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
@@ -310,8 +329,9 @@ def run_ours(args):
                 "sequences_per_ply": seqs_all / plies_all, "scored_per_ply": scored_all / plies_all,
                 "tree_edges_per_ply_rank0": edges / max(plies, 1), "ply_warps_per_cta": int(os.environ.get("BGX_PLY_WARPS", "16")),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 32, "d2h_bytes_per_step": G * 36,
-                        "note": "one step = one ply for all 65,536 games through bgx_select_moves_host; "
-                                f"{e2e_steps} timed plies incl. the numpy host loop"},
+                        "note": "one step = one ply for all 65,536 games through bgx_select_moves_host_async (two half-populations "
+                                "on two lanes, pinned host buffers, H2D + k_select + D2H per ply); "
+                                f"{e2e_steps} timed ply-steps incl. the numpy host loop that advances the games"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

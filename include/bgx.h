@@ -167,6 +167,18 @@ int bgx_select_moves_host(bgx_engine *e, const int8_t *queries, int64_t n, float
                           int8_t *chosen, int8_t *moves, int8_t *moves_len, float *value,
                           int32_t *n_seq, int32_t *n_scored);
 
+/* The same call, asynchronous: copies and kernel are queued on lane `lane`'s own stream
+ * (0 <= lane < BGX_ASYNC_LANES) and the call returns at once; bgx_lane_wait(lane) blocks until
+ * that lane's outputs are in the host buffers.  Host buffers should be page-locked and must
+ * stay untouched until the wait.  A lane holds one batch at a time (BGX_E_STATE otherwise).
+ * With two lanes a host loop (model.py make_move callers: train.py:107, benchmark.py:86)
+ * advances one half of its games while the GPU plays the other half. */
+#define BGX_ASYNC_LANES 4
+int bgx_select_moves_host_async(bgx_engine *e, int lane, const int8_t *queries, int64_t n, float epsilon, uint64_t seed,
+                                int8_t *chosen, int8_t *moves, int8_t *moves_len, float *value,
+                                int32_t *n_seq, int32_t *n_scored);
+int bgx_lane_wait(bgx_engine *e, int lane);
+
 /* ------------------------------------------------------------------------------------
  * 4. Self-play population (replaces play_game, train.py:64-121, for many games at once)
  * ---------------------------------------------------------------------------------- */

@@ -190,6 +190,46 @@ def test_select_moves_vs_oracle(eng, orc, golden, tag):
     assert soft <= (300 if tag == "rand" else 30), soft     # near-ties: ~10 % with random-init weights
 
 
+@pytest.mark.parametrize("tag", ["rand", "trained"])
+def test_select_moves_is_a_pure_function_of_the_query(eng, golden, tag):
+    """The choice must not depend on batch composition, on which warp walked a position, on what the
+    per-warp caches held, or on how many sub-trees of a big double were walked by helper warps: the
+    same queries alone (most warps idle, heavy sharing), inside a large batch (little sharing), in a
+    different order and through the asynchronous lanes give bit-identical records, moves and values."""
+    import torch
+    from bgx.synth import make_queries
+    w = golden_weights(golden("model.npz"), tag)
+    eng.set_weights(*w)
+    q, _ = make_queries(20000, seed=424242)
+    keys = ("chosen", "moves", "moves_len", "value", "n_seq")
+    whole = eng.select_moves_host(q)
+    big = np.flatnonzero((q[:, 29] == q[:, 30]) & (whole["n_seq"] > 500))[:64]      # big doubles
+    assert big.size >= 16
+    few = eng.select_moves_host(q[big])                                             # 64 queries on 2,368 warps
+    for k in keys:
+        assert np.array_equal(few[k], whole[k][big], equal_nan=(k == "value")), k
+    perm = np.random.default_rng(1).permutation(q.shape[0])
+    shuf = eng.select_moves_host(q[perm])
+    for k in keys:
+        assert np.array_equal(shuf[k], whole[k][perm], equal_nan=(k == "value")), k
+    # asynchronous lanes: two halves in flight at once, pinned buffers
+    h = q.shape[0] // 2
+    pin = {k: torch.from_numpy(np.zeros_like(whole[k])).pin_memory().numpy() for k in keys}
+    qp = torch.from_numpy(q.copy()).pin_memory().numpy()
+    for lane, (lo, hi) in enumerate(((0, h), (h, q.shape[0]))):
+        eng.select_moves_host_async(lane, qp[lo:hi], {k: pin[k][lo:hi] for k in keys})
+    eng.wait(0)
+    eng.wait(1)
+    for k in keys:
+        assert np.array_equal(pin[k], whole[k], equal_nan=(k == "value")), k
+    # a lane holds one batch at a time
+    from bgx.lib import BgxError
+    eng.select_moves_host_async(2, qp[:16], {"chosen": pin["chosen"][:16]})
+    with pytest.raises(BgxError):
+        eng.select_moves_host_async(2, qp[:16], {"chosen": pin["chosen"][:16]})
+    eng.wait(2)
+
+
 def test_select_moves_golden_games(eng, orc, golden):
     """The reference's own greedy games (model.make_move on the reference engine), ply by ply."""
     g = golden("games.npz")
