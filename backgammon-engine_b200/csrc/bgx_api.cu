@@ -146,7 +146,7 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaMalloc(&e->flat, BGX_NPARAMS_PADDED * sizeof(float)));
     CU(cudaMemset(e->flat, 0, BGX_NPARAMS_PADDED * sizeof(float)));
     CU(cudaMalloc(&e->wt, kTableBytes));
-    CU(cudaMalloc(&e->fixed, kTableBytes));
+    CU(cudaMalloc(&e->fixed, kFixedBytes));
     CU(cudaMalloc(&e->aux, 4 * sizeof(float)));
     CU(cudaMemset(e->aux, 0, 4 * sizeof(float)));
     CU(cudaMalloc(&e->counter, sizeof(unsigned long long)));
@@ -167,9 +167,9 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaFuncSetAttribute(k_select<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));             \
     CU(cudaFuncSetAttribute(k_selfplay<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));          \
     CU(cudaFuncSetAttribute(k_selfplay<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));
-    BGX_SMEM_ATTR(16, 126)
-    BGX_SMEM_ATTR(24, 84)
-    BGX_SMEM_ATTR(32, 62)
+    BGX_SMEM_ATTR(16, 112)
+    BGX_SMEM_ATTR(24, 74)
+    BGX_SMEM_ATTR(32, 55)
 #undef BGX_SMEM_ATTR
     CU(cudaFuncSetAttribute(k_td_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
     *out = e;
@@ -214,7 +214,7 @@ static int rebuild_table(bgx_engine *e)
 {
     k_build_table<<<(kTableFloats + 255) / 256, 256, 0, e->stream>>>(e->flat, e->wt);
     k_fixed_scale<<<1, kHidden, 0, e->stream>>>(e->flat, e->aux);
-    k_build_fixed<<<(kTableFloats + 255) / 256, 256, 0, e->stream>>>(e->flat, e->aux, e->fixed);
+    k_build_fixed<<<(kFixedInts + 255) / 256, 256, 0, e->stream>>>(e->flat, e->aux, e->fixed);
     e->launches += 3;
     CU(cudaGetLastError());
     return BGX_OK;
@@ -436,9 +436,9 @@ static int launch_select(bgx_engine *e, cudaStream_t stream, unsigned long long 
     k_select<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), stream>>>(queries, n, epsilon, (uint32_t)seed, \
                                                                           (uint32_t)(seed >> 32), out, e->fixed, e->flat, e->aux, counter, steal)
     const bool ex = epsilon > 0.f;
-    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 126, true); else BGX_LAUNCH_SELECT(16, 126, false); }
-    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 84, true); else BGX_LAUNCH_SELECT(24, 84, false); }
-    else { if (ex) BGX_LAUNCH_SELECT(32, 62, true); else BGX_LAUNCH_SELECT(32, 62, false); }
+    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 112, true); else BGX_LAUNCH_SELECT(16, 112, false); }
+    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 74, true); else BGX_LAUNCH_SELECT(24, 74, false); }
+    else { if (ex) BGX_LAUNCH_SELECT(32, 55, true); else BGX_LAUNCH_SELECT(32, 55, false); }
 #undef BGX_LAUNCH_SELECT
     e->launches++;
     CU(cudaGetLastError());
@@ -624,9 +624,9 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
     tick(e);
 #define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->fixed, e->flat, e->aux, e->steal)
     const bool ex = epsilon > 0.f;
-    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 126, true); else BGX_LAUNCH_SELFPLAY(16, 126, false); }
-    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 84, true); else BGX_LAUNCH_SELFPLAY(24, 84, false); }
-    else { if (ex) BGX_LAUNCH_SELFPLAY(32, 62, true); else BGX_LAUNCH_SELFPLAY(32, 62, false); }
+    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 112, true); else BGX_LAUNCH_SELFPLAY(16, 112, false); }
+    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 74, true); else BGX_LAUNCH_SELFPLAY(24, 74, false); }
+    else { if (ex) BGX_LAUNCH_SELFPLAY(32, 55, true); else BGX_LAUNCH_SELFPLAY(32, 55, false); }
 #undef BGX_LAUNCH_SELFPLAY
     tock(e);
     e->launches++;

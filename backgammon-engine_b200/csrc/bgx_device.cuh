@@ -21,6 +21,9 @@ constexpr int kFeatures = 198;
 constexpr int kHidden = 128;
 constexpr int kTableFloats = kFeatures * kHidden;                 // 25 344
 constexpr int kTableBytes = kTableFloats * 4;                     // 101 376
+constexpr int kFixedRows = kFeatures + 30;                        // + borne-off step rows (bgx_ply.cuh)
+constexpr int kFixedInts = kFixedRows * kHidden;                  // 29 184
+constexpr int kFixedBytes = kFixedInts * 4;                       // 116 736
 
 // status byte (record byte 31) of a self-play slot
 enum { kRunning = 0, kP1Won = 1, kP2Won = 2, kTruncated = 3 };
@@ -162,7 +165,7 @@ __device__ __forceinline__ float off_feature(int k) { return __fdiv_rn((float)k,
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Every thread of the CTA must call this; returns once the table is visible.
-__device__ __forceinline__ void stage_table(void *dst_smem, const void *src_gmem, uint64_t *bar)
+__device__ __forceinline__ void stage_table(void *dst_smem, const void *src_gmem, uint64_t *bar, int bytes)
 {
     const uint32_t b = smem_u32(bar);
     if (threadIdx.x == 0) {
@@ -171,9 +174,9 @@ __device__ __forceinline__ void stage_table(void *dst_smem, const void *src_gmem
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(kTableBytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(kTableBytes), "r"(b)
+                     ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(b)
                      : "memory");
     }
     uint32_t done = 0;

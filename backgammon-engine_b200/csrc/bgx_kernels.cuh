@@ -10,7 +10,7 @@ constexpr int kGameWarps = 16;                     // warps per CTA in the warp-
 constexpr int kGameThreads = kGameWarps * 32;
 // dynamic shared memory of the fused ply kernels: weight table + per-warp scratch + barrier
 template <int kWarps, int kSets>
-constexpr int ply_smem() { return kTableBytes + kWarps * (int)sizeof(PlyScratch<kSets>) + (int)sizeof(StealShared<kWarps>) + 16; }
+constexpr int ply_smem() { return kFixedBytes + kWarps * (int)sizeof(PlyScratch<kSets>) + (int)sizeof(StealShared<kWarps>) + 16; }
 constexpr int kEvalSmem = kTableBytes + 16;            // k_evaluate: table + barrier
 
 // exact-dedup table of the summary kernel: per warp, in global memory (L2 resident)
@@ -63,15 +63,22 @@ __global__ void k_fixed_scale(const float *__restrict__ flat, float *__restrict_
     }
 }
 
-// Ti[198][128]: the fixed-point table of the ply evaluator (layout in bgx_ply.cuh)
+// Ti[228][128]: the fixed-point table of the ply evaluator (layout in bgx_ply.cuh)
 __global__ void k_build_fixed(const float *__restrict__ flat, const float *__restrict__ aux, int32_t *__restrict__ Ti)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= kTableFloats) return;
+    if (idx >= kFixedInts) return;
     const int f = idx / kHidden, j = idx % kHidden;
-    const float w = flat[j * kFeatures + f], S = aux[0];
-    const bool half = (f < 192 && (f & 3) == 3) || f == 194 || f == 195;
-    Ti[idx] = f >= 196 ? __float_as_int(w) : __float2int_rn(w * (half ? 0.5f * S : S));
+    const float S = aux[0];
+    if (f < kFeatures) {
+        const float w = flat[j * kFeatures + f];
+        const bool half = (f < 192 && (f & 3) == 3) || f == 194 || f == 195;
+        Ti[idx] = f >= 196 ? __float_as_int(w) : __float2int_rn(w * (half ? 0.5f * S : S));
+    } else {                                       // row 198 + 15 p + k: what the (k+1)-th borne-off checker of player p adds
+        const int p = (f - kFeatures) / 15, k = (f - kFeatures) % 15;
+        const float w = flat[j * kFeatures + 196 + p];
+        Ti[idx] = __float2int_rn(w * (kOffFeature[k + 1] * S)) - __float2int_rn(w * (kOffFeature[k] * S));
+    }
 }
 
 // a warp-wide work queue: lane 0 claims, everybody learns
@@ -271,7 +278,7 @@ k_evaluate(const int8_t *__restrict__ records, long long n, float *__restrict__ 
     extern __shared__ __align__(128) unsigned char smem[];
     int32_t *sT = reinterpret_cast<int32_t *>(smem);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes);
-    stage_table(sT, Ti, bar);
+    stage_table(sT, Ti, bar, kTableBytes);
     const int lane = threadIdx.x & 31;
     PlyEvaluator ev;
     ev.T4 = reinterpret_cast<const int4 *>(sT);
@@ -322,9 +329,9 @@ struct PlySmem {
     __device__ __forceinline__ explicit PlySmem(unsigned char *smem)
     {
         table = reinterpret_cast<int32_t *>(smem);
-        scratch = reinterpret_cast<PlyScratch<kSets> *>(smem + kTableBytes);
-        share = reinterpret_cast<StealShared<kWarps> *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>));
-        bar = reinterpret_cast<uint64_t *>(smem + kTableBytes + kWarps * sizeof(PlyScratch<kSets>) + sizeof(StealShared<kWarps>));
+        scratch = reinterpret_cast<PlyScratch<kSets> *>(smem + kFixedBytes);
+        share = reinterpret_cast<StealShared<kWarps> *>(smem + kFixedBytes + kWarps * sizeof(PlyScratch<kSets>));
+        bar = reinterpret_cast<uint64_t *>(smem + kFixedBytes + kWarps * sizeof(PlyScratch<kSets>) + sizeof(StealShared<kWarps>));
     }
     // every thread calls this before stage_table(), whose __syncthreads publishes it
     __device__ __forceinline__ void init_share() const
@@ -350,7 +357,7 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
     PlyCache<kSets> cache;
     cache.reset(sm.scratch[warp].cache, lane);
     sm.init_share();
-    stage_table(sm.table, Ti, sm.bar);
+    stage_table(sm.table, Ti, sm.bar, kFixedBytes);
     PlyEvaluator ev;
     ev.T4 = reinterpret_cast<const int4 *>(sm.table);
     ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, aux, lane);
@@ -420,7 +427,7 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
     PlyCache<kSets> cache;
     cache.reset(sm.scratch[warp].cache, lane);
     sm.init_share();
-    stage_table(sm.table, Ti, sm.bar);
+    stage_table(sm.table, Ti, sm.bar, kFixedBytes);
     PlyEvaluator ev;
     ev.T4 = reinterpret_cast<const int4 *>(sm.table);
     ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, aux, lane);

@@ -68,7 +68,8 @@ __device__ __constant__ float kOffFeature[17] = {
 //   slope features (f % 4 == 3): (n-3)/2 grows by 1/2 per checker   round(W1[:,f] S / 2), coefficient +-1
 //   bar features 194/195: n/2                                       round(W1[:,f] S / 2), coefficient +-1
 //   borne-off features 196/197: k/15 is not a multiple of a step    the fp32 weight itself (bit pattern);
-//                                                                   contribution round(fl(k/15) W1 S), a function of k
+//                                                                   contribution T(k) = round(W1 (fl(k/15) S)), a function of k
+//   rows 198 + 15 p + k (k = 0..14): T(k+1) - T(k) of player p      what the (k+1)-th borne-off checker adds
 struct PlyEvaluator {
     const int4 *T4;      // shared memory, fixed-point table Ti[198][32] int4
     int4 b1;             // round(b1 S), this lane's 4 hidden units
@@ -91,7 +92,7 @@ struct PlyEvaluator {
     __device__ __forceinline__ int4 off_term(int k, int player, int lane) const
     {
         const int4 w = T4[(196 + player) * 32 + lane];
-        const float f = kOffFeature[k] * scale;
+        const float f = kOffFeature[k] * scale;                              // same expression as k_build_fixed
         return make_int4(__float2int_rn(__int_as_float(w.x) * f), __float2int_rn(__int_as_float(w.y) * f),
                          __float2int_rn(__int_as_float(w.z) * f), __float2int_rn(__int_as_float(w.w) * f));
     }
@@ -221,6 +222,24 @@ struct PlyCache {
     }
 };
 
+// A sequence that ends before the dice are used up (no legal move left) is the rare kind of leaf.  Its
+// afterstate is scored FROM SCRATCH by this out-of-line routine - the fixed-point z of a position does not
+// depend on how it is computed - so the fully inlined walk carries the leaf code only at its last level
+// (the kernel's code has to stay close to the 32 KB instruction cache).  Returns NaN if scored before.
+template <int kSets>
+__device__ __noinline__ float score_early_leaf(uint8_t *slots, uint32_t gen, uint32_t kmul, const int4 *T4, int4 b1, float4 w2,
+                                               float b2, float scale, float inv_scale, int v, int lane, int player)
+{
+    PlyCache<kSets> cache;
+    cache.slots = slots; cache.gen = gen; cache.kmul = kmul;
+    const typename PlyCache<kSets>::Probe pr = cache.probe(v, 0, lane);
+    if (pr.hit()) return __int_as_float(0x7fc00000);
+    cache.write(pr, v, 0, 0, lane);
+    PlyEvaluator e;
+    e.T4 = T4; e.b1 = b1; e.w2 = w2; e.b2 = b2; e.scale = scale; e.inv_scale = inv_scale;
+    return e.finish(e.preactivation(v, lane, player));
+}
+
 // ---- the walk ----------------------------------------------------------------------------
 // One template instance per tree depth (the recursion is fully inlined), so the per-depth
 // state of the walk - node state, node pre-activation, origins still to try - lives in
@@ -309,23 +328,17 @@ struct PlyWalk {
         const int sval = __shfl_sync(kFull, vpar, src);
         const int4 *T4 = ev.T4 + lane;
         int4 z = zpar;
-        if (src >= 24) {
-            PlyEvaluator::sub(z, T4[(194 + player) * 32]);                  // one checker less on the bar
-        } else {
-            const int n = sval < 0 ? -sval : sval;
-            PlyEvaluator::sub(z, T4[(8 * src + c_me + (n < 4 ? n : 4) - 1) * 32]);
-        }
-        if (dst >= 24) {
-            PlyEvaluator::add(z, ev.off_term(dval + 1, player, lane));
-            PlyEvaluator::sub(z, ev.off_term(dval, player, lane));
-        } else if (dval * unit_of_points() == -1) {                          // a hit
+        const int n = sval < 0 ? -sval : sval;
+        const int row_src = src >= 24 ? 194 + player : 8 * src + c_me + (n < 4 ? n : 4) - 1;
+        PlyEvaluator::sub(z, T4[row_src * 32]);                             // one checker less on the origin (or the bar)
+        const int k = (dval < 0 ? -dval : dval) + 1;
+        int row_dst = dst >= 24 ? kFeatures + 15 * player + dval : 8 * dst + c_me + (k < 4 ? k : 4) - 1;
+        if (dst < 24 && dval * unit_of_points() == -1) {                    // a hit
             PlyEvaluator::sub(z, T4[(8 * dst + 4 - c_me) * 32]);            // the blot leaves ...
             PlyEvaluator::add(z, T4[(195 - player) * 32]);                  // ... for the enemy's bar
-            PlyEvaluator::add(z, T4[(8 * dst + c_me) * 32]);
-        } else {
-            const int k = (dval < 0 ? -dval : dval) + 1;
-            PlyEvaluator::add(z, T4[(8 * dst + c_me + (k < 4 ? k : 4) - 1) * 32]);
+            row_dst = 8 * dst + c_me;
         }
+        PlyEvaluator::add(z, T4[row_dst * 32]);                             // one more on the landing point (or borne off)
         return z;
     }
 
@@ -344,6 +357,17 @@ struct PlyWalk {
         if (key > best_key) { best_key = key; best_v = v; best_path = path | ((uint32_t)D << 20); }
     }
 
+    __device__ __forceinline__ void early_leaf(int v, uint32_t path_and_len)
+    {
+        n_seq++;
+        const float val = score_early_leaf<kSets>(cache.slots, cache.gen, cache.kmul, ev.T4, ev.b1, ev.w2, ev.b2, ev.scale,
+                                                  ev.inv_scale, v, lane, player);
+        if (val != val) return;
+        n_scored++;
+        const float key = player ? -val : val;
+        if (key > best_key) { best_key = key; best_v = v; best_path = path_and_len; }
+    }
+
     template <int D, bool kDbl>
     __device__ __forceinline__ void visit(int v, const int4 &zpar, int vpar, int o, int d, int dval, uint32_t path)
     {
@@ -356,7 +380,8 @@ struct PlyWalk {
         if (legal == 0) {
             // a node without a move ends the sequence (game.cpp:117-121, 148-151); the root of a
             // non-double pass emits nothing
-            if (kDbl || D > 0) leaf<D>(v, zpar, vpar, o, d, dval, path);
+            if constexpr (D == kMax) leaf<D>(v, zpar, vpar, o, d, dval, path);
+            else if (kDbl || D > 0) early_leaf(v, path | ((uint32_t)D << 20));
             return;
         }
         if constexpr (D < kMax) {
@@ -453,7 +478,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
         w.dieA = w.dieB = d1;
         uint32_t legal = w.legal_here(root, d1) & root_only;
         if (legal == 0) {
-            w.template leaf<0>(root, w.zroot, root, 0, 0, 0, 0u);        // no move at all: the empty sequence
+            w.early_leaf(root, 0u);                                      // no move at all: the empty sequence
         } else {
             shared = slot != nullptr && __popc(legal) >= kStealMinChildren;
             if (shared) {                                                // publish the root's origins
