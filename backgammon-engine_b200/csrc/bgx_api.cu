@@ -160,7 +160,7 @@ int bgx_create(int device, bgx_engine **out)
     {
         const char *w = getenv("BGX_PLY_WARPS");       // tuning knob: 16 (default), 24 or 32 warps per CTA
         e->ply_warps = w ? atoi(w) : 16;
-        if (e->ply_warps != 16 && e->ply_warps != 24 && e->ply_warps != 32) { set_error("BGX_PLY_WARPS must be 16, 24 or 32"); delete e; return BGX_E_INVALID; }
+        if (e->ply_warps != 16 && e->ply_warps != 20 && e->ply_warps != 24 && e->ply_warps != 32) { set_error("BGX_PLY_WARPS must be 16, 20, 24 or 32"); delete e; return BGX_E_INVALID; }
     }
 #define BGX_SMEM_ATTR(W, S)                                                                                                    \
     CU(cudaFuncSetAttribute(k_select<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));            \
@@ -168,6 +168,7 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaFuncSetAttribute(k_selfplay<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));          \
     CU(cudaFuncSetAttribute(k_selfplay<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));
     BGX_SMEM_ATTR(16, 112)
+    BGX_SMEM_ATTR(20, 88)
     BGX_SMEM_ATTR(24, 74)
     BGX_SMEM_ATTR(32, 55)
 #undef BGX_SMEM_ATTR
@@ -437,6 +438,7 @@ static int launch_select(bgx_engine *e, cudaStream_t stream, unsigned long long 
                                                                           (uint32_t)(seed >> 32), out, e->fixed, e->flat, e->aux, counter, steal)
     const bool ex = epsilon > 0.f;
     if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 112, true); else BGX_LAUNCH_SELECT(16, 112, false); }
+    else if (e->ply_warps == 20) { if (ex) BGX_LAUNCH_SELECT(20, 88, true); else BGX_LAUNCH_SELECT(20, 88, false); }
     else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 74, true); else BGX_LAUNCH_SELECT(24, 74, false); }
     else { if (ex) BGX_LAUNCH_SELECT(32, 55, true); else BGX_LAUNCH_SELECT(32, 55, false); }
 #undef BGX_LAUNCH_SELECT
@@ -625,6 +627,7 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
 #define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->fixed, e->flat, e->aux, e->steal)
     const bool ex = epsilon > 0.f;
     if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 112, true); else BGX_LAUNCH_SELFPLAY(16, 112, false); }
+    else if (e->ply_warps == 20) { if (ex) BGX_LAUNCH_SELFPLAY(20, 88, true); else BGX_LAUNCH_SELFPLAY(20, 88, false); }
     else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 74, true); else BGX_LAUNCH_SELFPLAY(24, 74, false); }
     else { if (ex) BGX_LAUNCH_SELFPLAY(32, 55, true); else BGX_LAUNCH_SELFPLAY(32, 55, false); }
 #undef BGX_LAUNCH_SELFPLAY
