@@ -1,34 +1,35 @@
 // bgx_td.cuh — exact online TD(lambda) replay, apply_td_updates (train.py:124-172).
 //
-// One CTA per game, weights AND eligibility traces resident in shared memory
-// (2 x 25 601 fp32 = 204.8 KB of the 227 KB a CTA may own), so the 4 x 102 KB of
-// read-modify-write traffic per TD step never leaves the SM.  The replay is the
-// reference's, step for step: two forwards per step with the CURRENT weights, closed-form
-// gradients of the 2-layer sigmoid net, e <- lambda*e + grad,
-// p <- p + (lr*delta)*e with the same fp32 roundings torch produces (separate multiply
-// and add, lr*delta formed in float64 then rounded to fp32).
+// One CTA per game, 16 warps.  Weights AND eligibility traces of the 198 x 128 first layer live in
+// REGISTERS: warp w owns the feature rows f = w, w+16, w+32, ... (13 rows), lane l the hidden units
+// 4l..4l+3 of each, i.e. 13 float4 of W1 and 13 float4 of traces per thread (104 of the 128
+// registers a thread of a 512-thread CTA may have).  The dense part of a TD step - e <- lambda*e +
+// grad and p <- p + (lr*delta)*e over all 25,344 first-layer parameters - is then pure register
+// arithmetic; only the two forward passes exchange data (per-warp partial pre-activations through
+// shared memory, 16 KB).  The replay is the reference's, step for step: two forwards per step with
+// the CURRENT weights, closed-form gradients of the 2-layer sigmoid net,
+// and the same fp32 roundings torch produces (separate multiply and add, lr*delta formed in
+// float64 then rounded to fp32).  Two __syncthreads per step.
 #pragma once
 #include "bgx_device.cuh"
 
 namespace bgx {
 
 constexpr int kTdThreads = 512;
-constexpr int kTdListCap = 48;                     // >= 35 non-zero features of any legal position
+constexpr int kTdWarps = kTdThreads / 32;
+constexpr int kTdRows = (kFeatures + kTdWarps - 1) / kTdWarps;      // 13 feature rows per warp
+constexpr int kTdXStride = 200;                    // dense x of one state (198 + pad)
 // shared memory map (floats)
-constexpr int kTdW = 0;                            // W  [198][128] feature-major
-constexpr int kTdE = kTdW + kTableFloats;          // E  [198][128]
-constexpr int kTdB1 = kTdE + kTableFloats;         // b1, eb1, w2, ew2: 128 each
+constexpr int kTdX = 0;                            // x of three consecutive states, rotating
+constexpr int kTdPart = kTdX + 3 * kTdXStride;     // partial pre-activations [16 warps][2 states][128]
+constexpr int kTdH = kTdPart + kTdWarps * 2 * kHidden;   // hidden activations [2][128]
+constexpr int kTdB1 = kTdH + 2 * kHidden;          // b1, eb1: 128 each
 constexpr int kTdEB1 = kTdB1 + kHidden;
-constexpr int kTdW2 = kTdEB1 + kHidden;
-constexpr int kTdEW2 = kTdW2 + kHidden;
-constexpr int kTdX = kTdEW2 + kHidden;             // dense x of s_t: 198 (+2 pad)
-constexpr int kTdPart = kTdX + 200;                // partial z: [2 states][2 halves][128]
-constexpr int kTdH = kTdPart + 4 * kHidden;        // hidden activations [2][128]
-constexpr int kTdList = kTdH + 2 * kHidden;        // feature lists: idx[2][48] (int) then val[2][48]
-constexpr int kTdRed = kTdList + 4 * kTdListCap;   // y partials [2][4 warps] + scalars
-constexpr int kTdFloats = kTdRed + 32;
+constexpr int kTdW2 = kTdEB1 + kHidden;            // w2 double-buffered [2][128] (read and rewritten in the same phase)
+constexpr int kTdEW2 = kTdW2 + 2 * kHidden;
+constexpr int kTdRed = kTdEW2 + kHidden;           // [0..7] output partials of the two states, [8..9] b2 (double-buffered), [10] eb2
+constexpr int kTdFloats = kTdRed + 16;
 constexpr int kTdSmem = kTdFloats * 4;
-static_assert(kTdSmem <= 227 * 1024, "TD kernel shared memory");
 
 struct TdParams {
     const int8_t *traj;        // [n_games][traj_cap][32] pre-move records (byte 28 = turn flag)
@@ -47,70 +48,44 @@ struct TdParams {
     double *dstats;            // [0] sum of squared TD errors
 };
 
-// one warp turns one 32-byte record into (a) a compact list of non-zero features and
-// (b) optionally the dense x[198] (model.py:111-144)
-__device__ __forceinline__ int td_features(const int8_t *rec, int lane, int *idx, float *val, float *dense)
+// one warp turns one 32-byte record into the dense x[198] (model.py:111-144); every entry is written
+__device__ __forceinline__ void td_features(int b, int lane, float *dense)
 {
-    const int b = (int)rec[lane];
     const int v = lane < 28 ? b : 0;
     const int turn = __shfl_sync(kFull, b, 28) ? 1 : 0;
     const int c = v < 0 ? -v : v;
-    int nf = 0;
-    if (lane < 24) nf = c < 4 ? c : 4;
-    else if (lane < 28) nf = v != 0 ? 1 : 0;
-    else if (lane == 28) nf = 1;
-    int pos = nf;                                   // inclusive prefix sum over lanes
-#pragma unroll
-    for (int s = 1; s < 32; s <<= 1) {
-        const int t = __shfl_up_sync(kFull, pos, s);
-        if (lane >= s) pos += t;
-    }
-    const int total = __shfl_sync(kFull, pos, 31);
-    pos -= nf;
     if (lane < 24) {
-        const int base = 8 * lane + (v > 0 ? 0 : 4);
-        for (int k = 0; k < nf && pos + k < kTdListCap; k++) {
-            idx[pos + k] = base + k;
-            val[pos + k] = k < 3 ? 1.0f : (float)(c - 3) * 0.5f;
-        }
-        if (dense) {
-            float2 *d = reinterpret_cast<float2 *>(dense + 8 * lane);
-            const float a = c >= 1 ? 1.f : 0.f, bb = c >= 2 ? 1.f : 0.f, cc = c >= 3 ? 1.f : 0.f;
-            const float dd = c >= 4 ? (float)(c - 3) * 0.5f : 0.f;
-            const bool p1 = v > 0;
-            d[0] = p1 ? make_float2(a, bb) : make_float2(0.f, 0.f);
-            d[1] = p1 ? make_float2(cc, dd) : make_float2(0.f, 0.f);
-            d[2] = p1 ? make_float2(0.f, 0.f) : make_float2(a, bb);
-            d[3] = p1 ? make_float2(0.f, 0.f) : make_float2(cc, dd);
-        }
+        float2 *d = reinterpret_cast<float2 *>(dense + 8 * lane);
+        const float a = c >= 1 ? 1.f : 0.f, bb = c >= 2 ? 1.f : 0.f, cc = c >= 3 ? 1.f : 0.f;
+        const float dd = c >= 4 ? (float)(c - 3) * 0.5f : 0.f;
+        const bool p1 = v > 0;
+        d[0] = p1 ? make_float2(a, bb) : make_float2(0.f, 0.f);
+        d[1] = p1 ? make_float2(cc, dd) : make_float2(0.f, 0.f);
+        d[2] = p1 ? make_float2(0.f, 0.f) : make_float2(a, bb);
+        d[3] = p1 ? make_float2(0.f, 0.f) : make_float2(cc, dd);
     } else if (lane < 28) {
-        const float x = lane < 26 ? (float)v * 0.5f : off_feature(v);
-        if (nf && pos < kTdListCap) { idx[pos] = 170 + lane; val[pos] = x; }
-        if (dense) dense[170 + lane] = x;
+        dense[170 + lane] = lane < 26 ? (float)v * 0.5f : off_feature(v);
     } else if (lane == 28) {
-        if (pos < kTdListCap) { idx[pos] = 192 + turn; val[pos] = 1.0f; }
-        if (dense) { dense[192] = turn == 0 ? 1.f : 0.f; dense[193] = turn == 0 ? 0.f : 1.f; }
+        dense[192] = turn == 0 ? 1.f : 0.f;
+        dense[193] = turn == 0 ? 0.f : 1.f;
     }
-    return total < kTdListCap ? total : kTdListCap;
 }
 
 __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
 {
     extern __shared__ __align__(16) float sm[];
-    float *W = sm + kTdW, *E = sm + kTdE;
-    float *b1 = sm + kTdB1, *eb1 = sm + kTdEB1, *w2 = sm + kTdW2, *ew2 = sm + kTdEW2;
-    float *x = sm + kTdX, *part = sm + kTdPart, *hs = sm + kTdH;
-    int *lidx = reinterpret_cast<int *>(sm + kTdList);
-    float *lval = sm + kTdList + 2 * kTdListCap;
-    float *red = sm + kTdRed;                       // [0..7] y partials, [8] b2, [9] eb2, [10..11] list sizes, [12..13] v
+    float *xs = sm + kTdX, *part = sm + kTdPart, *hs = sm + kTdH;
+    float *b1 = sm + kTdB1, *eb1 = sm + kTdEB1, *w2 = sm + kTdW2, *ew2 = sm + kTdEW2, *red = sm + kTdRed;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float lam = p.lambda;
+    const float4 *wt4 = reinterpret_cast<const float4 *>(p.wt);
 
     float *mine = p.partial + (size_t)blockIdx.x * BGX_NPARAMS_PADDED;
     for (int i = tid; i < BGX_NPARAMS_PADDED; i += kTdThreads) mine[i] = 0.f;
 
     unsigned long long steps = 0, games = 0;
     double sq_sum = 0.0;
+    float4 W[kTdRows], E[kTdRows];                  // this thread's slice of W1 and of its traces
 
     for (long long g = blockIdx.x; g < p.n_games; g += gridDim.x) {
         const int status = (int)p.slots[g * 32 + 31];
@@ -121,61 +96,72 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
         const bool p1_won = status == kP1Won;
         const int8_t *traj = p.traj + (size_t)g * p.traj_cap * 32;
 
-        // round snapshot -> shared memory; traces start at zero (train.py:539-540)
+        // round snapshot -> registers / shared memory; traces start at zero (train.py:539-540)
         __syncthreads();
-        {
-            const float4 *src = reinterpret_cast<const float4 *>(p.wt);
-            float4 *dw = reinterpret_cast<float4 *>(W), *de = reinterpret_cast<float4 *>(E);
-            for (int i = tid; i < kTableFloats / 4; i += kTdThreads) {
-                dw[i] = src[i];
-                de[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (tid < kHidden) {
-                b1[tid] = p.flat[kTableFloats + tid];
-                w2[tid] = p.flat[kTableFloats + kHidden + tid];
-                eb1[tid] = 0.f;
-                ew2[tid] = 0.f;
-            }
-            if (tid == 0) { red[8] = p.flat[kTableFloats + 2 * kHidden]; red[9] = 0.f; }
+#pragma unroll
+        for (int r = 0; r < kTdRows; r++) {
+            const int f = warp + kTdWarps * r;
+            W[r] = f < kFeatures ? wt4[f * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            E[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if (tid < kHidden) {
+            b1[tid] = p.flat[kTableFloats + tid];
+            w2[tid] = p.flat[kTableFloats + kHidden + tid];
+            eb1[tid] = 0.f;
+            ew2[tid] = 0.f;
+        }
+        if (tid == 0) { red[8] = p.flat[kTableFloats + 2 * kHidden]; red[10] = 0.f; }
+        if (warp == 2) td_features((int)traj[lane], lane, xs);
+        if (warp == 3 && T > 1) td_features((int)traj[32 + lane], lane, xs + kTdXStride);
+        int ahead = (warp == 8 && T > 2) ? (int)traj[2 * 32 + lane] : 0;     // warp 8 keeps one record in flight
         __syncthreads();
 
         for (int t = 0; t < T; t++) {
             const bool terminal = t == T - 1;
-            // (1) features of s_t (list 0 + dense x) and s_{t+1} (list 1)
-            if (warp == 0) {
-                const int n = td_features(traj + (size_t)t * 32, lane, lidx, lval, x);
-                if (lane == 0) red[10] = __int_as_float(n);
-            } else if (warp == 1 && !terminal) {
-                const int n = td_features(traj + (size_t)(t + 1) * 32, lane, lidx + kTdListCap, lval + kTdListCap, nullptr);
-                if (lane == 0) red[11] = __int_as_float(n);
-            }
-            __syncthreads();
-            // (2) both forwards at once: thread = (state s, half, hidden unit j)
-            const int s = tid >> 8, half = (tid >> 7) & 1, j = tid & 127;
-            if (s == 0 || !terminal) {
-                const int n = __float_as_int(red[10 + s]);
-                const int *li = lidx + s * kTdListCap;
-                const float *lv = lval + s * kTdListCap;
-                float z = 0.f;
-                for (int k = half; k < n; k += 2) z += lv[k] * W[li[k] * kHidden + j];
-                part[(s * 2 + half) * kHidden + j] = z;
-            }
-            __syncthreads();
-            if (half == 0 && (s == 0 || !terminal)) {
-                const float z = b1[j] + part[(s * 2) * kHidden + j] + part[(s * 2 + 1) * kHidden + j];
-                const float h = sigmoid_f32(z);
-                hs[s * kHidden + j] = h;
-                float y = w2[j] * h;
+            const float *xc = xs + (t % 3) * kTdXStride, *xn = xs + ((t + 1) % 3) * kTdXStride;
+            const float *w2c = w2 + (t & 1) * kHidden;
+            float *w2n = w2 + ((t + 1) & 1) * kHidden;
+            // (1) both forwards, first layer: this warp's rows against x(s_t) and x(s_t+1)
+            {
+                float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(kFull, y, o);
-                if (lane == 0) red[s * 4 + (j >> 5)] = y;
+                for (int r = 0; r < kTdRows; r++) {
+                    const int f = warp + kTdWarps * r;
+                    if (f < kFeatures) {
+                        const float xa = xc[f], xb = terminal ? 0.f : xn[f];
+                        if (xa != 0.f) { za.x += xa * W[r].x; za.y += xa * W[r].y; za.z += xa * W[r].z; za.w += xa * W[r].w; }
+                        if (xb != 0.f) { zb.x += xb * W[r].x; zb.y += xb * W[r].y; zb.z += xb * W[r].z; zb.w += xb * W[r].w; }
+                    }
+                }
+                reinterpret_cast<float4 *>(part + (warp * 2 + 0) * kHidden)[lane] = za;
+                reinterpret_cast<float4 *>(part + (warp * 2 + 1) * kHidden)[lane] = zb;
             }
             __syncthreads();
-            const float v_cur = sigmoid_f32(red[0] + red[1] + red[2] + red[3] + red[8]);
+            // (2) hidden layer and output partials: thread = (state s, hidden unit j); meanwhile warp 8 encodes s_t+2
+            if (tid < 2 * kHidden) {
+                const int s = tid >> 7, j = tid & 127;
+                if (s == 0 || !terminal) {
+                    double zd = 0.0;                               // few-term fp32 partials, summed without further rounding
+#pragma unroll 4
+                    for (int w = 0; w < kTdWarps; w++) zd += (double)part[(w * 2 + s) * kHidden + j];
+                    const float h = sigmoid_f32((float)(zd + (double)b1[j]));
+                    hs[s * kHidden + j] = h;
+                    float y = w2c[j] * h;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(kFull, y, o);
+                    if (lane == 0) red[s * 4 + (j >> 5)] = y;
+                }
+            } else if (warp == 8 && t + 2 < T) {
+                td_features(ahead, lane, xs + ((t + 2) % 3) * kTdXStride);
+                if (t + 3 < T) ahead = (int)traj[(size_t)(t + 3) * 32 + lane];      // lands during the next step
+            }
+            __syncthreads();
+            // (3) TD error, gradients w.r.t. the pre-update weights
+            const float b2c = red[8 + (t & 1)];
+            const float v_cur = sigmoid_f32(red[0] + red[1] + red[2] + red[3] + b2c);
             double delta;
             if (!terminal) {
-                const float v_next = sigmoid_f32(red[4] + red[5] + red[6] + red[7] + red[8]);
+                const float v_next = sigmoid_f32(red[4] + red[5] + red[6] + red[7] + b2c);
                 delta = (double)__fsub_rn(v_next, v_cur);                    // train.py:160
                 if (tid == 0) {
                     sq_sum += delta * delta;
@@ -185,86 +171,93 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
                 delta = (p1_won ? 1.0 : 0.0) - (double)v_cur;               // train.py:168
             }
             const float c = (float)(p.lr * delta);                           // train.py:147
-            // (3) gradients w.r.t. the pre-update weights; this thread owns hidden units 4*lane..+3
             const float gv = __fmul_rn(__fsub_rn(1.0f, v_cur), v_cur);
             float gh[4], hh[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 hh[k] = hs[4 * lane + k];
-                gh[k] = __fmul_rn(__fmul_rn(__fmul_rn(gv, w2[4 * lane + k]), __fsub_rn(1.0f, hh[k])), hh[k]);
+                gh[k] = __fmul_rn(__fmul_rn(__fmul_rn(gv, w2c[4 * lane + k]), __fsub_rn(1.0f, hh[k])), hh[k]);
             }
-            __syncthreads();                                                 // everyone has read w2/h
             // (4) e <- lambda*e + grad ; p <- p + c*e   (train.py:141-147), all 25 601 parameters
-            {
-                float4 *W4 = reinterpret_cast<float4 *>(W), *E4 = reinterpret_cast<float4 *>(E);
-                for (int f = warp; f < kFeatures; f += kTdThreads / 32) {
-                    const float xf = x[f];
-                    float4 e = E4[f * 32 + lane], w = W4[f * 32 + lane];
-                    e.x = __fadd_rn(__fmul_rn(lam, e.x), __fmul_rn(gh[0], xf));
-                    e.y = __fadd_rn(__fmul_rn(lam, e.y), __fmul_rn(gh[1], xf));
-                    e.z = __fadd_rn(__fmul_rn(lam, e.z), __fmul_rn(gh[2], xf));
-                    e.w = __fadd_rn(__fmul_rn(lam, e.w), __fmul_rn(gh[3], xf));
-                    w.x = __fadd_rn(w.x, __fmul_rn(c, e.x));
-                    w.y = __fadd_rn(w.y, __fmul_rn(c, e.y));
-                    w.z = __fadd_rn(w.z, __fmul_rn(c, e.z));
-                    w.w = __fadd_rn(w.w, __fmul_rn(c, e.w));
-                    E4[f * 32 + lane] = e;
-                    W4[f * 32 + lane] = w;
-                }
-                if (warp == 0) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int jj = 4 * lane + k;
-                        const float e = __fadd_rn(__fmul_rn(lam, eb1[jj]), gh[k]);
-                        eb1[jj] = e;
-                        b1[jj] = __fadd_rn(b1[jj], __fmul_rn(c, e));
-                    }
-                } else if (warp == 1) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int jj = 4 * lane + k;
-                        const float e = __fadd_rn(__fmul_rn(lam, ew2[jj]), __fmul_rn(gv, hh[k]));
-                        ew2[jj] = e;
-                        w2[jj] = __fadd_rn(w2[jj], __fmul_rn(c, e));
-                    }
-                } else if (tid == 64) {
-                    const float e = __fadd_rn(__fmul_rn(lam, red[9]), gv);
-                    red[9] = e;
-                    red[8] = __fadd_rn(red[8], __fmul_rn(c, e));
+            for (int r = 0; r < kTdRows; r++) {
+                const int f = warp + kTdWarps * r;
+                if (f < kFeatures) {
+                    const float xf = xc[f];
+                    E[r].x = __fadd_rn(__fmul_rn(lam, E[r].x), __fmul_rn(gh[0], xf));
+                    E[r].y = __fadd_rn(__fmul_rn(lam, E[r].y), __fmul_rn(gh[1], xf));
+                    E[r].z = __fadd_rn(__fmul_rn(lam, E[r].z), __fmul_rn(gh[2], xf));
+                    E[r].w = __fadd_rn(__fmul_rn(lam, E[r].w), __fmul_rn(gh[3], xf));
+                    W[r].x = __fadd_rn(W[r].x, __fmul_rn(c, E[r].x));
+                    W[r].y = __fadd_rn(W[r].y, __fmul_rn(c, E[r].y));
+                    W[r].z = __fadd_rn(W[r].z, __fmul_rn(c, E[r].z));
+                    W[r].w = __fadd_rn(W[r].w, __fmul_rn(c, E[r].w));
                 }
             }
-            __syncthreads();
+            if (warp == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int jj = 4 * lane + k;
+                    const float e = __fadd_rn(__fmul_rn(lam, eb1[jj]), gh[k]);
+                    eb1[jj] = e;
+                    b1[jj] = __fadd_rn(b1[jj], __fmul_rn(c, e));
+                }
+            } else if (warp == 1) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int jj = 4 * lane + k;
+                    const float e = __fadd_rn(__fmul_rn(lam, ew2[jj]), __fmul_rn(gv, hh[k]));
+                    ew2[jj] = e;
+                    w2n[jj] = __fadd_rn(w2c[jj], __fmul_rn(c, e));
+                }
+            } else if (tid == 64) {
+                const float e = __fadd_rn(__fmul_rn(lam, red[10]), gv);
+                red[10] = e;
+                red[8 + ((t + 1) & 1)] = __fadd_rn(b2c, __fmul_rn(c, e));
+            }
+            // no barrier here: the next step's phase (1) touches only registers, x and `part`
         }
+        __syncthreads();
         steps += (unsigned long long)T;
         games++;
+        const float *w2f = w2 + (T & 1) * kHidden;
+        const float b2f = red[8 + (T & 1)];
 
         // this game's weight change, accumulated per CTA (feature-major W1, then b1, w2, b2)
         {
-            const float4 *w0 = reinterpret_cast<const float4 *>(p.wt);
-            const float4 *W4 = reinterpret_cast<const float4 *>(W);
             float4 *acc = reinterpret_cast<float4 *>(mine);
-            for (int i = tid; i < kTableFloats / 4; i += kTdThreads) {
-                float4 a = acc[i];
-                const float4 w = W4[i], o = w0[i];
-                a.x += w.x - o.x; a.y += w.y - o.y; a.z += w.z - o.z; a.w += w.w - o.w;
-                acc[i] = a;
+#pragma unroll
+            for (int r = 0; r < kTdRows; r++) {
+                const int f = warp + kTdWarps * r;
+                if (f < kFeatures) {
+                    float4 a = acc[f * 32 + lane];
+                    const float4 o = wt4[f * 32 + lane];
+                    a.x += W[r].x - o.x; a.y += W[r].y - o.y; a.z += W[r].z - o.z; a.w += W[r].w - o.w;
+                    acc[f * 32 + lane] = a;
+                }
             }
             if (tid < kHidden) {
                 mine[kTableFloats + tid] += b1[tid] - p.flat[kTableFloats + tid];
-                mine[kTableFloats + kHidden + tid] += w2[tid] - p.flat[kTableFloats + kHidden + tid];
+                mine[kTableFloats + kHidden + tid] += w2f[tid] - p.flat[kTableFloats + kHidden + tid];
             }
-            if (tid == 0) mine[kTableFloats + 2 * kHidden] += red[8] - p.flat[kTableFloats + 2 * kHidden];
+            if (tid == 0) mine[kTableFloats + 2 * kHidden] += b2f - p.flat[kTableFloats + 2 * kHidden];
         }
         if (p.final_weights) {
-            for (int i = tid; i < kTableFloats; i += kTdThreads) {
-                const int f = i >> 7, jj = i & 127;
-                p.final_weights[jj * kFeatures + f] = W[i];
+#pragma unroll
+            for (int r = 0; r < kTdRows; r++) {
+                const int f = warp + kTdWarps * r;
+                if (f < kFeatures) {
+                    p.final_weights[(4 * lane + 0) * kFeatures + f] = W[r].x;
+                    p.final_weights[(4 * lane + 1) * kFeatures + f] = W[r].y;
+                    p.final_weights[(4 * lane + 2) * kFeatures + f] = W[r].z;
+                    p.final_weights[(4 * lane + 3) * kFeatures + f] = W[r].w;
+                }
             }
             if (tid < kHidden) {
                 p.final_weights[kTableFloats + tid] = b1[tid];
-                p.final_weights[kTableFloats + kHidden + tid] = w2[tid];
+                p.final_weights[kTableFloats + kHidden + tid] = w2f[tid];
             }
-            if (tid == 0) p.final_weights[kTableFloats + 2 * kHidden] = red[8];
+            if (tid == 0) p.final_weights[kTableFloats + 2 * kHidden] = b2f;
         }
     }
     if (tid == 0) {
