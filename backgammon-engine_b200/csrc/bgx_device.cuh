@@ -3,11 +3,12 @@
 // Execution model: ONE WARP PER POSITION.  Lane i (0..27) holds element i of the
 // reference's 28-int state row (cppsrc/game.hpp:17-28): lanes 0..23 the board points,
 // 24/25 the bar counts, 26/27 the borne-off counts; lanes 28..31 hold 0.  Everything a
-// rule needs about the whole board is four __ballot_sync masks (bgx_core.h), a move is
-// two predicated register updates, and the turn tree of cppsrc/game.cpp:109-191 is walked
-// with warp-uniform control flow (no divergence, no per-thread stacks in memory).  The
-// 198-128-1 network (model.py:63-67) is evaluated by the same warp with 4 hidden units
-// per lane against a feature-major weight table resident in shared memory.
+// rule needs about the whole board is two __ballot_sync masks in the mover's frame (struct
+// Mover; the mask algebra is bgx_core.h's), a move is one shuffle and three predicated adds,
+// and the turn tree of cppsrc/game.cpp:109-191 is walked with warp-uniform control flow (no
+// divergence, no per-thread stacks in memory).  The 198-128-1 network (model.py:63-67) is
+// evaluated by the same warp with 4 hidden units per lane against a feature-major weight
+// table resident in shared memory (bgx_ply.cuh).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,38 +33,6 @@ enum { kRunning = 0, kP1Won = 1, kP2Won = 2, kTruncated = 3 };
 // lane-distributed state
 // ------------------------------------------------------------------------------------
 
-__device__ __forceinline__ Masks masks_on_lanes(int v, int player, bool &mover_on_bar)
-{
-    const uint32_t pos = __ballot_sync(kFull, v > 0);
-    const uint32_t neg = __ballot_sync(kFull, v < 0);
-    const uint32_t w1 = __ballot_sync(kFull, v <= -2);
-    const uint32_t w2 = __ballot_sync(kFull, v >= 2);
-    mover_on_bar = (pos >> (24 + player)) & 1u;
-    Masks m;
-    m.occ1 = (pos & 0xFFFFFFu) << 1;
-    m.occ2 = (neg & 0xFFFFFFu) << 1;
-    m.wall1 = (w1 & 0xFFFFFFu) << 1;
-    m.wall2 = (w2 & 0xFFFFFFu) << 1;
-    return m;
-}
-
-// apply a generated move (origin code o -> destination code d): cppsrc/game.cpp:624-659
-__device__ __forceinline__ int apply_on_lanes(int v, int lane, int player, int o, int d)
-{
-    const int m = player ? -1 : 1;
-    const bool from_bar = (o == 0) | (o == 25);
-    const bool off = (d == 0) | (d == 25);
-    const int src = from_bar ? 24 + player : o - 1;
-    const int dst = off ? 26 + player : d - 1;
-    const int dv = __shfl_sync(kFull, v, dst);
-    const bool hit = !off && dv == -m;                 // single enemy blot on the landing point
-    int nv = v;
-    if (lane == src) nv -= from_bar ? 1 : m;
-    if (lane == dst) nv = off ? nv + 1 : (hit ? m : nv + m);
-    if (hit && lane == 25 - player) nv += 1;           // the enemy's bar count
-    return nv;
-}
-
 // the five bit-planes of the row: the canonical 160-bit key of a position
 __device__ __forceinline__ void key_planes(int v, uint32_t k[5])
 {
@@ -86,71 +55,114 @@ __device__ __forceinline__ uint32_t hash_planes(const uint32_t k[5])
 }
 
 // ------------------------------------------------------------------------------------
+// the mover's view of a lane-distributed position
+// ------------------------------------------------------------------------------------
+struct Mover {
+    int lane, player;
+    int unit;             // what one checker of the mover adds to this lane: +-1 on points, +1 on bar/off lanes
+
+    __device__ __forceinline__ Mover(int ln, int pl) : lane(ln), player(pl) { unit = ln < 24 ? (pl ? -1 : 1) : 1; }
+
+    // legal origins of the mover on state v for one die (bgx_core.h legal_origins) from two ballots
+    __device__ __forceinline__ uint32_t legal_here(int v, int die) const
+    {
+        const int rel = lane < 24 ? v * unit : v;                         // mover-relative count; bar/off lanes as they are
+        const uint32_t own = __ballot_sync(kFull, rel > 0);
+        const uint32_t blk = __ballot_sync(kFull, rel < -1) & 0xFFFFFFu;  // points the mover cannot land on
+        const uint32_t occ = (own & 0xFFFFFFu) << 1, wall = blk << 1;
+        const bool on_bar = (own >> (24 + player)) & 1u;
+        if (player == 0) {
+            if (on_bar) return ((wall >> die) & 1u) ? 0u : 1u;
+            uint32_t legal = occ & ((~wall & kPoints) >> die);
+            if (occ != 0 && (occ & kP1Outside) == 0) {
+                legal |= occ & (1u << (25 - die));
+                const int hi = highest_bit(occ);
+                if (hi + die > 25) legal |= 1u << hi;
+            }
+            return legal;
+        }
+        if (on_bar) return ((wall >> (25 - die)) & 1u) ? 0u : (1u << 25);
+        uint32_t legal = occ & ((~wall & kPoints) << die) & kPoints;
+        if (occ != 0 && (occ & kP2Outside) == 0) {
+            legal |= occ & (1u << die);
+            const uint32_t any = (__ballot_sync(kFull, v != 0) & 0xFFFFFFu) << 1;   // either colour
+            const int hi = highest_bit(any & kP2Window);
+            if (hi < die && ((occ >> hi) & 1u)) legal |= 1u << hi;
+        }
+        return legal;
+    }
+
+    // lanes of the origin / destination codes
+    __device__ __forceinline__ int src_lane(int o) const { return (o == (player ? 25 : 0)) ? 24 + player : o - 1; }
+    __device__ __forceinline__ int dst_lane(int d) const { return (d == (player ? 0 : 25)) ? 26 + player : d - 1; }
+    __device__ __forceinline__ int unit_of_points() const { return player ? -1 : 1; }
+
+    // the child state (game.cpp:624-659); dval = what stood on the landing lane
+    __device__ __forceinline__ int apply(int v, int o, int d, int &dval) const
+    {
+        const int src = src_lane(o), dst = dst_lane(d);
+        dval = __shfl_sync(kFull, v, dst);
+        const bool hit = dst < 24 && dval * unit_of_points() == -1;
+        int t = lane == dst ? (hit ? 2 * unit : unit) : 0;
+        t -= lane == src ? unit : 0;
+        t += (hit && lane == 25 - player) ? 1 : 0;
+        return v + t;
+    }
+};
+
+// ------------------------------------------------------------------------------------
 // the turn tree: legalTurnSequences (cppsrc/game.cpp:134-191) + collectDoubles (109-131)
 // ------------------------------------------------------------------------------------
 // Leaf is called as leaf(state_of_this_lane, packed_moves_with_length, length) once per
 // legal turn sequence, in the reference's order, duplicates included.  All control flow
-// is warp-uniform; the per-depth stack lives in registers.
-#define BGX_STK_GET(a, d) ((d) == 0 ? a##0 : (d) == 1 ? a##1 : (d) == 2 ? a##2 : a##3)
-#define BGX_STK_SET(a, d, x)          \
-    do {                              \
-        if ((d) == 0) a##0 = (x);     \
-        else if ((d) == 1) a##1 = (x);\
-        else if ((d) == 2) a##2 = (x);\
-        else a##3 = (x);              \
-    } while (0)
+// is warp-uniform; the recursion is a template over the depth and fully inlined, so the
+// per-depth state lives in registers.
+template <class Leaf>
+struct TurnWalk : Mover {
+    Leaf &leaf;
+    int dieA, dieB;       // die of even / odd depths
+
+    __device__ __forceinline__ TurnWalk(Leaf &lf, int ln, int pl) : Mover(ln, pl), leaf(lf) {}
+
+    template <int D, bool kDbl>
+    __device__ __forceinline__ void visit(int v, uint64_t moves)
+    {
+        constexpr int kMax = kDbl ? 4 : 2;
+        uint32_t legal = 0;
+        if constexpr (D < kMax) legal = legal_here(v, (D & 1) ? dieB : dieA);
+        if (legal == 0) {
+            // a node without a move ends the sequence (game.cpp:117-121, 148-151); the root of a
+            // non-double pass emits nothing
+            if (kDbl || D > 0) leaf(v, moves | ((uint64_t)D << 40), D);
+            return;
+        }
+        if constexpr (D < kMax) {
+            const int die = (D & 1) ? dieB : dieA;
+            do {
+                const int o = lowest_bit(legal);
+                legal &= legal - 1;
+                const int d = destination(player, o, die);
+                int dv;
+                const int child = apply(v, o, d, dv);
+                visit<D + 1, kDbl>(child, moves | pack_move(o, d, D));
+            } while (legal);
+        }
+    }
+};
 
 template <class Leaf>
 __device__ __forceinline__ void walk_turn(int root, int lane, int player, int d1, int d2, Leaf &leaf)
 {
-    const bool dbl = d1 == d2;
-    const int maxlen = dbl ? 4 : 2;
-    const int npass = dbl ? 1 : 2;
-    for (int pass = 0; pass < npass; pass++) {
-        const int dieA = pass ? d2 : d1, dieB = pass ? d1 : d2;
-        int cur = root;
-        int sv0 = 0, sv1 = 0, sv2 = 0, sv3 = 0;             // node state per depth (this lane)
-        uint32_t lg0 = 0, lg1 = 0, lg2 = 0, lg3 = 0;        // origins still to try per depth
-        uint64_t prefix = 0;
-        int depth = 0;
-        bool entering = true;
-        for (;;) {
-            if (entering) {
-                uint32_t legal = 0;
-                if (depth < maxlen) {
-                    bool on_bar;
-                    const Masks mk = masks_on_lanes(cur, player, on_bar);
-                    legal = legal_origins(player, (depth & 1) ? dieB : dieA, mk, on_bar ? 1 : 0);
-                }
-                if (legal == 0) {
-                    // a node without a move ends the sequence (game.cpp:117-121, 148-151); the
-                    // root of a non-double pass emits nothing
-                    if (dbl || depth > 0)
-                        leaf(cur, (prefix & ((1ull << (10 * depth)) - 1)) | ((uint64_t)depth << 40), depth);
-                    if (depth == 0) break;
-                    depth--;
-                    cur = BGX_STK_GET(sv, depth);
-                    entering = false;
-                    continue;
-                }
-                BGX_STK_SET(lg, depth, legal);
-                BGX_STK_SET(sv, depth, cur);
-                entering = false;
-            }
-            const uint32_t rest = BGX_STK_GET(lg, depth);
-            if (rest == 0) {
-                if (depth == 0) break;
-                depth--;
-                cur = BGX_STK_GET(sv, depth);
-                continue;
-            }
-            const int o = lowest_bit(rest);
-            BGX_STK_SET(lg, depth, rest & (rest - 1));
-            const int d = destination(player, o, (depth & 1) ? dieB : dieA);
-            cur = apply_on_lanes(cur, lane, player, o, d);
-            prefix = (prefix & ~(0x3FFull << (10 * depth))) | pack_move(o, d, depth);
-            depth++;
-            entering = true;
+    TurnWalk<Leaf> w(leaf, lane, player);
+    if (d1 == d2) {
+        w.dieA = w.dieB = d1;
+        w.template visit<0, true>(root, 0ull);
+    } else {
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {          // game.cpp:143-188: d1 first, then d2 first
+            w.dieA = pass ? d2 : d1;
+            w.dieB = pass ? d1 : d2;
+            w.template visit<0, false>(root, 0ull);
         }
     }
 }

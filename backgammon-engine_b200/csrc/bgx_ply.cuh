@@ -249,11 +249,9 @@ __device__ __noinline__ float score_early_leaf(uint8_t *slots, uint32_t gen, uin
 // move changes in the network input, its pre-activation and its value are computed only for
 // afterstates that were not scored yet in this ply and for interior nodes.
 template <int kSets>
-struct PlyWalk {
+struct PlyWalk : Mover {
     const PlyEvaluator &ev;
     const PlyCache<kSets> &cache;
-    int lane, player;
-    int unit;             // what one checker of the mover adds to this lane: +-1 on points, +1 on bar/off lanes
     int c_me;             // feature block of the mover inside a point's 8 features (0 or 4)
     int dieA, dieB;       // die of even / odd depths
     uint32_t root_only;   // restricts the root's origins (all ones: no restriction)
@@ -265,61 +263,14 @@ struct PlyWalk {
     int n_seq, n_scored, n_visited;
 
     __device__ __forceinline__ PlyWalk(const PlyEvaluator &e, const PlyCache<kSets> &c, int ln, int pl)
-        : ev(e), cache(c), lane(ln), player(pl)
+        : Mover(ln, pl), ev(e), cache(c)
     {
-        unit = ln < 24 ? (pl ? -1 : 1) : 1;
         c_me = pl ? 4 : 0;
         root_only = kFull;
         best_key = __int_as_float(0xff800000);          // -inf
         best_v = 0; best_path = 0;
         n_seq = n_scored = n_visited = 0;
     }
-
-    // legal origins of the mover on state v (bgx_core.h legal_origins) from two ballots
-    __device__ __forceinline__ uint32_t legal_here(int v, int die) const
-    {
-        const int rel = lane < 24 ? v * unit : v;                         // mover-relative count; bar/off lanes as they are
-        const uint32_t own = __ballot_sync(kFull, rel > 0);
-        const uint32_t blk = __ballot_sync(kFull, rel < -1) & 0xFFFFFFu;  // points the mover cannot land on
-        const uint32_t occ = (own & 0xFFFFFFu) << 1, wall = blk << 1;
-        const bool on_bar = (own >> (24 + player)) & 1u;
-        if (player == 0) {
-            if (on_bar) return ((wall >> die) & 1u) ? 0u : 1u;
-            uint32_t legal = occ & ((~wall & kPoints) >> die);
-            if (occ != 0 && (occ & kP1Outside) == 0) {
-                legal |= occ & (1u << (25 - die));
-                const int hi = highest_bit(occ);
-                if (hi + die > 25) legal |= 1u << hi;
-            }
-            return legal;
-        }
-        if (on_bar) return ((wall >> (25 - die)) & 1u) ? 0u : (1u << 25);
-        uint32_t legal = occ & ((~wall & kPoints) << die) & kPoints;
-        if (occ != 0 && (occ & kP2Outside) == 0) {
-            legal |= occ & (1u << die);
-            const uint32_t any = (__ballot_sync(kFull, v != 0) & 0xFFFFFFu) << 1;   // either colour
-            const int hi = highest_bit(any & kP2Window);
-            if (hi < die && ((occ >> hi) & 1u)) legal |= 1u << hi;
-        }
-        return legal;
-    }
-
-    // lanes of the origin / destination codes
-    __device__ __forceinline__ int src_lane(int o) const { return (o == (player ? 25 : 0)) ? 24 + player : o - 1; }
-    __device__ __forceinline__ int dst_lane(int d) const { return (d == (player ? 0 : 25)) ? 26 + player : d - 1; }
-
-    // the child state (game.cpp:624-659); dval = what stood on the landing lane
-    __device__ __forceinline__ int apply(int v, int o, int d, int &dval) const
-    {
-        const int src = src_lane(o), dst = dst_lane(d);
-        dval = __shfl_sync(kFull, v, dst);
-        const bool hit = dst < 24 && dval * unit_of_points() == -1;
-        int t = lane == dst ? (hit ? 2 * unit : unit) : 0;
-        t -= lane == src ? unit : 0;
-        t += (hit && lane == 25 - player) ? 1 : 0;
-        return v + t;
-    }
-    __device__ __forceinline__ int unit_of_points() const { return player ? -1 : 1; }
 
     // pre-activation of the child reached from (vpar, zpar) by o -> d: 2 rows, 4 after a hit
     __device__ __forceinline__ int4 child_z(const int4 &zpar, int vpar, int o, int d, int dval) const

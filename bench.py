@@ -192,15 +192,26 @@ def side_legs(eng, dev, peaks, n_positions):
     chosen = torch.zeros((n, 32), dtype=torch.int8, device=dev)
     val = torch.zeros(n, dtype=torch.float32, device=dev)
     t_sel = best_ms(lambda: eng.select_moves(qd, chosen=chosen, value=val)) * 1e-3
-    rows = min(n, 1 << 20)
+    # the materialised list (batched evaluateTurnSequences): every sequence's moves, length and 32-byte state row
+    offs = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    offs[1:] = torch.cumsum(n_seq.to(torch.int64), 0)
+    mv = torch.empty((seqs, 8), dtype=torch.int8, device=dev)
+    ln = torch.empty(seqs, dtype=torch.int8, device=dev)
+    st = torch.empty((seqs, 32), dtype=torch.int8, device=dev)
+    t_wr = best_ms(lambda: eng.enumerate(qd, offs, mv, ln, st)) * 1e-3
+    del mv, ln, st
+    rows = 4 * n
+    qrep = qd.repeat(4, 1)
     X = torch.empty((rows, 198), dtype=torch.float32, device=dev)
-    t_enc = best_ms(lambda: eng.encode(qd[:rows], X)) * 1e-3
+    t_enc = best_ms(lambda: eng.encode(qrep, X)) * 1e-3
     enc_gbs = rows * (32 + 792) / t_enc / 1e9
     V = torch.zeros(n, dtype=torch.float32, device=dev)
     t_ev = best_ms(lambda: eng.evaluate(qd, V)) * 1e-3
     return {"positions": n, "sequences": seqs, "unique_afterstates": uniq,
             "enumerate": {"kernel": "k_enumerate_summary", "ms": t_enum * 1e3, "positions_per_sec": n / t_enum,
                           "sequences_per_sec": seqs / t_enum, "unique_afterstates_per_sec": uniq / t_enum},
+            "enumerate_materialised": {"kernel": "k_enumerate_write", "ms": t_wr * 1e3, "sequences_per_sec": seqs / t_wr,
+                                       "bytes_written_per_sequence": 41, "write_gbs": seqs * 41 / t_wr / 1e9},
             "select": {"kernel": "k_select", "ms": t_sel * 1e3, "positions_per_sec": n / t_sel,
                        "afterstates_enumerated_and_evaluated_per_sec": seqs / t_sel},
             "encode": {"kernel": "k_encode", "rows": rows, "ms": t_enc * 1e3, "rows_per_sec": rows / t_enc,
