@@ -163,6 +163,11 @@ class BatchEngine:
     def wait(self, lane):
         L.check(self._lib.bgx_lane_wait(self._h, int(lane)))
 
+    def advance(self, chosen, nxt, seed, ply, game_id=None, winner=None):
+        """device tensors: afterstates int8[n,32] -> next queries (mover flipped, dice of `ply` rolled, byte 31 = result)"""
+        L.check(self._lib.bgx_advance(self._h, L.ptr(chosen), L.ptr(nxt), chosen.shape[0], int(seed), int(ply),
+                                      L.ptr(game_id), L.ptr(winner)))
+
     def select_moves(self, queries, epsilon=0.0, seed=0, chosen=None, moves=None, moves_len=None, value=None,
                      n_seq=None, n_scored=None):
         L.check(self._lib.bgx_select_moves(self._h, L.ptr(queries), queries.shape[0], float(epsilon), int(seed),

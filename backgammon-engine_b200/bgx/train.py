@@ -43,6 +43,25 @@ def play_game(model, game_idx, epsilon=0.0):
         total_moves += 1
 
 
+def play_games_batch(model, n_games, epsilon=0.0, seed=0x5EED2026, device=0, first_id=0):
+    """`play_game` for n_games at once on the GPU: one self-play round from the model's current weights.
+    Returns a list of (winner, states, total_moves) with the reference's types (train.py:64-121): winner 0/1,
+    states = the pre-move encodings float32[198] of every ply, total_moves = len(states) - 1 — ready for
+    `apply_td_updates`.  Dice are Philox(seed, ply, first_id + i); opening roll-off as train.py:89-97."""
+    eng = model.engine(device)
+    eng.selfplay_init(n_games, first_id=first_id, id_stride=n_games, seed=seed, first_mover=L.FIRST_ROLLOFF, traj_cap=2048)
+    st = eng.selfplay_round(epsilon)
+    if st["truncated"]:
+        raise RuntimeError(f"{st['truncated']} games exceeded 2048 plies")
+    rec, ply, _ = eng.selfplay_read()
+    games = []
+    for slot in range(n_games):
+        pre, _ = eng.export_trajectory(slot)
+        X = eng.encode_host(pre)                                     # _encode_states_np with the mover's flag
+        games.append((int(rec[slot, 31]) - 1, [x for x in X], len(pre) - 1))
+    return games
+
+
 def apply_td_updates(model, optimizer, states, player1_won):
     """Online TD(lambda) over one recorded game (train.py:124-172): traces reset by the caller,
     weights and model.eligibility_traces updated in place, returns the squared TD errors."""
@@ -116,3 +135,35 @@ class GpuTrainer:
     def sync_model(self):
         self.model.load_engine_weights()
         return self.model
+
+
+# ------------------------------------------------------------------ checkpoints (train.py:361-381, 513-515)
+
+def model_compatible(path):
+    """True iff the checkpoint loads into the current TDLGammonModel architecture (train.py:361-368)."""
+    from .model import TDLGammonModel
+    try:
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+        TDLGammonModel().load_state_dict(sd)
+        return True
+    except Exception:
+        return False
+
+
+def latest_compatible_model(models_dir):
+    """Most recently modified .pth in `models_dir` that fits the 198-128-1 architecture, or None; the load
+    test skips the reference's old 3-layer checkpoints (train.py:371-381)."""
+    import os
+    if not os.path.isdir(models_dir):
+        return None
+    files = [f for f in os.listdir(models_dir) if f.endswith(".pth")]
+    files.sort(key=lambda f: os.path.getmtime(os.path.join(models_dir, f)), reverse=True)
+    for f in files:
+        if model_compatible(os.path.join(models_dir, f)):
+            return f
+    return None
+
+
+def save_checkpoint(model, path):
+    """The reference's checkpoint format: the 4-tensor state_dict (train.py:513-515)."""
+    torch.save(model.state_dict(), path)

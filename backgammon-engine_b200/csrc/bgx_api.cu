@@ -562,6 +562,21 @@ int bgx_lane_wait(bgx_engine *e, int lane)
     return BGX_OK;
 }
 
+int bgx_advance(bgx_engine *e, const int8_t *chosen, int8_t *next, int64_t n, uint64_t seed, int32_t ply,
+                const int64_t *game_id, int8_t *winner)
+{
+    USE(e);
+    NEED(chosen && next && n >= 0 && ply >= 0, "bad argument");
+    if (n == 0) return BGX_OK;
+    long long grid = (n + 7) / 8;
+    if (grid > (long long)e->sm_count * 8) grid = (long long)e->sm_count * 8;
+    k_advance<<<(int)grid, 256, 0, e->stream>>>(chosen, next, n, (uint32_t)seed, (uint32_t)(seed >> 32), ply,
+                                                (const long long *)game_id, winner);
+    e->launches++;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
 // ------------------------------------------------------------------------ self-play
 
 int bgx_selfplay_init(bgx_engine *e, int64_t n_slots, int64_t first_id, int64_t id_stride, uint64_t seed,

@@ -399,6 +399,24 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
     }
 }
 
+// ---- the rest of a host-driven ply: game over? flip the mover, roll the next dice ---------------
+__global__ void k_advance(const int8_t *__restrict__ chosen, int8_t *__restrict__ next, long long n, uint32_t seed_lo,
+                          uint32_t seed_hi, int ply, const long long *__restrict__ game_id, int8_t *__restrict__ winner)
+{
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int lane = threadIdx.x & 31;
+    for (long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += warps) {
+        const int b = load_record_byte(chosen + q * 32, lane);
+        const int off1 = __shfl_sync(kFull, b, 26), off2 = __shfl_sync(kFull, b, 27), mover = __shfl_sync(kFull, b, 28) ? 1 : 0;
+        const int win = off1 == 15 ? 0 : (off2 == 15 ? 1 : -1);            // game.cpp:388-407
+        const unsigned long long g = game_id ? (unsigned long long)game_id[q] : (unsigned long long)q;
+        const Philox r = philox4x32_10(seed_lo, seed_hi, (uint32_t)ply, (uint32_t)g, (uint32_t)(g >> 32), 0u);
+        const int tail = lane == 28 ? (win < 0 ? mover ^ 1 : mover) : lane == 29 ? die_of(r.x[0]) : lane == 30 ? die_of(r.x[1]) : win + 1;
+        next[q * 32 + lane] = (int8_t)(lane < 28 ? b : tail);
+        if (winner && lane == 0) winner[q] = (int8_t)win;
+    }
+}
+
 // ---- self-play population: play_game (train.py:64-121) for n_slots games at once ---------
 struct SelfplayParams {
     int8_t *slots;          // [n_slots][32]: position, byte 28 player to move, byte 31 status

@@ -179,6 +179,16 @@ int bgx_select_moves_host_async(bgx_engine *e, int lane, const int8_t *queries, 
                                 int32_t *n_seq, int32_t *n_scored);
 int bgx_lane_wait(bgx_engine *e, int lane);
 
+/* The rest of a host-driven ply (train.py:113-121, benchmark.py:88-101) for n games at once, on
+ * DEVICE buffers: next[i] = chosen[i] (an afterstate RECORD as bgx_select_moves writes it) with
+ *   byte 31 = 1 / 2 when the move ended the game for PLAYER1 / PLAYER2 (game.cpp:388-407, PLAYER1
+ *             is checked first), else 0 and the mover (byte 28) flipped,
+ *   bytes 29,30 = the dice of ply `ply` of game game_id[i] (NULL: i) under the self-play dice rule
+ *             (Philox key = seed, counter = (ply, id lo, id hi, 0)).
+ * winner[i] (may be NULL) = 0 / 1 / -1.  next may alias chosen. */
+int bgx_advance(bgx_engine *e, const int8_t *chosen, int8_t *next, int64_t n, uint64_t seed, int32_t ply,
+                const int64_t *game_id, int8_t *winner);
+
 /* ------------------------------------------------------------------------------------
  * 4. Self-play population (replaces play_game, train.py:64-121, for many games at once)
  * ---------------------------------------------------------------------------------- */

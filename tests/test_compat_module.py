@@ -85,6 +85,33 @@ def test_play_game_and_td_updates_compat(golden):
         assert np.array_equal(m.state_dict()[name].numpy(), g[f"trained5.new_{k}"]), k
 
 
+def test_checkpoint_discovery_skips_incompatible_files(tmp_path):
+    """save_checkpoint writes the reference's 4-tensor state_dict; latest_compatible_model picks the newest file
+    that loads into the 198-128-1 net and skips other architectures (train.py:361-381)."""
+    import os
+    import torch
+    from bgx.model import TDLGammonModel
+    from bgx.train import latest_compatible_model, model_compatible, save_checkpoint
+    assert latest_compatible_model(str(tmp_path / "missing")) is None
+    m = TDLGammonModel()
+    good = tmp_path / "tdgammon_a.pth"
+    save_checkpoint(m, str(good))
+    sd = torch.load(str(good), map_location="cpu", weights_only=True)
+    assert sorted(sd) == ["fc1.bias", "fc1.weight", "fc2.bias", "fc2.weight"]
+    assert sd["fc1.weight"].shape == (128, 198) and sd["fc2.weight"].shape == (1, 128)
+    old = tmp_path / "old3layer.pth"                       # the reference's earlier 3-layer checkpoints
+    torch.save({"fc1.weight": torch.zeros(80, 198), "fc1.bias": torch.zeros(80), "fc2.weight": torch.zeros(40, 80),
+                "fc2.bias": torch.zeros(40), "fc3.weight": torch.zeros(1, 40), "fc3.bias": torch.zeros(1)}, str(old))
+    (tmp_path / "notes.txt").write_text("not a checkpoint")
+    os.utime(str(good), (1000, 1000))
+    os.utime(str(old), (2000, 2000))                       # newer, but incompatible
+    assert model_compatible(str(good)) and not model_compatible(str(old))
+    assert latest_compatible_model(str(tmp_path)) == "tdgammon_a.pth"
+    m2 = TDLGammonModel()
+    m2.load_state_dict(sd)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
 def test_batch_engine_binding_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():

@@ -10,6 +10,7 @@ from conftest import golden_weights
 pytestmark = pytest.mark.gpu
 
 SEED = 0x5EED2026
+START_BOARD_NP = np.array([2, 0, 0, 0, 0, -5, 0, -3, 0, 0, 0, 5, -5, 0, 0, 0, 3, 0, 5, 0, 0, 0, 0, -2], np.int8)   # game.cpp:251
 
 
 @pytest.fixture(scope="module")
@@ -425,3 +426,93 @@ def test_td_round_delta_is_sum_of_per_game_replays(eng, orc, golden, tag):
     eng.apply_delta(delta, 0.5)
     after = np.concatenate([np.asarray(a).reshape(-1) for a in eng.get_weights()])
     assert np.allclose(after, flat0 + 0.5 * got[:25601], rtol=0, atol=1e-7 * np.max(np.abs(flat0)) + 1e-9)
+
+
+# ------------------------------------------------------------------ batched head-to-head (train.py:262-302, benchmark.py:64-130)
+
+def test_arena_games_replay_through_the_oracle(orc, golden):
+    """Every ply of every head-to-head game: dice follow the Philox rule, the mover alternates, the policy that
+    owns the mover picked the oracle's move (within the value tolerance), the winner is the reference's."""
+    from bgx.evaluate import Arena
+    gm = golden("model.npz")
+    wa, wb = golden_weights(gm, "trained"), golden_weights(gm, "rand")
+    n = 24
+    side = (np.arange(n) % 2).astype(np.int8)
+    first = ((np.arange(n) // 2) % 2).astype(np.int8)
+    arena = Arena(0)
+    try:
+        res = arena.play(wa, wb, side, first, seed=SEED, record=True)
+    finally:
+        arena.close()
+    assert (res["winner"] >= 0).all()
+    state = {i: None for i in range(n)}
+    count = np.zeros(n, np.int64)
+    soft = 0
+    for ply, idx, q, ch in res["log"]:
+        for j, g in enumerate(idx):
+            r = q[j]
+            x = orc.philox(SEED, ply, int(g))
+            assert (int(r[29]), int(r[30])) == (orc.die(x[0]), orc.die(x[1]))
+            assert int(r[28]) == (int(first[g]) ^ (ply & 1))
+            if state[g] is None:
+                assert np.array_equal(r[:24], START_BOARD_NP) and not r[24:28].any()
+            else:
+                assert np.array_equal(r[:28], state[g])
+            w = wa if int(r[28]) == int(side[g]) else wb
+            soft += check_choice(orc, w, r, ch[j])
+            state[g] = ch[j, :28].copy()
+            count[g] += 1
+    assert soft <= 0.1 * count.sum()
+    for g in range(n):
+        assert orc.game_over(state[g].astype(np.int32)) == int(res["winner"][g])
+        assert count[g] == res["plies"][g]
+
+
+def test_arena_reference_evaluation_loops(golden):
+    """evaluate_parallel / play_vs_random / play_vs_model on the GPU: a trained net beats the random policy and the
+    random-init net; a net against itself is even; results are reproducible."""
+    from bgx.evaluate import Arena, evaluate, play_vs_model, play_vs_random
+    gm = golden("model.npz")
+    wt, wr = golden_weights(gm, "trained"), golden_weights(gm, "rand")
+    arena = Arena(0)
+    try:
+        rate, avg_len = play_vs_random(arena, wt, 512)
+        assert rate > 0.9 and 20 < avg_len < 200
+        assert play_vs_random(arena, wt, 512) == (rate, avg_len)          # random draws are seeded too
+        assert evaluate(arena, wt, wr, 512) > 0.85
+        r1, _ = play_vs_model(arena, wt, wt, 2048)
+        assert 0.42 < r1 < 0.58
+    finally:
+        arena.close()
+
+
+def test_play_games_batch_feeds_the_reference_td_update(eng, golden):
+    """bgx.train.play_games_batch returns play_game's tuples; the reference-contract apply_td_updates (torch autograd,
+    CPU) on those states and the GPU replay of the same trajectory give the same weights."""
+    import torch
+    from bgx.model import TDLGammonModel
+    from bgx.train import apply_td_updates, play_games_batch
+    W1, b1, w2, b2 = golden_weights(golden("model.npz"), "trained")
+    sd = {"fc1.weight": torch.from_numpy(W1), "fc1.bias": torch.from_numpy(b1),
+          "fc2.weight": torch.from_numpy(w2), "fc2.bias": torch.from_numpy(b2)}
+    m = TDLGammonModel()
+    m.load_state_dict(sd)
+    games = play_games_batch(m, 6, seed=SEED, first_id=40)
+    assert len(games) == 6
+    for winner, states, total in games:
+        assert winner in (0, 1) and len(states) == total + 1
+        assert states[0].shape == (198,) and states[0].dtype == np.float32
+        assert states[0][:192].sum() == 26.0 and states[0][192] + states[0][193] == 1.0      # the opening position
+    winner, states, _ = min(games, key=lambda g: len(g[1]))
+    m.update_learning_params(1)
+    m.initialize_traces()
+    apply_td_updates(m, torch.optim.SGD(m.parameters(), lr=0.1), states, winner == 0)
+    eng.set_weights(W1, b1, w2, b2)
+    # the same trajectory as records: slot order is game order
+    idx = [i for i, g in enumerate(games) if g[1] is states][0]
+    pre, _ = m.engine(0).export_trajectory(idx)
+    new, _ = eng.td_replay_host(pre, winner == 0, m.learning_rate, m.lambda_decay)
+    for a, name in zip(new, ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")):
+        ref = m.state_dict()[name].numpy().reshape(-1)
+        d_ref = ref - sd[name].numpy().reshape(-1)
+        assert np.max(np.abs(np.asarray(a).reshape(-1) - ref)) <= td_tol(d_ref, ref), name
