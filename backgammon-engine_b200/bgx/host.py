@@ -60,3 +60,17 @@ def turn_sequences(position, player, d1, d2):
 def sequences_as_lists(position, player, d1, d2):
     mv, ln, st = turn_sequences(position, player, d1, d2)
     return [[(int(mv[i, j, 0]), int(mv[i, j, 1])) for j in range(ln[i])] for i in range(len(ln))], st
+
+
+def advance(chosen, nxt, seed, ply=None, game_id=None, winner=None):
+    """bgx_advance_host: the rest of a host-driven ply for n games (train.py:113-121) on numpy buffers.
+    chosen int8[n,32] afterstate records -> nxt int8[n,32] (may be `chosen`): byte 31 = 1/2 when the game ended,
+    else mover flipped; bytes 29,30 = Philox dice of (seed, ply[i], game_id[i]).  winner int8[n] optional."""
+    n = chosen.shape[0]
+    for a in (chosen, nxt):
+        assert a.dtype == np.int8 and a.flags["C_CONTIGUOUS"] and a.shape == (n, 32)
+    L.check(L.load().bgx_advance_host(chosen.ctypes.data, nxt.ctypes.data, n, int(seed),
+                                      None if ply is None else ply.ctypes.data,
+                                      None if game_id is None else game_id.ctypes.data,
+                                      None if winner is None else winner.ctypes.data))
+    return nxt

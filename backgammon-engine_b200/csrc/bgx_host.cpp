@@ -11,6 +11,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace bgx {
 
@@ -234,6 +235,32 @@ int bgx_turn_sequences(const int32_t *position, int player, int d1, int d2, int6
     }
     *n = out.n;
     if (out.n > cap) { set_error("bgx_turn_sequences: %lld sequences, cap %lld", (long long)out.n, (long long)cap); return BGX_E_CAPACITY; }
+    return BGX_OK;
+}
+
+int bgx_advance_host(const int8_t *chosen, int8_t *next, int64_t n, uint64_t seed, const int32_t *ply,
+                     const int64_t *game_id, int8_t *winner)
+{
+    if (!chosen || !next || n < 0) { set_error("bgx_advance_host: bad argument"); return BGX_E_INVALID; }
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    // a Philox block per game: ~15 ns each, so big batches are split over a few host threads
+    int threads = (int)std::thread::hardware_concurrency();
+    threads = threads > 8 ? 8 : (threads < 1 ? 1 : threads);
+#pragma omp parallel for schedule(static) num_threads(threads) if (n >= 4096)
+    for (int64_t i = 0; i < n; i++) {
+        const int8_t *c = chosen + 32 * i;
+        int8_t *o = next + 32 * i;
+        const int win = c[26] == 15 ? 0 : (c[27] == 15 ? 1 : -1);           // game.cpp:388-407
+        const uint64_t g = game_id ? (uint64_t)game_id[i] : (uint64_t)i;
+        const Philox r = philox4x32_10(k0, k1, ply ? (uint32_t)ply[i] : 0u, (uint32_t)g, (uint32_t)(g >> 32), 0u);
+        const int mover = c[28] ? 1 : 0;
+        if (o != c) std::memcpy(o, c, 28);
+        o[28] = (int8_t)(win < 0 ? mover ^ 1 : mover);
+        o[29] = (int8_t)die_of(r.x[0]);
+        o[30] = (int8_t)die_of(r.x[1]);
+        o[31] = (int8_t)(win + 1);
+        if (winner) winner[i] = (int8_t)win;
+    }
     return BGX_OK;
 }
 

@@ -341,7 +341,7 @@ struct PlySmem {
             share->slot[threadIdx.x].pending = 0;
             share->slot[threadIdx.x].nres = 0;
         }
-        if (threadIdx.x == 0) share->active = kWarps;
+        if (threadIdx.x == 0) { share->active = kWarps; share->urgent = 0; }
     }
 };
 
@@ -361,16 +361,26 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
     PlyEvaluator ev;
     ev.T4 = reinterpret_cast<const int4 *>(sm.table);
     ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, aux, lane);
-    StealSlot *mine = &sm.share->slot[warp];
     StealResult *cta_results = steal + (size_t)blockIdx.x * kWarps * kStealMaxResults;
-    StealResult *my_results = cta_results + warp * kStealMaxResults;
+    const ShareCtx mine = {&sm.share->slot[warp], cta_results + warp * kStealMaxResults, &sm.share->urgent, 1u << warp,
+                           counter, 0ull, 8};                 // one ply per launch: latency first
     bool helping = false;
     for (;;) {
         int root = 0, player = 0, d1 = 0, d2 = 0, vw = 0;
-        uint32_t only = kFull, u = 0;
+        uint32_t only = 0, u = 0;
         long long q = 0;
         bool explore = false;
-        if (!helping) {
+        // a sub-tree of a neighbour's double: whenever the queue is empty, and before new queue work if it is a huge one
+        if (helping || *(volatile uint32_t *)&sm.share->urgent != 0) {
+            bool done;
+            only = take_child<kWarps>(sm.share, lane, vw, root, player, d1, done, !helping);
+            d2 = d1;
+            if (helping && only == 0) {
+                if (done) break;
+                continue;
+            }
+        }
+        if (only == 0) {
             q = claim(counter, lane);
             if (q >= n) {                                   // queue empty: help the owners of big doubles
                 helping = true;
@@ -385,16 +395,10 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
                 explore = (float)r.x[0] * 2.3283064365386963e-10f < epsilon;
                 u = r.x[1];
             }
-        } else {
-            bool done;
-            only = take_child<kWarps>(sm.share, lane, vw, root, player, d1, done);
-            if (done) break;
-            if (only == 0) continue;
-            d2 = d1;
         }
-        const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, player, d1, d2, ev, cache, explore, u, only,
-                                                          helping ? nullptr : mine, my_results);
-        if (helping) deliver_child<kWarps>(sm.share, cta_results, vw, only, c, lane);
+        const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, player, d1, d2, ev, cache, explore, u, only ? only : kFull,
+                                                          only ? nullptr : &mine);
+        if (only) deliver_child<kWarps>(sm.share, cta_results, vw, only, c, lane);
         else store_choice(out, q, c, lane, player);
     }
 }
@@ -449,9 +453,9 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
     PlyEvaluator ev;
     ev.T4 = reinterpret_cast<const int4 *>(sm.table);
     ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, aux, lane);
-    StealSlot *mine = &sm.share->slot[warp];
     StealResult *cta_results = steal + (size_t)blockIdx.x * kWarps * kStealMaxResults;
-    StealResult *my_results = cta_results + warp * kStealMaxResults;
+    const ShareCtx mine = {&sm.share->slot[warp], cta_results + warp * kStealMaxResults, &sm.share->urgent, 1u << warp,
+                           p.counter, (unsigned long long)(p.n_slots - p.n_slots / 4), 8};
 
     unsigned long long s_plies = 0, s_seq = 0, s_scored = 0, s_fin = 0, s_p1 = 0, s_trunc = 0, s_visited = 0;
     const int budget = p.round_mode ? 0x7fffffff : p.n_plies;
@@ -459,12 +463,22 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
     long long slot = 0;
     int v = 0, player = 0, status = kRunning, ply = 0, step = 0;
     unsigned long long gid = 0;
-    // one iteration = one ply: of the slot this warp is seated at, or (queue empty) of a sub-tree taken from a neighbour
+    // one iteration = one ply: of the slot this warp is seated at, or of a sub-tree taken from a neighbour
+    // (whenever the queue is empty, and before its own next ply if the neighbour's double is a huge one)
     for (;;) {
         int root = 0, mover = 0, d1 = 0, d2 = 0, vw = 0;
-        uint32_t only = kFull, u = 0;
+        uint32_t only = 0, u = 0;
         bool explore = false, rec_traj = false;
-        if (!helping) {
+        if (helping || *(volatile uint32_t *)&sm.share->urgent != 0) {
+            bool done;
+            only = take_child<kWarps>(sm.share, lane, vw, root, mover, d1, done, !helping);
+            d2 = d1;
+            if (helping && only == 0) {
+                if (done) break;
+                continue;
+            }
+        }
+        if (only == 0) {
             if (!seated) {
                 slot = claim(p.counter, lane);
                 if (slot >= p.n_slots) {
@@ -503,17 +517,11 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
                 root = v;
                 mover = player;
             }
-        } else {
-            bool done;
-            only = take_child<kWarps>(sm.share, lane, vw, root, mover, d1, done);
-            if (done) break;
-            if (only == 0) continue;
-            d2 = d1;
         }
-        if (helping || seated) {
-            const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, mover, d1, d2, ev, cache, explore, u, only,
-                                                              helping ? nullptr : mine, my_results);   // model.py:180-222
-            if (helping) {
+        if (only || seated) {
+            const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, mover, d1, d2, ev, cache, explore, u, only ? only : kFull,
+                                                              only ? nullptr : &mine);                  // model.py:180-222
+            if (only) {
                 deliver_child<kWarps>(sm.share, cta_results, vw, only, c, lane);
                 continue;
             }

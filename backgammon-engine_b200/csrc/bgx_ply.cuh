@@ -366,6 +366,9 @@ struct PlyWalk : Mover {
 // order, the merge prefers the better value and, on equal values, the lower root origin, which
 // is the reference's first-index rule (model.py:212-213); N is the sum of the parts.
 constexpr int kStealMinChildren = 4;     // root origins from which a double is worth publishing
+constexpr int kGiantMinChildren = 10;    // ... and from which its CTA helps at once wherever the double sits in the queue
+// (ShareCtx::urgent_min / urgent_from: the same for smaller doubles from a queue position on - a one-ply launch wants
+// that everywhere, a many-ply launch only in its last stretch, because helpers re-score what the owner's cache holds)
 constexpr int kStealMaxResults = 16;     // >= the 15 origins a root can have
 
 struct StealSlot {                       // shared memory, one per warp
@@ -387,7 +390,19 @@ template <int kWarps>
 struct StealShared {
     StealSlot slot[kWarps];
     int32_t active;                      // warps that still own queue work
-    int32_t pad[3];
+    uint32_t urgent;                     // warps whose published double is so big that the others help before claiming new work
+    int32_t pad[2];
+};
+
+// what a warp needs to publish its doubles: its slot, its result area, the CTA's urgent mask and its bit in it
+struct ShareCtx {
+    StealSlot *slot;
+    StealResult *results;
+    uint32_t *urgent;
+    uint32_t my_bit;
+    const unsigned long long *queue;     // the launch's work-queue counter ...
+    unsigned long long urgent_from;      // ... and the position from which big doubles are urgent
+    int urgent_min;                      // root origins that make a double "big" for that purpose
 };
 
 __device__ __forceinline__ Choice finish_choice(const uint32_t best_path, float best_key, int best_v, int n_seq, int n_scored,
@@ -416,9 +431,10 @@ __device__ __forceinline__ Choice finish_choice(const uint32_t best_path, float 
 // slot/results: the caller's sharing slot (nullptr: never publish).
 template <int kSets>
 __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int d1, int d2, const PlyEvaluator &ev,
-                                             PlyCache<kSets> &cache, uint32_t root_only = kFull,
-                                             StealSlot *slot = nullptr, StealResult *results = nullptr)
+                                             PlyCache<kSets> &cache, uint32_t root_only = kFull, const ShareCtx *share = nullptr)
 {
+    StealSlot *slot = share ? share->slot : nullptr;
+    StealResult *results = share ? share->results : nullptr;
     cache.next_ply(lane);
     PlyWalk<kSets> w(ev, cache, lane, player);
     w.root_only = root_only;
@@ -437,7 +453,14 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
                 if (lane == 0) { slot->meta = (uint32_t)player | ((uint32_t)d1 << 8); slot->nres = 0; }
                 __threadfence_block();
                 __syncwarp();
-                if (lane == 0) atomicExch(&slot->legal0, legal);
+                if (lane == 0) {
+                    atomicExch(&slot->legal0, legal);
+                    // near the end of the queue a huge double is the tail of the launch: ask for help at once
+                    const int kids = __popc(legal);
+                    if (kids >= kGiantMinChildren ||
+                        (kids >= share->urgent_min && *(volatile const unsigned long long *)share->queue >= share->urgent_from))
+                        atomicOr(share->urgent, share->my_bit);
+                }
             }
             for (;;) {
                 uint32_t bit = 0;
@@ -463,6 +486,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
                 w.n_visited++;
                 w.template visit<1, true>(child, w.zroot, root, oc, dc, dv, (uint32_t)oc);
             }
+            if (shared && lane == 0) atomicAnd(share->urgent, ~share->my_bit);
         }
     } else {
         float key1 = 0.f;
@@ -507,12 +531,16 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
 // from warp `vw` (filling root / player / die), 0 when there is nothing to take right now, and
 // sets `done` once every warp of the CTA has left the queue.
 template <int kWarps>
-__device__ __forceinline__ uint32_t take_child(StealShared<kWarps> *sh, int lane, int &vw, int &root, int &player, int &die, bool &done)
+__device__ __forceinline__ uint32_t take_child(StealShared<kWarps> *sh, int lane, int &vw, int &root, int &player, int &die, bool &done,
+                                               bool urgent_only = false)
 {
     done = false;
     const uint32_t avail = lane < kWarps ? *(volatile uint32_t *)&sh->slot[lane].legal0 : 0u;
-    const uint32_t m = __ballot_sync(kFull, avail != 0);
-    if (m == 0) {
+    uint32_t m = __ballot_sync(kFull, avail != 0);
+    if (urgent_only) {
+        m &= *(volatile uint32_t *)&sh->urgent;
+        if (m == 0) return 0u;
+    } else if (m == 0) {
         done = __shfl_sync(kFull, *(volatile int32_t *)&sh->active, 0) <= 0;
         if (!done) __nanosleep(200);
         return 0u;
@@ -562,7 +590,7 @@ __device__ __forceinline__ void deliver_child(StealShared<kWarps> *sh, StealResu
 template <int kSets, bool kExplore>
 __device__ __forceinline__ Choice choose_ply_fast(int root, int lane, int player, int d1, int d2, const PlyEvaluator &ev,
                                                   PlyCache<kSets> &cache, bool explore, uint32_t u,
-                                                  uint32_t root_only = kFull, StealSlot *slot = nullptr, StealResult *results = nullptr)
+                                                  uint32_t root_only = kFull, const ShareCtx *share = nullptr)
 {
     if (kExplore && explore) {
         CountLeaf cnt;
@@ -577,7 +605,7 @@ __device__ __forceinline__ Choice choose_ply_fast(int root, int lane, int player
         }
         return c;
     }
-    return greedy_ply<kSets>(root, lane, player, d1, d2, ev, cache, root_only, slot, results);
+    return greedy_ply<kSets>(root, lane, player, d1, d2, ev, cache, root_only, share);
 }
 
 } // namespace bgx

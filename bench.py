@@ -280,52 +280,59 @@ def run_ours(args):
     value = plies_all / total_s
 
     # ---- end to end: host-driven self-play through the batched make_move C-ABI call, pinned host buffers.
-    # The population is split into two halves, each on its own asynchronous lane: while the GPU plays
-    # one half (H2D of its records, k_select, D2H of the chosen afterstates) the host advances the other
+    # The population is split into four parts, each on its own asynchronous lane: while the GPU plays
+    # some (H2D of the records, k_select, D2H of the chosen afterstates) the host advances another
     # (game over?, restart, flip the mover, next dice) - the loop of train.py:99-121 for 65,536 games.
     e2e_steps = max(2, min(args.steps, 8)) * PLIES_PER_STEP
+    from bgx import host as bgx_host
+    LANES = 2
     q_pin = torch.zeros((G, 32), dtype=torch.int8).pin_memory()
     ch_pin = torch.zeros((G, 32), dtype=torch.int8).pin_memory()
     val_pin = torch.zeros(G, dtype=torch.float32).pin_memory()
     q, ch, val = q_pin.numpy(), ch_pin.numpy(), val_pin.numpy()
-    rec, _, _ = eng.selfplay_read()          # continue the (desynchronised) games of the population from the host
+    rec, h_ply, h_gid = eng.selfplay_read()          # continue the (desynchronised) games of the population from the host
     q[:] = rec
-    q[:, 31] = 0
-    rng = np.random.default_rng(SEED + rank)
-    halves = [(0, G // 2), (G // 2, G)]
+    h_win = np.zeros(G, np.int8)
+    parts = [(i * G // LANES, (i + 1) * G // LANES) for i in range(LANES)]
+    stride = world * G
 
     def submit(h):
-        lo, hi = halves[h]
-        q[lo:hi, 29:31] = rng.integers(1, 7, (hi - lo, 2), dtype=np.int8)
+        lo, hi = parts[h]
         eng.select_moves_host_async(h, q[lo:hi], {"chosen": ch[lo:hi], "value": val[lo:hi]})
 
     def advance(h):
-        lo, hi = halves[h]
+        lo, hi = parts[h]
         eng.wait(h)
-        c = ch[lo:hi]
-        over = (c[:, 26] == 15) | (c[:, 27] == 15)
-        q[lo:hi, :28] = c[:, :28]
-        q[lo:hi, 28] ^= 1
-        if over.any():
-            idx = np.flatnonzero(over) + lo
-            q[idx, :24] = START_BOARD
-            q[idx, 24:28] = 0
+        h_ply[lo:hi] += 1
+        bgx_host.advance(ch[lo:hi], q[lo:hi], SEED, h_ply[lo:hi], h_gid[lo:hi], h_win[lo:hi])   # over? flip mover, roll
+        done = np.flatnonzero(h_win[lo:hi] >= 0)
+        if done.size:                                   # restart in place with the next game id (first mover: id % 2)
+            idx = done + lo
+            h_gid[idx] += stride
+            h_ply[idx] = 0
+            fresh = np.zeros((idx.size, 32), np.int8)
+            fresh[:, :24] = START_BOARD
+            fresh[:, 28] = (h_gid[idx] & 1) ^ 1         # bgx_advance_host flips it and rolls ply 0
+            q[idx] = bgx_host.advance(fresh, fresh, SEED, h_ply[idx], h_gid[idx])
         return hi - lo
 
-    submit(0)
-    submit(1)
+    bgx_host.advance(q, q, SEED, h_ply, h_gid)           # dice of the current ply for every game (undo the flip below)
+    q[:, 28] ^= 1
+    q[:, 31] = 0
+    for h in range(LANES):
+        submit(h)
     e2e_plies = 0
-    for it in range(-2, e2e_steps):                 # 2 untimed warm-up plies
+    for it in range(-2, e2e_steps):                 # 2 untimed warm-up ply-steps
         if it == 0:
             barrier()                               # drains nothing of ours: the lanes are non-blocking streams
             t0 = time.perf_counter()
-        for h in (0, 1):
+        for h in range(LANES):
             n_adv = advance(h)
             submit(h)
             if it >= 0:
                 e2e_plies += n_adv
-    eng.wait(0)
-    eng.wait(1)
+    for h in range(LANES):
+        eng.wait(h)
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
@@ -390,9 +397,9 @@ def run_ours(args):
                 "sequences_per_ply": seqs_all / plies_all, "scored_per_ply": scored_all / plies_all,
                 "tree_edges_per_ply_rank0": edges / max(plies, 1), "ply_warps_per_cta": int(os.environ.get("BGX_PLY_WARPS", "16")),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 32, "d2h_bytes_per_step": G * 36,
-                        "note": "one step = one ply for all 65,536 games through bgx_select_moves_host_async (two half-populations "
-                                "on two lanes, pinned host buffers, H2D + k_select + D2H per ply); "
-                                f"{e2e_steps} timed ply-steps incl. the numpy host loop that advances the games"},
+                        "note": "one step = one ply for all 65,536 games through bgx_select_moves_host_async (four quarter-populations "
+                                "on four lanes, pinned host buffers, H2D + k_select + D2H per ply), bgx_advance_host + numpy restarts "
+                                f"on the host between plies; {e2e_steps} timed ply-steps"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -188,6 +188,10 @@ int bgx_lane_wait(bgx_engine *e, int lane);
  * winner[i] (may be NULL) = 0 / 1 / -1.  next may alias chosen. */
 int bgx_advance(bgx_engine *e, const int8_t *chosen, int8_t *next, int64_t n, uint64_t seed, int32_t ply,
                 const int64_t *game_id, int8_t *winner);
+/* The same on HOST buffers, for a host loop around bgx_select_moves_host[_async] whose games are not in
+ * lockstep: ply[i] is the ply whose dice game i gets (the caller counts; NULL: 0), no engine needed. */
+int bgx_advance_host(const int8_t *chosen, int8_t *next, int64_t n, uint64_t seed, const int32_t *ply,
+                     const int64_t *game_id, int8_t *winner);
 
 /* ------------------------------------------------------------------------------------
  * 4. Self-play population (replaces play_game, train.py:64-121, for many games at once)

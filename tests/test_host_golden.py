@@ -113,3 +113,33 @@ def test_engine_fails_loudly_without_gpu():
     with pytest.raises(BgxError) as ei:
         BatchEngine(0)
     assert ei.value.code == -2 and "no CPU path" in str(ei.value)
+
+
+def test_advance_host_matches_the_dice_rule_and_game_over(orc):
+    """bgx_advance_host = the rest of a host-driven ply (train.py:113-121): winner as Game::over reports it
+    (PLAYER1 first, game.cpp:388-407), mover flipped unless the game ended, Philox dice of (seed, ply, game id)."""
+    from bgx import host
+    rng = np.random.default_rng(3)
+    n = 500
+    c = np.zeros((n, 32), np.int8)
+    c[:, :24] = rng.integers(-3, 4, (n, 24))
+    c[:, 26] = rng.choice([0, 3, 15], n)
+    c[:, 27] = rng.choice([0, 7, 15], n)
+    c[:, 28] = rng.integers(0, 2, n)
+    ply = rng.integers(0, 400, n).astype(np.int32)
+    gid = rng.integers(0, 2 ** 40, n).astype(np.int64)
+    win = np.zeros(n, np.int8)
+    seed = 0x0123456789ABCDEF
+    nxt = host.advance(c, np.zeros_like(c), seed, ply, gid, win)
+    for i in range(n):
+        w = orc.game_over(c[i, :28].astype(np.int32))
+        assert win[i] == w and nxt[i, 31] == w + 1
+        assert np.array_equal(nxt[i, :28], c[i, :28])
+        assert nxt[i, 28] == (c[i, 28] if w >= 0 else c[i, 28] ^ 1)
+        x = orc.philox(seed, int(ply[i]), int(gid[i]) & 0xFFFFFFFF, int(gid[i]) >> 32)
+        assert (nxt[i, 29], nxt[i, 30]) == (orc.die(x[0]), orc.die(x[1]))
+    # in place, defaults (ply 0, game id = index)
+    d = c.copy()
+    host.advance(d, d, seed)
+    x = orc.philox(seed, 0, 7, 0)
+    assert (d[7, 29], d[7, 30]) == (orc.die(x[0]), orc.die(x[1]))
