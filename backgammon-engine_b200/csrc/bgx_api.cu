@@ -157,6 +157,7 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaEventCreate(&e->ev1));
     CU(cudaEventCreateWithFlags(&e->ev_sync, cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, kEvalSmem));
+    CU(cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmem));
     {
         const char *w = getenv("BGX_PLY_WARPS");       // tuning knob: 16 (default), 24 or 32 warps per CTA
         e->ply_warps = w ? atoi(w) : 16;
@@ -371,10 +372,10 @@ int bgx_encode(bgx_engine *e, const int8_t *records, int64_t n, float *X)
     NEED(((uintptr_t)X & 15) == 0 && ((uintptr_t)records & 3) == 0, "X must be 16-byte aligned, records 4-byte aligned");
     if (n == 0) return BGX_OK;
     const long long tiles = (n + kEncRows - 1) / kEncRows;
-    long long grid = (long long)e->sm_count * 8;
+    long long grid = (long long)e->sm_count * 4;     // 4 CTAs of 2 x 25 KB tiles are resident per SM
     if (grid > tiles) grid = tiles;
     tick(e);
-    k_encode<<<(int)grid, kEncWarps * 32, 0, e->stream>>>(records, n, X);
+    k_encode<<<(int)grid, kEncWarps * 32, kEncSmem, e->stream>>>(records, n, X);
     tock(e);
     e->launches++;
     CU(cudaGetLastError());

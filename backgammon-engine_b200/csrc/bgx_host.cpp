@@ -238,14 +238,32 @@ int bgx_turn_sequences(const int32_t *position, int player, int d1, int d2, int6
     return BGX_OK;
 }
 
+// host threads of bgx_advance_host: BGX_HOST_THREADS, else this process's share of the cores when several ranks
+// run on one box (torchrun exports LOCAL_WORLD_SIZE), at most 8
+static int advance_threads()
+{
+    static int cached = 0;
+    if (cached) return cached;
+    int t;
+    if (const char *e = std::getenv("BGX_HOST_THREADS")) {
+        t = std::atoi(e);
+    } else {
+        const char *l = std::getenv("LOCAL_WORLD_SIZE");
+        const int ranks = l ? std::atoi(l) : 1;
+        t = (int)std::thread::hardware_concurrency() / (ranks > 0 ? ranks : 1);
+        if (t > 8) t = 8;
+    }
+    cached = t < 1 ? 1 : (t > 64 ? 64 : t);
+    return cached;
+}
+
 int bgx_advance_host(const int8_t *chosen, int8_t *next, int64_t n, uint64_t seed, const int32_t *ply,
                      const int64_t *game_id, int8_t *winner)
 {
     if (!chosen || !next || n < 0) { set_error("bgx_advance_host: bad argument"); return BGX_E_INVALID; }
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     // a Philox block per game: ~15 ns each, so big batches are split over a few host threads
-    int threads = (int)std::thread::hardware_concurrency();
-    threads = threads > 8 ? 8 : (threads < 1 ? 1 : threads);
+    const int threads = advance_threads();
 #pragma omp parallel for schedule(static) num_threads(threads) if (n >= 4096)
     for (int64_t i = 0; i < n; i++) {
         const int8_t *c = chosen + 32 * i;

@@ -207,20 +207,27 @@ k_enumerate_write(const int8_t *__restrict__ queries, long long n, const long lo
 }
 
 // ---- _encode_states_np (model.py:111-144): records -> fp32 [n][198], HBM-bound -----------
-// A CTA stages a tile of kEncRows rows (kEncRows*792 B, a 16-byte multiple starting on a
-// 16-byte boundary because tiles start on even rows) in shared memory, then streams it out
-// with 16-byte vector stores: every store instruction of a warp covers 512 contiguous bytes.
+// A CTA builds a tile of kEncRows rows (kEncRows * 792 B, contiguous in X and a 16-byte multiple starting
+// on a 16-byte boundary because tiles start on even rows) in shared memory and hands it to the TMA engine:
+// one cp.async.bulk.global.shared per tile (SASS UBLKCP), two tiles in flight per CTA, so the store
+// stream costs the SM one instruction per 25 KB and overlaps the encoding of the next tile.
 constexpr int kEncWarps = 8;
 constexpr int kEncRows = 32;                        // rows per tile (4 per warp)
 constexpr int kEncTileFloats = kEncRows * kFeatures;
+constexpr int kEncSmem = 2 * kEncTileFloats * 4;    // 50,688 B
 
 __global__ void __launch_bounds__(kEncWarps * 32)
 k_encode(const int8_t *__restrict__ records, long long n, float *__restrict__ X)
 {
-    __shared__ __align__(16) float tile[kEncTileFloats];
+    extern __shared__ __align__(128) float enc_tiles[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long n_tiles = (n + kEncRows - 1) / kEncRows;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    int buf = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, buf ^= 1) {
+        float *tile = enc_tiles + buf * kEncTileFloats;
+        // the bulk store that last read this buffer (two tiles ago) must have finished reading it
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
         const long long row0 = t * kEncRows;
         // 4 records (128 B) per warp in one coalesced 4-byte-per-lane load
         const long long r_first = row0 + warp * 4;
@@ -233,9 +240,8 @@ k_encode(const int8_t *__restrict__ records, long long n, float *__restrict__ X)
         for (int r = 0; r < 4; r++) {
             const int w = __shfl_sync(kFull, word, r * 8 + (lane >> 2));
             const int v = (int)(int8_t)(w >> (8 * (lane & 3)));        // byte `lane` of record r
-            const int turn = __shfl_sync(kFull, v, 28);
-            const int jail1 = __shfl_sync(kFull, v, 24), jail2 = __shfl_sync(kFull, v, 25);
-            const int off1 = __shfl_sync(kFull, v, 26), off2 = __shfl_sync(kFull, v, 27);
+            // every lane encodes the element it holds: lanes 0..23 a point (8 features), 24..27 a bar / borne-off
+            // count (1 feature), 28 the turn flag (2 features); no cross-lane traffic, no divergent slow paths
             float *row = tile + (warp * 4 + r) * kFeatures;
             if (lane < 24) {
                 const int c = v < 0 ? -v : v;
@@ -247,27 +253,30 @@ k_encode(const int8_t *__restrict__ records, long long n, float *__restrict__ X)
                 dst[1] = p1 ? make_float2(cc, d) : make_float2(0.f, 0.f);
                 dst[2] = p1 ? make_float2(0.f, 0.f) : make_float2(a, b);
                 dst[3] = p1 ? make_float2(0.f, 0.f) : make_float2(cc, d);
-            } else if (lane == 24) {
-                row[192] = turn == 0 ? 1.f : 0.f;
-                row[193] = turn == 0 ? 0.f : 1.f;
-                row[194] = (float)jail1 * 0.5f;
-                row[195] = (float)jail2 * 0.5f;
-            } else if (lane == 25) {
-                row[196] = off_feature(off1);
-                row[197] = off_feature(off2);
+            } else if (lane < 28) {
+                row[170 + lane] = lane < 26 ? (float)v * 0.5f : kOffFeature[v & 15];
+            } else if (lane == 28) {
+                *reinterpret_cast<float2 *>(row + 192) = v == 0 ? make_float2(1.f, 0.f) : make_float2(0.f, 1.f);
             }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the TMA engine
         __syncthreads();
         const long long rows_here = (n - row0) < kEncRows ? (n - row0) : kEncRows;
-        const int floats_here = (int)rows_here * kFeatures;
         float *out = X + row0 * kFeatures;
-        const int vec = floats_here / 4;
-        const float4 *src4 = reinterpret_cast<const float4 *>(tile);
-        float4 *out4 = reinterpret_cast<float4 *>(out);
-        for (int i = threadIdx.x; i < vec; i += blockDim.x) __stcs(out4 + i, src4[i]);
-        for (int i = vec * 4 + threadIdx.x; i < floats_here; i += blockDim.x) out[i] = tile[i];
-        __syncthreads();
+        const int bulk_rows = (int)rows_here & ~1;                        // an even number of rows is a 16-byte multiple
+        if (threadIdx.x == 0) {
+            if (bulk_rows > 0)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(out), "r"(smem_u32(tile)), "r"(bulk_rows * kFeatures * 4)
+                             : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (rows_here & 1) {                                              // the odd last row of the whole array
+            const int base = bulk_rows * kFeatures;
+            for (int i = threadIdx.x; i < kFeatures; i += blockDim.x) out[base + i] = tile[base + i];
+        }
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---- forward(_encode_states_np(states, turn)) (model.py:63-67): records -> V ------------
