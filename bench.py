@@ -78,6 +78,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, args.cpu_procs or cores))
     w = init_weights()
+    # every step is a bounded sample of the workload; the whole run stays within ~3 minutes whatever K is
+    args.cpu_seconds = max(1.0, min(args.cpu_seconds, 150.0 / max(args.steps, 1)))
     if ref_play.available():
         kind = "reference"
         for _ in range(args.warmup):
@@ -346,6 +348,8 @@ def run_ours(args):
 
     # ---- one TD(lambda) round (BASELINE configs[3]/[4]): play to the end, replay, all-reduce, apply
     td = None
+    if args.td_games < 0:                            # BASELINE.json configs[3] / configs[4]
+        args.td_games = 262144 if world == 1 else (1 << 20) // world
     if args.td_games > 0:
         from bgx.lib import FIRST_ROLLOFF
         from bgx.parallel import allreduce_delta, shard
@@ -369,7 +373,10 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         ms, cnt = ms.tolist(), cnt.tolist()
-        td = {"games": int(args.td_games * world), "plies": int(cnt[0]), "td_steps": int(cnt[1]), "games_finished": int(cnt[2]),
+        td = {"workload": ("TD(lambda) self-play training, 262,144 concurrent games on 1 GPU (BASELINE.json configs[3])" if world == 1 and args.td_games == 262144
+                           else f"TD(lambda) self-play training sharded over {world} GPU(s), {args.td_games * world:,} games in total (BASELINE.json configs[4])"
+                           if world > 1 and args.td_games * world == 1 << 20 else f"TD(lambda) self-play training, {args.td_games:,} games per GPU"),
+              "games": int(args.td_games * world), "plies": int(cnt[0]), "td_steps": int(cnt[1]), "games_finished": int(cnt[2]),
               "truncated": int(cnt[3]), "play_ms": ms[0], "td_replay_ms": ms[1], "allreduce_apply_ms": ms[2], "round_ms": ms[3],
               "plies_per_sec_incl_update": cnt[0] / (ms[3] * 1e-3), "td_steps_per_sec": cnt[1] / (ms[1] * 1e-3),
               "note": "one round: every game played to its end from one snapshot (k_selfplay), exact online TD(lambda) replay "
@@ -460,7 +467,8 @@ def main():
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--side-positions", type=int, default=1000000, help="positions of the enumeration/encode side legs (0 = skip)")
-    ap.add_argument("--td-games", type=int, default=65536, help="games per GPU in the TD(lambda) round leg (0 = skip)")
+    ap.add_argument("--td-games", type=int, default=-1,
+                    help="games per GPU in the TD(lambda) round leg (0 = skip; default: 262,144 on one GPU, 2^20 / N on N)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
