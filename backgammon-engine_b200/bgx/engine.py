@@ -72,6 +72,11 @@ class BatchEngine:
         L.check(self._lib.bgx_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def kernel_config(self):
+        a, b = C.c_int(), C.c_int()
+        L.check(self._lib.bgx_kernel_config(self._h, C.byref(a), C.byref(b)))
+        return {"k_selfplay": a.value, "k_select": b.value}
+
     def device_props(self):
         sm, khz, mem = C.c_int(), C.c_int(), C.c_int64()
         L.check(self._lib.bgx_device_props(self._h, C.byref(sm), C.byref(khz), C.byref(mem)))

@@ -80,6 +80,7 @@ _SIGNATURES = {
     # section 6
     "bgx_launch_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "bgx_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "bgx_kernel_config": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bgx_device_props": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64)]),
 }
 

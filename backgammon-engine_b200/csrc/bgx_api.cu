@@ -58,7 +58,7 @@ struct bgx_engine {
     // TD
     float *td_partial = nullptr;             // [td_grid][25604] per-CTA delta accumulators
     int td_grid = 0;
-    int ply_warps = 16;                      // warps per CTA of the fused ply kernels
+    int selfplay_warps = 24, select_warps = 20;   // warps per CTA of k_selfplay / k_select (measured best; BGX_*_WARPS override)
     // bookkeeping
     long long launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
@@ -159,19 +159,25 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, kEvalSmem));
     CU(cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmem));
     {
-        const char *w = getenv("BGX_PLY_WARPS");       // tuning knob: 16 (default), 24 or 32 warps per CTA
-        e->ply_warps = w ? atoi(w) : 16;
-        if (e->ply_warps != 16 && e->ply_warps != 20 && e->ply_warps != 24 && e->ply_warps != 32) { set_error("BGX_PLY_WARPS must be 16, 20, 24 or 32"); delete e; return BGX_E_INVALID; }
+        // tuning knobs: BGX_PLY_WARPS sets both kernels, BGX_SELFPLAY_WARPS / BGX_SELECT_WARPS one of them (16, 20, 24 or 32)
+        const char *both = getenv("BGX_PLY_WARPS"), *sp = getenv("BGX_SELFPLAY_WARPS"), *se = getenv("BGX_SELECT_WARPS");
+        if (both) e->selfplay_warps = e->select_warps = atoi(both);
+        if (sp) e->selfplay_warps = atoi(sp);
+        if (se) e->select_warps = atoi(se);
+        for (int w : {e->selfplay_warps, e->select_warps})
+            if (w != 16 && w != 20 && w != 24 && w != 32) { set_error("BGX_*_WARPS must be 16, 20, 24 or 32"); delete e; return BGX_E_INVALID; }
     }
+static_assert(ply_smem<16, 110>() <= 232448 && ply_smem<20, 87>() <= 232448 && ply_smem<24, 73>() <= 232448 && ply_smem<32, 54>() <= 232448,
+                  "fused ply kernels: shared memory per CTA");
 #define BGX_SMEM_ATTR(W, S)                                                                                                    \
     CU(cudaFuncSetAttribute(k_select<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));            \
     CU(cudaFuncSetAttribute(k_select<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));             \
     CU(cudaFuncSetAttribute(k_selfplay<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));          \
     CU(cudaFuncSetAttribute(k_selfplay<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));
-    BGX_SMEM_ATTR(16, 112)
-    BGX_SMEM_ATTR(20, 88)
-    BGX_SMEM_ATTR(24, 74)
-    BGX_SMEM_ATTR(32, 55)
+    BGX_SMEM_ATTR(16, 110)
+    BGX_SMEM_ATTR(20, 87)
+    BGX_SMEM_ATTR(24, 73)
+    BGX_SMEM_ATTR(32, 54)
 #undef BGX_SMEM_ATTR
     CU(cudaFuncSetAttribute(k_td_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
     *out = e;
@@ -405,7 +411,7 @@ int bgx_evaluate(bgx_engine *e, const int8_t *records, int64_t n, float *V)
     if (!e->have_weights) { set_error("bgx_evaluate: weights not set"); return BGX_E_STATE; }
     if (n == 0) return BGX_OK;
     tick(e);
-    k_evaluate<<<game_grid(e), kGameThreads, kEvalSmem, e->stream>>>(records, n, V, e->fixed, e->flat, e->aux);
+    k_evaluate<<<game_grid(e), kGameThreads, kEvalSmem, e->stream>>>(records, n, V, e->fixed, e->flat);
     tock(e);
     e->launches++;
     CU(cudaGetLastError());
@@ -436,12 +442,12 @@ static int launch_select(bgx_engine *e, cudaStream_t stream, unsigned long long 
     CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
 #define BGX_LAUNCH_SELECT(W, S, X)                                                                          \
     k_select<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), stream>>>(queries, n, epsilon, (uint32_t)seed, \
-                                                                          (uint32_t)(seed >> 32), out, e->fixed, e->flat, e->aux, counter, steal)
+                                                                          (uint32_t)(seed >> 32), out, e->fixed, e->flat, counter, steal)
     const bool ex = epsilon > 0.f;
-    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 112, true); else BGX_LAUNCH_SELECT(16, 112, false); }
-    else if (e->ply_warps == 20) { if (ex) BGX_LAUNCH_SELECT(20, 88, true); else BGX_LAUNCH_SELECT(20, 88, false); }
-    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 74, true); else BGX_LAUNCH_SELECT(24, 74, false); }
-    else { if (ex) BGX_LAUNCH_SELECT(32, 55, true); else BGX_LAUNCH_SELECT(32, 55, false); }
+    if (e->select_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 110, true); else BGX_LAUNCH_SELECT(16, 110, false); }
+    else if (e->select_warps == 20) { if (ex) BGX_LAUNCH_SELECT(20, 87, true); else BGX_LAUNCH_SELECT(20, 87, false); }
+    else if (e->select_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 73, true); else BGX_LAUNCH_SELECT(24, 73, false); }
+    else { if (ex) BGX_LAUNCH_SELECT(32, 54, true); else BGX_LAUNCH_SELECT(32, 54, false); }
 #undef BGX_LAUNCH_SELECT
     e->launches++;
     CU(cudaGetLastError());
@@ -640,12 +646,12 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
     tick(e);
-#define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->fixed, e->flat, e->aux, e->steal)
+#define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->fixed, e->flat, e->steal)
     const bool ex = epsilon > 0.f;
-    if (e->ply_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 112, true); else BGX_LAUNCH_SELFPLAY(16, 112, false); }
-    else if (e->ply_warps == 20) { if (ex) BGX_LAUNCH_SELFPLAY(20, 88, true); else BGX_LAUNCH_SELFPLAY(20, 88, false); }
-    else if (e->ply_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 74, true); else BGX_LAUNCH_SELFPLAY(24, 74, false); }
-    else { if (ex) BGX_LAUNCH_SELFPLAY(32, 55, true); else BGX_LAUNCH_SELFPLAY(32, 55, false); }
+    if (e->selfplay_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 110, true); else BGX_LAUNCH_SELFPLAY(16, 110, false); }
+    else if (e->selfplay_warps == 20) { if (ex) BGX_LAUNCH_SELFPLAY(20, 87, true); else BGX_LAUNCH_SELFPLAY(20, 87, false); }
+    else if (e->selfplay_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 73, true); else BGX_LAUNCH_SELFPLAY(24, 73, false); }
+    else { if (ex) BGX_LAUNCH_SELFPLAY(32, 54, true); else BGX_LAUNCH_SELFPLAY(32, 54, false); }
 #undef BGX_LAUNCH_SELFPLAY
     tock(e);
     e->launches++;
@@ -825,6 +831,14 @@ int bgx_last_kernel_ms(bgx_engine *e, float *ms)
     if (!e->timed) { set_error("bgx_last_kernel_ms: nothing launched yet"); return BGX_E_STATE; }
     CU(cudaEventSynchronize(e->ev1));
     CU(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return BGX_OK;
+}
+
+int bgx_kernel_config(bgx_engine *e, int *selfplay_warps, int *select_warps)
+{
+    if (!e) { set_error("bgx_kernel_config: null"); return BGX_E_INVALID; }
+    if (selfplay_warps) *selfplay_warps = e->selfplay_warps;
+    if (select_warps) *select_warps = e->select_warps;
     return BGX_OK;
 }
 

@@ -22,9 +22,12 @@ constexpr int kFeatures = 198;
 constexpr int kHidden = 128;
 constexpr int kTableFloats = kFeatures * kHidden;                 // 25 344
 constexpr int kTableBytes = kTableFloats * 4;                     // 101 376
-constexpr int kFixedRows = kFeatures + 30;                        // + borne-off step rows (bgx_ply.cuh)
-constexpr int kFixedInts = kFixedRows * kHidden;                  // 29 184
-constexpr int kFixedBytes = kFixedInts * 4;                       // 116 736
+constexpr int kFixedRows = kFeatures + 30 + 3;                    // + borne-off step rows, b1, w2, constants (bgx_ply.cuh)
+constexpr int kFixedInts = kFixedRows * kHidden;                  // 29 568
+constexpr int kFixedBytes = kFixedInts * 4;                       // 118 272
+constexpr int kRowB1 = kFeatures + 30;                            // round(b1 S)
+constexpr int kRowW2 = kFeatures + 31;                            // w2 (fp32 bit patterns)
+constexpr int kRowConst = kFeatures + 32;                         // every float4: {S, 1/S, b2, 0}
 
 // status byte (record byte 31) of a self-play slot
 enum { kRunning = 0, kP1Won = 1, kP2Won = 2, kTruncated = 3 };

@@ -8,10 +8,21 @@ namespace bgx {
 
 constexpr int kGameWarps = 16;                     // warps per CTA in the warp-per-position kernels
 constexpr int kGameThreads = kGameWarps * 32;
-// dynamic shared memory of the fused ply kernels: weight table + per-warp scratch + barrier
+// what a self-play warp knows about the slot it is seated at, apart from the position itself: kept in shared
+// memory (every lane writes the same value, so each lane reads back its own write) to leave the registers to the walk
+struct WarpSeat {
+    long long slot;
+    unsigned long long gid;
+    int ply, step, status, player;
+};
+
+// dynamic shared memory of the fused ply kernels: weight table + per-warp scratch + sharing slots + seats + barrier
 template <int kWarps, int kSets>
-constexpr int ply_smem() { return kFixedBytes + kWarps * (int)sizeof(PlyScratch<kSets>) + (int)sizeof(StealShared<kWarps>) + 16; }
-constexpr int kEvalSmem = kTableBytes + 16;            // k_evaluate: table + barrier
+constexpr int ply_smem()
+{
+    return kFixedBytes + kWarps * (int)sizeof(PlyScratch<kSets>) + (int)sizeof(StealShared<kWarps>) + kWarps * (int)sizeof(WarpSeat) + 16;
+}
+constexpr int kEvalSmem = kFixedBytes + 16;            // k_evaluate: table + barrier
 
 // exact-dedup table of the summary kernel: per warp, in global memory (L2 resident)
 constexpr int kUniqSlots = 4096;                   // 8 words each, probed as buckets of 4 slots
@@ -74,10 +85,17 @@ __global__ void k_build_fixed(const float *__restrict__ flat, const float *__res
         const float w = flat[j * kFeatures + f];
         const bool half = (f < 192 && (f & 3) == 3) || f == 194 || f == 195;
         Ti[idx] = f >= 196 ? __float_as_int(w) : __float2int_rn(w * (half ? 0.5f * S : S));
-    } else {                                       // row 198 + 15 p + k: what the (k+1)-th borne-off checker of player p adds
+    } else if (f < kRowB1) {                       // row 198 + 15 p + k: what the (k+1)-th borne-off checker of player p adds
         const int p = (f - kFeatures) / 15, k = (f - kFeatures) % 15;
         const float w = flat[j * kFeatures + 196 + p];
         Ti[idx] = __float2int_rn(w * (kOffFeature[k + 1] * S)) - __float2int_rn(w * (kOffFeature[k] * S));
+    } else if (f == kRowB1) {
+        Ti[idx] = __float2int_rn(flat[kTableFloats + j] * S);
+    } else if (f == kRowW2) {
+        Ti[idx] = __float_as_int(flat[kTableFloats + kHidden + j]);
+    } else {                                       // constants, the same float4 for every lane
+        const float c[4] = {S, aux[1], flat[kTableFloats + 2 * kHidden], 0.f};
+        Ti[idx] = __float_as_int(c[j & 3]);
     }
 }
 
@@ -282,21 +300,20 @@ k_encode(const int8_t *__restrict__ records, long long n, float *__restrict__ X)
 // ---- forward(_encode_states_np(states, turn)) (model.py:63-67): records -> V ------------
 __global__ void __launch_bounds__(kGameThreads, 1)
 k_evaluate(const int8_t *__restrict__ records, long long n, float *__restrict__ V,
-           const int32_t *__restrict__ Ti, const float *__restrict__ flat, const float *__restrict__ aux)
+           const int32_t *__restrict__ Ti, const float *__restrict__ flat)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     int32_t *sT = reinterpret_cast<int32_t *>(smem);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kTableBytes);
-    stage_table(sT, Ti, bar, kTableBytes);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kFixedBytes);
+    stage_table(sT, Ti, bar, kFixedBytes);
     const int lane = threadIdx.x & 31;
     PlyEvaluator ev;
     ev.T4 = reinterpret_cast<const int4 *>(sT);
-    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, aux, lane);
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += warps) {
         const int b = load_record_byte(records + q * 32, lane);
         const int v = lane < 28 ? b : 0;
-        const float val = ev.finish(ev.preactivation(v, lane, __shfl_sync(kFull, b, 28) ? 1 : 0));
+        const float val = ev.finish(ev.preactivation(v, lane, __shfl_sync(kFull, b, 28) ? 1 : 0), lane);
         if (lane == 0) V[q] = val;
     }
 }
@@ -328,19 +345,22 @@ __device__ __forceinline__ void store_choice(const SelectOut &o, long long q, co
     }
 }
 
-// shared-memory carve-up of the fused ply kernels: weight table | per-warp caches | sharing slots | barrier
+// shared-memory carve-up of the fused ply kernels: weight table | per-warp caches | sharing slots | seats | barrier
 template <int kWarps, int kSets>
 struct PlySmem {
     int32_t *table;
     PlyScratch<kSets> *scratch;
     StealShared<kWarps> *share;
+    WarpSeat *seat;
     uint64_t *bar;
     __device__ __forceinline__ explicit PlySmem(unsigned char *smem)
     {
         table = reinterpret_cast<int32_t *>(smem);
         scratch = reinterpret_cast<PlyScratch<kSets> *>(smem + kFixedBytes);
         share = reinterpret_cast<StealShared<kWarps> *>(smem + kFixedBytes + kWarps * sizeof(PlyScratch<kSets>));
-        bar = reinterpret_cast<uint64_t *>(smem + kFixedBytes + kWarps * sizeof(PlyScratch<kSets>) + sizeof(StealShared<kWarps>));
+        seat = reinterpret_cast<WarpSeat *>(smem + kFixedBytes + kWarps * sizeof(PlyScratch<kSets>) + sizeof(StealShared<kWarps>));
+        bar = reinterpret_cast<uint64_t *>(smem + kFixedBytes + kWarps * sizeof(PlyScratch<kSets>) + sizeof(StealShared<kWarps>) +
+                                           kWarps * sizeof(WarpSeat));
     }
     // every thread calls this before stage_table(), whose __syncthreads publishes it
     __device__ __forceinline__ void init_share() const
@@ -350,14 +370,16 @@ struct PlySmem {
             share->slot[threadIdx.x].pending = 0;
             share->slot[threadIdx.x].nres = 0;
         }
+        if (threadIdx.x == 0) share->pad[0] = 0;
         if (threadIdx.x == 0) { share->active = kWarps; share->urgent = 0; }
+        if (threadIdx.x < 8) share->stats[threadIdx.x] = 0;
     }
 };
 
 template <int kWarps, int kSets, bool kExplore>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_t seed_lo, uint32_t seed_hi,
-         SelectOut out, const int32_t *__restrict__ Ti, const float *__restrict__ flat, const float *__restrict__ aux,
+         SelectOut out, const int32_t *__restrict__ Ti, const float *__restrict__ flat,
          unsigned long long *counter, StealResult *__restrict__ steal)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -369,7 +391,6 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
     stage_table(sm.table, Ti, sm.bar, kFixedBytes);
     PlyEvaluator ev;
     ev.T4 = reinterpret_cast<const int4 *>(sm.table);
-    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, aux, lane);
     StealResult *cta_results = steal + (size_t)blockIdx.x * kWarps * kStealMaxResults;
     const ShareCtx mine = {&sm.share->slot[warp], cta_results + warp * kStealMaxResults, &sm.share->urgent, 1u << warp,
                            counter, 0ull, 8};                 // one ply per launch: latency first
@@ -449,8 +470,7 @@ struct SelfplayParams {
 
 template <int kWarps, int kSets, bool kExplore>
 __global__ void __launch_bounds__(kWarps * 32, 1)
-k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__restrict__ flat, const float *__restrict__ aux,
-           StealResult *__restrict__ steal)
+k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__restrict__ flat, StealResult *__restrict__ steal)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const PlySmem<kWarps, kSets> sm(smem);
@@ -461,17 +481,15 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
     stage_table(sm.table, Ti, sm.bar, kFixedBytes);
     PlyEvaluator ev;
     ev.T4 = reinterpret_cast<const int4 *>(sm.table);
-    ev.load_params(flat + kTableFloats, flat + kTableFloats + kHidden, flat + kTableFloats + 2 * kHidden, aux, lane);
     StealResult *cta_results = steal + (size_t)blockIdx.x * kWarps * kStealMaxResults;
     const ShareCtx mine = {&sm.share->slot[warp], cta_results + warp * kStealMaxResults, &sm.share->urgent, 1u << warp,
                            p.counter, (unsigned long long)(p.n_slots - p.n_slots / 4), 8};
 
-    unsigned long long s_plies = 0, s_seq = 0, s_scored = 0, s_fin = 0, s_p1 = 0, s_trunc = 0, s_visited = 0;
+    unsigned long long *cta_stats = sm.share->stats;    // plies, sequences, scored, finished, p1 wins, truncated, -, tree edges
     const int budget = p.round_mode ? 0x7fffffff : p.n_plies;
     bool helping = false, seated = false;
-    long long slot = 0;
-    int v = 0, player = 0, status = kRunning, ply = 0, step = 0;
-    unsigned long long gid = 0;
+    int v = 0;
+    WarpSeat &S = sm.seat[warp];
     // one iteration = one ply: of the slot this warp is seated at, or of a sub-tree taken from a neighbour
     // (whenever the queue is empty, and before its own next ply if the neighbour's double is a huge one)
     for (;;) {
@@ -489,7 +507,7 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
         }
         if (only == 0) {
             if (!seated) {
-                slot = claim(p.counter, lane);
+                const long long slot = claim(p.counter, lane);
                 if (slot >= p.n_slots) {
                     helping = true;
                     if (lane == 0) atomicSub(&sm.share->active, 1);
@@ -497,25 +515,30 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
                 }
                 const int b = load_record_byte(p.slots + slot * 32, lane);
                 v = lane < 28 ? b : 0;
-                player = __shfl_sync(kFull, b, 28) ? 1 : 0;
-                status = __shfl_sync(kFull, b, 31);
-                ply = p.ply[slot];
-                gid = (unsigned long long)p.game_id[slot];
+                const int status = __shfl_sync(kFull, b, 31);
                 if (p.round_mode && status != kRunning) continue;
-                step = 0;
+                S.slot = slot;
+                S.player = __shfl_sync(kFull, b, 28) ? 1 : 0;
+                S.status = status;
+                S.ply = p.ply[slot];
+                S.gid = (unsigned long long)p.game_id[slot];
+                S.step = 0;
                 seated = true;
             }
+            const int ply = S.ply;
             if (p.round_mode && p.traj_cap > 0 && ply >= p.traj_cap) {   // the log is full: give the game up
-                status = kTruncated;
-                s_trunc++;
+                S.status = kTruncated;
+                if (lane == 0) atomicAdd(cta_stats + 5, 1ull);
                 seated = false;
             } else {
+                const unsigned long long gid = S.gid;
                 const Philox r = philox4x32_10(p.seed_lo, p.seed_hi, (uint32_t)ply, (uint32_t)gid, (uint32_t)(gid >> 32), 0u);
                 d1 = die_of(r.x[0]); d2 = die_of(r.x[1]);
-                rec_traj = p.traj_pre != nullptr && ply < p.traj_cap && status == kRunning;
+                mover = S.player;
+                rec_traj = p.traj_pre != nullptr && ply < p.traj_cap && S.status == kRunning;
                 if (rec_traj) {
-                    int8_t *t = p.traj_pre + ((size_t)slot * p.traj_cap + ply) * 32;
-                    const int out = lane < 28 ? v : (lane == 28 ? player : (lane == 29 ? d1 : (lane == 30 ? d2 : 0)));
+                    int8_t *t = p.traj_pre + ((size_t)S.slot * p.traj_cap + ply) * 32;
+                    const int out = lane < 28 ? v : (lane == 28 ? mover : (lane == 29 ? d1 : (lane == 30 ? d2 : 0)));
                     t[lane] = (int8_t)out;                           // train.py:105-106
                 }
                 if (kExplore && p.epsilon > 0.f) {
@@ -524,7 +547,6 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
                     u = e.x[1];
                 }
                 root = v;
-                mover = player;
             }
         }
         if (only || seated) {
@@ -535,57 +557,61 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
                 continue;
             }
             v = c.v;
-            s_plies++;
-            s_seq += (unsigned long long)c.n_seq;
-            s_scored += (unsigned long long)c.n_scored;
-            s_visited += (unsigned long long)c.n_visited;
+            if (lane == 0) {
+                atomicAdd(cta_stats + 0, 1ull);
+                atomicAdd(cta_stats + 1, (unsigned long long)c.n_seq);
+                atomicAdd(cta_stats + 2, (unsigned long long)c.n_scored);
+                atomicAdd(cta_stats + 7, (unsigned long long)c.n_visited);
+            }
             if (rec_traj && p.traj_chosen) {
-                int8_t *t = p.traj_chosen + ((size_t)slot * p.traj_cap + ply) * 32;
+                int8_t *t = p.traj_chosen + ((size_t)S.slot * p.traj_cap + S.ply) * 32;
                 const int len = (int)(c.moves >> 40);
-                const int out = lane < 28 ? v : (lane == 28 ? player : (lane == 31 ? (len > 0 ? 1 : 0) : 0));
+                const int out = lane < 28 ? v : (lane == 28 ? S.player : (lane == 31 ? (len > 0 ? 1 : 0) : 0));
                 t[lane] = (int8_t)out;
             }
             // is_game_over (game.cpp:388-407): PLAYER1 is checked first
             const int off1 = __shfl_sync(kFull, v, 26), off2 = __shfl_sync(kFull, v, 27);
             const int winner = off1 == 15 ? 0 : (off2 == 15 ? 1 : -1);
-            ply++;
-            step++;
+            S.ply = S.ply + 1;
+            const int step = S.step + 1;
+            S.step = step;
             if (winner >= 0) {
-                s_fin++;
-                s_p1 += winner == 0;
+                if (lane == 0) {
+                    atomicAdd(cta_stats + 3, 1ull);
+                    if (winner == 0) atomicAdd(cta_stats + 4, 1ull);
+                }
                 if (p.round_mode) {
-                    status = winner == 0 ? kP1Won : kP2Won;
+                    S.status = winner == 0 ? kP1Won : kP2Won;
                     seated = false;
                 } else {
-                    gid += (unsigned long long)p.id_stride;          // restart in place
+                    const unsigned long long gid = S.gid + (unsigned long long)p.id_stride;   // restart in place
+                    S.gid = gid;
                     v = start_value(lane);
-                    player = first_mover_of(p.seed_lo, p.seed_hi, gid, p.first_mover);
-                    ply = 0;
-                    status = kRunning;
+                    S.player = first_mover_of(p.seed_lo, p.seed_hi, gid, p.first_mover);
+                    S.ply = 0;
+                    S.status = kRunning;
                 }
             } else {
-                player ^= 1;                                         // train.py:119-120
+                S.player = S.player ^ 1;                             // train.py:119-120
             }
             if (step >= budget) seated = false;
         }
         if (!seated) {                                               // leave the slot: write it back
-            const int out = lane < 28 ? v : (lane == 28 ? player : (lane == 31 ? status : 0));
+            const long long slot = S.slot;
+            const int out = lane < 28 ? v : (lane == 28 ? S.player : (lane == 31 ? S.status : 0));
             p.slots[slot * 32 + lane] = (int8_t)out;
             if (lane == 0) {
-                p.ply[slot] = ply;
-                p.game_id[slot] = (long long)gid;
+                p.ply[slot] = S.ply;
+                p.game_id[slot] = (long long)S.gid;
             }
         }
     }
-    if (lane == 0) {
-        atomicAdd(p.stats + 0, s_plies);
-        atomicAdd(p.stats + 1, s_seq);
-        atomicAdd(p.stats + 2, s_scored);
-        atomicAdd(p.stats + 3, s_fin);
-        atomicAdd(p.stats + 4, s_p1);
-        atomicAdd(p.stats + 5, s_trunc);
-        atomicAdd(p.stats + 7, s_visited);
-    }
+    // the last warp to leave flushes the CTA's statistics
+    __syncwarp();
+    __threadfence_block();
+    int last = 0;
+    if (lane == 0) last = atomicAdd(&sm.share->pad[0], 1) == kWarps - 1;
+    if (__shfl_sync(kFull, last, 0) && lane < 8 && lane != 6) atomicAdd(p.stats + lane, cta_stats[lane]);
 }
 
 // (re)seat every slot: opening position, first mover, ply 0

@@ -70,21 +70,11 @@ __device__ __constant__ float kOffFeature[17] = {
 //   borne-off features 196/197: k/15 is not a multiple of a step    the fp32 weight itself (bit pattern);
 //                                                                   contribution T(k) = round(W1 (fl(k/15) S)), a function of k
 //   rows 198 + 15 p + k (k = 0..14): T(k+1) - T(k) of player p      what the (k+1)-th borne-off checker adds
+//   row 228: round(b1 S); row 229: w2; row 230: {S, 1/S, b2, 0} in every lane
+//                                                    the evaluator's constants are read where needed instead of living in registers
 struct PlyEvaluator {
-    const int4 *T4;      // shared memory, fixed-point table Ti[198][32] int4
-    int4 b1;             // round(b1 S), this lane's 4 hidden units
-    float4 w2;
-    float b2, scale, inv_scale;
+    const int4 *T4;      // shared memory, fixed-point table Ti[231][32] int4
 
-    __device__ __forceinline__ void load_params(const float *b1g, const float *w2g, const float *b2g, const float *aux, int lane)
-    {
-        scale = aux[0];
-        inv_scale = aux[1];
-        const float4 b = reinterpret_cast<const float4 *>(b1g)[lane];
-        b1 = make_int4(__float2int_rn(b.x * scale), __float2int_rn(b.y * scale), __float2int_rn(b.z * scale), __float2int_rn(b.w * scale));
-        w2 = reinterpret_cast<const float4 *>(w2g)[lane];
-        b2 = b2g[0];
-    }
     __device__ __forceinline__ static void add(int4 &z, const int4 &t) { z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w; }
     __device__ __forceinline__ static void sub(int4 &z, const int4 &t) { z.x -= t.x; z.y -= t.y; z.z -= t.z; z.w -= t.w; }
     __device__ __forceinline__ static void addn(int4 &z, int n, const int4 &t) { z.x += n * t.x; z.y += n * t.y; z.z += n * t.z; z.w += n * t.w; }
@@ -92,7 +82,7 @@ struct PlyEvaluator {
     __device__ __forceinline__ int4 off_term(int k, int player, int lane) const
     {
         const int4 w = T4[(196 + player) * 32 + lane];
-        const float f = kOffFeature[k] * scale;                              // same expression as k_build_fixed
+        const float f = kOffFeature[k] * __int_as_float(T4[kRowConst * 32 + lane].x);   // same expression as k_build_fixed
         return make_int4(__float2int_rn(__int_as_float(w.x) * f), __float2int_rn(__int_as_float(w.y) * f),
                          __float2int_rn(__int_as_float(w.z) * f), __float2int_rn(__int_as_float(w.w) * f));
     }
@@ -102,7 +92,7 @@ struct PlyEvaluator {
         const int n = v < 0 ? -v : v;
         const int packed = (8 * lane + (v > 0 ? 0 : 4)) | (n << 8);
         uint32_t occ = __ballot_sync(kFull, lane < 24 && v != 0);
-        int4 z = b1;
+        int4 z = T4[kRowB1 * 32 + lane];
         while (occ) {
             const int i = lowest_bit(occ);
             occ &= occ - 1;
@@ -123,10 +113,13 @@ struct PlyEvaluator {
         if (off2) add(z, off_term(off2, 1, lane));
         return z;
     }
-    __device__ __forceinline__ float finish(const int4 &zi) const
+    __device__ __forceinline__ float finish(const int4 &zi, int lane) const
     {
+        const int4 wi = T4[kRowW2 * 32 + lane], ci = T4[kRowConst * 32 + lane];
+        const float inv_scale = __int_as_float(ci.y), b2 = __int_as_float(ci.z);
         const float zx = (float)zi.x * inv_scale, zy = (float)zi.y * inv_scale, zz = (float)zi.z * inv_scale, zw = (float)zi.w * inv_scale;
-        float y = w2.x * fast_sigmoid(zx) + w2.y * fast_sigmoid(zy) + w2.z * fast_sigmoid(zz) + w2.w * fast_sigmoid(zw);
+        float y = __int_as_float(wi.x) * fast_sigmoid(zx) + __int_as_float(wi.y) * fast_sigmoid(zy) +
+                  __int_as_float(wi.z) * fast_sigmoid(zz) + __int_as_float(wi.w) * fast_sigmoid(zw);
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) y += __shfl_xor_sync(kFull, y, s);
         return fast_sigmoid(y + b2);
@@ -227,8 +220,7 @@ struct PlyCache {
 // depend on how it is computed - so the fully inlined walk carries the leaf code only at its last level
 // (the kernel's code has to stay close to the 32 KB instruction cache).  Returns NaN if scored before.
 template <int kSets>
-__device__ __noinline__ float score_early_leaf(uint8_t *slots, uint32_t gen, uint32_t kmul, const int4 *T4, int4 b1, float4 w2,
-                                               float b2, float scale, float inv_scale, int v, int lane, int player)
+__device__ __noinline__ float score_early_leaf(uint8_t *slots, uint32_t gen, uint32_t kmul, const int4 *T4, int v, int lane, int player)
 {
     PlyCache<kSets> cache;
     cache.slots = slots; cache.gen = gen; cache.kmul = kmul;
@@ -236,8 +228,8 @@ __device__ __noinline__ float score_early_leaf(uint8_t *slots, uint32_t gen, uin
     if (pr.hit()) return __int_as_float(0x7fc00000);
     cache.write(pr, v, 0, 0, lane);
     PlyEvaluator e;
-    e.T4 = T4; e.b1 = b1; e.w2 = w2; e.b2 = b2; e.scale = scale; e.inv_scale = inv_scale;
-    return e.finish(e.preactivation(v, lane, player));
+    e.T4 = T4;
+    return e.finish(e.preactivation(v, lane, player), lane);
 }
 
 // ---- the walk ----------------------------------------------------------------------------
@@ -302,7 +294,7 @@ struct PlyWalk : Mover {
         if (pr.hit()) return;
         cache.write(pr, v, 0, 0, lane);
         const int4 z = D == 0 ? zroot : child_z(zpar, vpar, o, d, dval);
-        const float val = ev.finish(z);
+        const float val = ev.finish(z, lane);
         n_scored++;
         const float key = player ? -val : val;
         if (key > best_key) { best_key = key; best_v = v; best_path = path | ((uint32_t)D << 20); }
@@ -311,8 +303,7 @@ struct PlyWalk : Mover {
     __device__ __forceinline__ void early_leaf(int v, uint32_t path_and_len)
     {
         n_seq++;
-        const float val = score_early_leaf<kSets>(cache.slots, cache.gen, cache.kmul, ev.T4, ev.b1, ev.w2, ev.b2, ev.scale,
-                                                  ev.inv_scale, v, lane, player);
+        const float val = score_early_leaf<kSets>(cache.slots, cache.gen, cache.kmul, ev.T4, v, lane, player);
         if (val != val) return;
         n_scored++;
         const float key = player ? -val : val;
@@ -392,6 +383,7 @@ struct StealShared {
     int32_t active;                      // warps that still own queue work
     uint32_t urgent;                     // warps whose published double is so big that the others help before claiming new work
     int32_t pad[2];
+    unsigned long long stats[8];         // the CTA's share of the launch statistics (kept out of the warps' registers)
 };
 
 // what a warp needs to publish its doubles: its slot, its result area, the CTA's urgent mask and its bit in it

@@ -402,7 +402,7 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world),
                 "sequences_per_sec": seqs_all / total_s, "afterstates_scored_per_sec": scored_all / total_s,
                 "sequences_per_ply": seqs_all / plies_all, "scored_per_ply": scored_all / plies_all,
-                "tree_edges_per_ply_rank0": edges / max(plies, 1), "ply_warps_per_cta": int(os.environ.get("BGX_PLY_WARPS", "16")),
+                "tree_edges_per_ply_rank0": edges / max(plies, 1), "ply_warps_per_cta": eng.kernel_config(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 32, "d2h_bytes_per_step": G * 36,
                         "note": "one step = one ply for all 65,536 games through bgx_select_moves_host_async (four quarter-populations "
                                 "on four lanes, pinned host buffers, H2D + k_select + D2H per ply), bgx_advance_host + numpy restarts "

@@ -263,6 +263,8 @@ int bgx_launch_count(bgx_engine *e, int64_t *n);
 /* CUDA-event duration (ms) of the last self-play / select / enumerate kernel launch */
 int bgx_last_kernel_ms(bgx_engine *e, float *ms);
 int bgx_device_props(bgx_engine *e, int *sm_count, int *clock_khz, int64_t *global_mem);
+/* warps per CTA of the fused ply kernels as configured (defaults or BGX_*_WARPS) */
+int bgx_kernel_config(bgx_engine *e, int *selfplay_warps, int *select_warps);
 
 #ifdef __cplusplus
 }
