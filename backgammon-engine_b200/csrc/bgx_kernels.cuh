@@ -9,7 +9,7 @@ namespace bgx {
 constexpr int kGameWarps = 16;                     // warps per CTA in the warp-per-position kernels
 constexpr int kGameThreads = kGameWarps * 32;
 // what a self-play warp knows about the slot it is seated at, apart from the position itself: kept in shared
-// memory (every lane writes the same value, so each lane reads back its own write) to leave the registers to the walk
+// memory (lane 0 writes, __syncwarp, everybody reads) to leave the registers to the walk
 struct WarpSeat {
     long long slot;
     unsigned long long gid;
@@ -517,17 +517,22 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
                 v = lane < 28 ? b : 0;
                 const int status = __shfl_sync(kFull, b, 31);
                 if (p.round_mode && status != kRunning) continue;
-                S.slot = slot;
-                S.player = __shfl_sync(kFull, b, 28) ? 1 : 0;
-                S.status = status;
-                S.ply = p.ply[slot];
-                S.gid = (unsigned long long)p.game_id[slot];
-                S.step = 0;
+                const int mover0 = __shfl_sync(kFull, b, 28) ? 1 : 0;
+                if (lane == 0) {
+                    S.slot = slot;
+                    S.player = mover0;
+                    S.status = status;
+                    S.ply = p.ply[slot];
+                    S.gid = (unsigned long long)p.game_id[slot];
+                    S.step = 0;
+                }
+                __syncwarp();
                 seated = true;
             }
             const int ply = S.ply;
             if (p.round_mode && p.traj_cap > 0 && ply >= p.traj_cap) {   // the log is full: give the game up
-                S.status = kTruncated;
+                if (lane == 0) S.status = kTruncated;
+                __syncwarp();
                 if (lane == 0) atomicAdd(cta_stats + 5, 1ull);
                 seated = false;
             } else {
@@ -572,28 +577,29 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
             // is_game_over (game.cpp:388-407): PLAYER1 is checked first
             const int off1 = __shfl_sync(kFull, v, 26), off2 = __shfl_sync(kFull, v, 27);
             const int winner = off1 == 15 ? 0 : (off2 == 15 ? 1 : -1);
-            S.ply = S.ply + 1;
             const int step = S.step + 1;
-            S.step = step;
+            const int mover_now = S.player;
+            unsigned long long gid = S.gid;
+            int next_player = mover_now ^ 1, next_ply = S.ply + 1, next_status = kRunning;   // train.py:119-120
             if (winner >= 0) {
                 if (lane == 0) {
                     atomicAdd(cta_stats + 3, 1ull);
                     if (winner == 0) atomicAdd(cta_stats + 4, 1ull);
                 }
                 if (p.round_mode) {
-                    S.status = winner == 0 ? kP1Won : kP2Won;
+                    next_status = winner == 0 ? kP1Won : kP2Won;
+                    next_player = mover_now;
                     seated = false;
                 } else {
-                    const unsigned long long gid = S.gid + (unsigned long long)p.id_stride;   // restart in place
-                    S.gid = gid;
+                    gid += (unsigned long long)p.id_stride;          // restart in place
                     v = start_value(lane);
-                    S.player = first_mover_of(p.seed_lo, p.seed_hi, gid, p.first_mover);
-                    S.ply = 0;
-                    S.status = kRunning;
+                    next_player = first_mover_of(p.seed_lo, p.seed_hi, gid, p.first_mover);
+                    next_ply = 0;
                 }
-            } else {
-                S.player = S.player ^ 1;                             // train.py:119-120
             }
+            __syncwarp();
+            if (lane == 0) { S.step = step; S.player = next_player; S.ply = next_ply; S.status = next_status; S.gid = gid; }
+            __syncwarp();
             if (step >= budget) seated = false;
         }
         if (!seated) {                                               // leave the slot: write it back
