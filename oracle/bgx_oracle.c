@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 
 /* ------------------------------------------------------------------ rules */
 
@@ -267,6 +268,42 @@ void orc_turn_summary(const int32_t *s, int player, int d1, int d2,
     if (n_unique) *n_unique = u;
     if (digest) *digest = dg;
     free(mv); free(ln); free(st);
+}
+
+/* orc_turn_summary over a batch of 32-byte records (28 state bytes, mover, d1, d2, pad) on
+ * `threads` POSIX threads: lets the tests check EVERY position of the 10^6-position sweep
+ * (BASELINE.json configs[1]) against this restatement instead of a sample. */
+typedef struct {
+    const int8_t *rec; long lo, hi;
+    int64_t *n_seq, *n_unique; uint64_t *digest;
+} batch_job;
+
+static void *batch_worker(void *arg)
+{
+    batch_job *j = (batch_job *)arg;
+    for (long i = j->lo; i < j->hi; i++) {
+        const int8_t *r = j->rec + 32 * i;
+        int32_t s[28];
+        for (int k = 0; k < 28; k++) s[k] = r[k];
+        orc_turn_summary(s, r[28], r[29], r[30], j->n_seq + i, j->n_unique + i, j->digest + i);
+    }
+    return NULL;
+}
+
+void orc_turn_summary_batch(const int8_t *records, long n, int threads,
+                            int64_t *n_seq, int64_t *n_unique, uint64_t *digest)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t tid[256];
+    batch_job job[256];
+    /* interleaved blocks would balance better, but the sweep is shuffled: contiguous is fine */
+    for (int t = 0; t < threads; t++) {
+        job[t].rec = records; job[t].lo = n * t / threads; job[t].hi = n * (t + 1) / threads;
+        job[t].n_seq = n_seq; job[t].n_unique = n_unique; job[t].digest = digest;
+        pthread_create(&tid[t], NULL, batch_worker, &job[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(tid[t], NULL);
 }
 
 /* ------------------------------------------------------------- the model */

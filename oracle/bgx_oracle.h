@@ -60,6 +60,10 @@ long orc_turn_sequences(const int32_t *s, int player, int d1, int d2, long cap,
 void orc_turn_summary(const int32_t *s, int player, int d1, int d2,
                       int64_t *n_seq, int64_t *n_unique, uint64_t *digest);
 
+/* the same over n 32-byte records (28 state bytes, mover, d1, d2, pad), on `threads` threads */
+void orc_turn_summary_batch(const int8_t *records, long n, int threads,
+                            int64_t *n_seq, int64_t *n_unique, uint64_t *digest);
+
 /* encoding + model (pysrc/TD(λ) model/model.py) ---------------------------- */
 void orc_encode(const int32_t *states, long n, int turn, float *X /*[n][198]*/);   /* model.py:111-144 */
 /* weights in state_dict layout: W1[128][198], b1[128], w2[128], b2[1] */

@@ -86,6 +86,11 @@ class Oracle(_SeqAPI):
         L.orc_turn_summary.argtypes = [_i32p, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
         L.orc_turn_summary.restype = None
+        L.orc_turn_summary_batch.argtypes = [_i8p, C.c_long, C.c_int,
+                                             np.ctypeslib.ndpointer(np.int64, flags="C"),
+                                             np.ctypeslib.ndpointer(np.int64, flags="C"),
+                                             np.ctypeslib.ndpointer(np.uint64, flags="C")]
+        L.orc_turn_summary_batch.restype = None
         L.orc_encode.argtypes = [_i32p, C.c_long, C.c_int, _f32p]
         L.orc_encode.restype = None
         L.orc_forward.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_long, _f32p, C.c_void_p]
@@ -121,6 +126,15 @@ class Oracle(_SeqAPI):
         n, u, d = C.c_int64(), C.c_int64(), C.c_uint64()
         self.lib.orc_turn_summary(_state(s), int(player), int(d1), int(d2), C.byref(n), C.byref(u), C.byref(d))
         return n.value, u.value, d.value
+
+    def turn_summary_batch(self, records, threads=None):
+        """records int8[n,32] (state, mover, d1, d2, pad) -> (N int64[n], U int64[n], digest uint64[n])."""
+        r = np.ascontiguousarray(records, dtype=np.int8).reshape(-1, 32)
+        n = r.shape[0]
+        ns, nu, dg = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.uint64)
+        if n:
+            self.lib.orc_turn_summary_batch(r.reshape(-1), n, int(threads or os.cpu_count() or 1), ns, nu, dg)
+        return ns, nu, dg
 
     # -- model
     def encode(self, states, turn):

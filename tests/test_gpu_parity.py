@@ -114,6 +114,20 @@ def test_enumerate_million_position_properties(eng):
     assert int(n.sum()) > 30_000_000
 
 
+def test_enumerate_million_positions_bit_exact_vs_oracle(eng, orc):
+    """BASELINE north_star: "bit-exact move sets against the reference on 10^6 seeded positions".
+    EVERY position of the configs[1] sweep: sequence count, exact number of distinct afterstates and
+    the ordered digest (which pins every move of every sequence, its order and its resulting 28-int
+    state) against the CPU oracle (threaded C restatement, itself pinned to the reference)."""
+    from bgx.synth import make_queries
+    q, _ = make_queries(1_000_000, seed=20260101)
+    n, u, d = eng.enumerate_summary_host(q)
+    on, ou, od = orc.turn_summary_batch(q)
+    assert np.array_equal(n.astype(np.int64), on)
+    assert np.array_equal(u.astype(np.int64), ou)
+    assert np.array_equal(d.astype(np.uint64), od)
+
+
 # ------------------------------------------------------------------ encoding (bit-exact) and values
 
 def test_encode_golden_bit_exact(eng, golden):

@@ -141,6 +141,18 @@ def test_enumeration_summary_golden(orc, golden):
         assert (n, u, d) == (int(g["n_seq"][i]), int(g["n_unique"][i]), int(g["digest"][i])), i
 
 
+def test_enumeration_summary_batch_golden(orc, golden):
+    """The threaded batch form used by the 10^6-position GPU sweep gives the golden answers too."""
+    g = golden("enum_summary.npz")
+    for threads in (1, 3):
+        n, u, d = orc.turn_summary_batch(g["queries"], threads=threads)
+        assert np.array_equal(n, g["n_seq"].astype(np.int64))
+        assert np.array_equal(u, g["n_unique"].astype(np.int64))
+        assert np.array_equal(d, g["digest"].astype(np.uint64))
+    n, u, d = orc.turn_summary_batch(np.zeros((0, 32), np.int8))
+    assert len(n) == 0
+
+
 def test_moves_golden(orc, golden):
     g = golden("moves.npz")
     for i, r in enumerate(g["queries"]):

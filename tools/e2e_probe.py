@@ -23,7 +23,7 @@ q = torch.zeros((G, 32), dtype=torch.int8).pin_memory().numpy(); q[:] = rec
 ch = torch.zeros((G, 32), dtype=torch.int8).pin_memory().numpy()
 _, h_ply, h_gid = eng.selfplay_read()
 h_win = np.zeros(G, np.int8)
-for lanes in (1, 2, 4, 8):
+for lanes in (1, 2, 3, 4):
     if lanes > 4: break
     parts = [(i * G // lanes, (i + 1) * G // lanes) for i in range(lanes)]
     def submit(h):
