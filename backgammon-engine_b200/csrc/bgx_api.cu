@@ -17,13 +17,14 @@ using namespace bgx;
 struct bgx_lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    unsigned long long *counter = nullptr;
+    unsigned long long *counter = nullptr;   // [0] work queue, [8..15] the 16 bucket totals of k_select_order
     StealResult *steal = nullptr;
-    void *buf[7] = {};
-    size_t cap[7] = {};
+    void *buf[8] = {};                       // [7]: sorted queue
+    size_t cap[8] = {};
     bool busy = false;
 };
 constexpr int kLanes = BGX_ASYNC_LANES;
+constexpr size_t kCounterBytes = 128;        // work-queue counter + 16 x uint32 bucket totals at byte 64
 
 struct bgx_engine {
     int device = 0;
@@ -58,6 +59,10 @@ struct bgx_engine {
     // TD
     float *td_partial = nullptr;             // [td_grid][25604] per-CTA delta accumulators
     int td_grid = 0;
+    int lane_grid = -1;                      // CTAs of a k_select launch on an asynchronous lane: half the SMs, so that two lanes'
+                                             // batches are resident at once (0: one per SM; BGX_SELECT_LANE_GRID)
+    long long select_order_max = 1 << 21;    // launches up to this many queries get a sorted queue (BGX_SELECT_ORDER_MAX; 64 B of scratch per query)
+    int select_urgent_min = 7, select_giant_min = kGiantMinChildren, select_urgent_from_pct = 0;   // k_select help policy (BGX_SELECT_*)
     int selfplay_warps = 24, select_warps = 20;   // warps per CTA of k_selfplay / k_select (measured best; BGX_*_WARPS override)
     // bookkeeping
     long long launches = 0;
@@ -149,7 +154,7 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaMalloc(&e->fixed, kFixedBytes));
     CU(cudaMalloc(&e->aux, 4 * sizeof(float)));
     CU(cudaMemset(e->aux, 0, 4 * sizeof(float)));
-    CU(cudaMalloc(&e->counter, sizeof(unsigned long long)));
+    CU(cudaMalloc(&e->counter, kCounterBytes));
     CU(cudaMalloc(&e->stats, 8 * sizeof(unsigned long long)));
     CU(cudaMalloc(&e->dstats, 2 * sizeof(double)));
     CU(cudaMalloc(&e->steal, (size_t)e->sm_count * 32 * kStealMaxResults * sizeof(StealResult)));
@@ -164,6 +169,12 @@ int bgx_create(int device, bgx_engine **out)
         if (both) e->selfplay_warps = e->select_warps = atoi(both);
         if (sp) e->selfplay_warps = atoi(sp);
         if (se) e->select_warps = atoi(se);
+        if (const char *v = getenv("BGX_SELECT_URGENT_MIN")) e->select_urgent_min = atoi(v);
+        if (const char *v = getenv("BGX_SELECT_ORDER_MAX")) e->select_order_max = atoll(v);
+        if (const char *v = getenv("BGX_SELECT_LANE_GRID")) e->lane_grid = atoi(v);
+        if (e->lane_grid < 0) e->lane_grid = e->sm_count / 2;
+        if (const char *v = getenv("BGX_SELECT_GIANT_MIN")) e->select_giant_min = atoi(v);
+        if (const char *v = getenv("BGX_SELECT_URGENT_FROM_PCT")) e->select_urgent_from_pct = atoi(v);
         for (int w : {e->selfplay_warps, e->select_warps})
             if (w != 16 && w != 20 && w != 24 && w != 32) { set_error("BGX_*_WARPS must be 16, 20, 24 or 32"); delete e; return BGX_E_INVALID; }
     }
@@ -437,12 +448,20 @@ int bgx_evaluate_host(bgx_engine *e, const int8_t *records, int64_t n, float *V)
 // ------------------------------------------------------------------------ batched make_move
 
 static int launch_select(bgx_engine *e, cudaStream_t stream, unsigned long long *counter, StealResult *steal,
-                         const int8_t *queries, int64_t n, float epsilon, uint64_t seed, const SelectOut &out)
+                         const int8_t *queries, int64_t n, float epsilon, uint64_t seed, const SelectOut &out, int32_t *region,
+                         int grid = 0)
 {
-    CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    if (grid <= 0 || grid > e->sm_count) grid = game_grid(e);
+    CU(cudaMemsetAsync(counter, 0, kCounterBytes, stream));
+    uint32_t *totals = reinterpret_cast<uint32_t *>(counter + 8);
+    if (region) {
+        k_select_order<<<(unsigned)((n + kOrderCtaQueries - 1) / kOrderCtaQueries), 256, 0, stream>>>(queries, n, region, totals);
+        e->launches++;
+    }
+    const SelectTune tune = {(unsigned long long)(n * (int64_t)e->select_urgent_from_pct / 100), e->select_urgent_min, e->select_giant_min};
 #define BGX_LAUNCH_SELECT(W, S, X)                                                                          \
-    k_select<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), stream>>>(queries, n, epsilon, (uint32_t)seed, \
-                                                                          (uint32_t)(seed >> 32), out, e->fixed, e->flat, counter, steal)
+    k_select<W, S, X><<<grid, W * 32, ply_smem<W, S>(), stream>>>(queries, n, epsilon, (uint32_t)seed, \
+                                                                          (uint32_t)(seed >> 32), out, e->fixed, e->flat, counter, steal, tune, region, totals)
     const bool ex = epsilon > 0.f;
     if (e->select_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 110, true); else BGX_LAUNCH_SELECT(16, 110, false); }
     else if (e->select_warps == 20) { if (ex) BGX_LAUNCH_SELECT(20, 87, true); else BGX_LAUNCH_SELECT(20, 87, false); }
@@ -462,8 +481,13 @@ int bgx_select_moves(bgx_engine *e, const int8_t *queries, int64_t n, float epsi
     if (!e->have_weights) { set_error("bgx_select_moves: weights not set"); return BGX_E_STATE; }
     if (n == 0) return BGX_OK;
     const SelectOut out = {chosen, moves, moves_len, value, n_seq, n_scored};
+    void *region = nullptr;
+    if (n <= e->select_order_max) {
+        const int rs = scratch(e, 11, (size_t)n * kOrderBuckets * 4, &region);
+        if (rs) return rs;
+    }
     tick(e);
-    const int rc = launch_select(e, e->stream, e->counter, e->steal, queries, n, epsilon, seed, out);
+    const int rc = launch_select(e, e->stream, e->counter, e->steal, queries, n, epsilon, seed, out, (int32_t *)region);
     tock(e);
     return rc;
 }
@@ -500,7 +524,7 @@ int bgx_select_moves_host(bgx_engine *e, const int8_t *queries, int64_t n, float
 
 // Asynchronous form of bgx_select_moves_host: the copies and the kernel are queued on lane `lane`'s own
 // stream and the call returns; bgx_lane_wait blocks until that lane's results are in the host buffers.
-// Two lanes in flight let the host advance one half of a population while the GPU plays the other.
+// A few lanes in flight let the host advance one part of a population while the GPU plays the others.
 static int lane_scratch(bgx_lane &l, int i, size_t bytes, void **out)
 {
     if (l.cap[i] < bytes) {
@@ -527,7 +551,7 @@ int bgx_select_moves_host_async(bgx_engine *e, int lane, const int8_t *queries, 
     if (!l.stream) {
         CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
-        CU(cudaMalloc(&l.counter, sizeof(unsigned long long)));
+        CU(cudaMalloc(&l.counter, kCounterBytes));
         CU(cudaMalloc(&l.steal, (size_t)e->sm_count * 32 * kStealMaxResults * sizeof(StealResult)));
     }
     if (n == 0) return BGX_OK;
@@ -546,7 +570,9 @@ int bgx_select_moves_host_async(bgx_engine *e, int lane, const int8_t *queries, 
     CU(cudaMemcpyAsync(dq, queries, (size_t)n * 32, cudaMemcpyHostToDevice, l.stream));
     const SelectOut out = {chosen ? (int8_t *)dc : nullptr, moves ? (int8_t *)dm : nullptr, moves_len ? (int8_t *)dl : nullptr,
                            value ? (float *)dv : nullptr, n_seq ? (int32_t *)dn : nullptr, n_scored ? (int32_t *)ds : nullptr};
-    if ((rc = launch_select(e, l.stream, l.counter, l.steal, (const int8_t *)dq, n, epsilon, seed, out))) return rc;
+    void *region = nullptr;
+    if (n <= e->select_order_max && (rc = lane_scratch(l, 7, (size_t)n * kOrderBuckets * 4, &region))) return rc;
+    if ((rc = launch_select(e, l.stream, l.counter, l.steal, (const int8_t *)dq, n, epsilon, seed, out, (int32_t *)region, e->lane_grid))) return rc;
     if (chosen) CU(cudaMemcpyAsync(chosen, dc, (size_t)n * 32, cudaMemcpyDeviceToHost, l.stream));
     if (moves) CU(cudaMemcpyAsync(moves, dm, (size_t)n * 8, cudaMemcpyDeviceToHost, l.stream));
     if (moves_len) CU(cudaMemcpyAsync(moves_len, dl, (size_t)n, cudaMemcpyDeviceToHost, l.stream));

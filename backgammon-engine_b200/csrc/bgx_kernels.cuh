@@ -376,11 +376,82 @@ struct PlySmem {
     }
 };
 
+// ---- queue order of a one-ply launch ----------------------------------------------------------------------
+// A one-ply launch over a few ten thousand queries is as long as its tail: turn trees range from 0 to ~12 k
+// sequences.  k_select_order sorts the queue heaviest first by a cheap estimate of the tree size (counting sort
+// into 16 power-of-two buckets): root origins k of each die, taken once as they are and - with checkers on the bar -
+// once more with the bar emptied (after the entries the turn goes on freely).  The order only decides WHEN a query
+// is walked, never its result (values are pure functions of the query).
+constexpr int kOrderBuckets = 16;
+constexpr int kOrderCtaQueries = 64;     // 8 warps x 8 queries
+
+__device__ __forceinline__ int order_bucket(int v, int lane, int player, int d1, int d2)
+{
+    const Mover m(lane, player);
+    const int bar = __shfl_sync(kFull, v, 24 + player);
+    const int k1 = __popc(m.legal_here(v, d1));
+    const int k2 = d1 == d2 ? k1 : __popc(m.legal_here(v, d2));
+    long long est;
+    if (bar == 0) {
+        est = d1 == d2 ? (long long)k1 * k1 * k1 * k1 : 2ll * k1 * k2 + k1 + k2;
+    } else {
+        const int vf = lane == 24 + player ? 0 : v;
+        const int f1 = __popc(m.legal_here(vf, d1)) + 1;
+        const int f2 = d1 == d2 ? f1 : __popc(m.legal_here(vf, d2)) + 1;
+        if (d1 == d2) {
+            est = k1;
+            for (int j = bar; j < 4; j++) est *= f1;
+        } else {
+            est = bar == 1 ? (long long)k1 * f2 + (long long)k2 * f1 + k1 + k2 : (long long)k1 * k2;
+        }
+    }
+    const int b = 63 - __clzll(est + 1);
+    return b < kOrderBuckets ? b : kOrderBuckets - 1;
+}
+
+// region[b][..totals[b]] = the queries of bucket b (any order inside a bucket); totals zeroed by the caller
+__global__ void __launch_bounds__(256) k_select_order(const int8_t *__restrict__ queries, long long n, int32_t *__restrict__ region,
+                                                      uint32_t *__restrict__ totals)
+{
+    __shared__ uint32_t hist[kOrderBuckets], base[kOrderBuckets];
+    __shared__ uint8_t key[kOrderCtaQueries];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long q0 = (long long)blockIdx.x * kOrderCtaQueries;
+    if (threadIdx.x < kOrderBuckets) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int j = warp; j < kOrderCtaQueries; j += 8) {
+        const long long q = q0 + j;
+        if (q >= n) break;
+        const int b = load_record_byte(queries + q * 32, lane);
+        const int player = __shfl_sync(kFull, b, 28) ? 1 : 0, d1 = __shfl_sync(kFull, b, 29), d2 = __shfl_sync(kFull, b, 30);
+        const int k = order_bucket(lane < 28 ? b : 0, lane, player, d1, d2);
+        if (lane == 0) { key[j] = (uint8_t)k; atomicAdd(&hist[k], 1u); }
+    }
+    __syncthreads();
+    if (threadIdx.x < kOrderBuckets) {
+        const uint32_t c = hist[threadIdx.x];
+        base[threadIdx.x] = c ? atomicAdd(&totals[threadIdx.x], c) : 0u;
+        hist[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x < kOrderCtaQueries && q0 + threadIdx.x < n) {
+        const int k = key[threadIdx.x];
+        region[(size_t)k * n + base[k] + atomicAdd(&hist[k], 1u)] = (int32_t)(q0 + threadIdx.x);
+    }
+}
+
+// when the CTA of a published double helps before claiming new queue work (bgx_ply.cuh ShareCtx)
+struct SelectTune {
+    unsigned long long urgent_from;      // queue position from which doubles with >= urgent_min root origins are urgent
+    int urgent_min, giant_min;           // giant_min: urgent wherever they sit
+};
+
 template <int kWarps, int kSets, bool kExplore>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_t seed_lo, uint32_t seed_hi,
          SelectOut out, const int32_t *__restrict__ Ti, const float *__restrict__ flat,
-         unsigned long long *counter, StealResult *__restrict__ steal)
+         unsigned long long *counter, StealResult *__restrict__ steal, SelectTune tune,
+         const int32_t *__restrict__ region, const uint32_t *__restrict__ totals)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const PlySmem<kWarps, kSets> sm(smem);
@@ -393,8 +464,19 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
     ev.T4 = reinterpret_cast<const int4 *>(sm.table);
     StealResult *cta_results = steal + (size_t)blockIdx.x * kWarps * kStealMaxResults;
     const ShareCtx mine = {&sm.share->slot[warp], cta_results + warp * kStealMaxResults, &sm.share->urgent, 1u << warp,
-                           counter, 0ull, 8};                 // one ply per launch: latency first
-    bool helping = false;
+                           counter, tune.urgent_from, tune.urgent_min, tune.giant_min};
+    bool helping = false, first = true;
+    const long long first_wave = (long long)gridDim.x * kWarps;
+    // sorted queue (k_select_order): lane r < 16 knows where the r-th heaviest bucket ends
+    uint32_t bucket_end = 0;
+    if (region) {
+        bucket_end = lane < kOrderBuckets ? totals[kOrderBuckets - 1 - lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < kOrderBuckets; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(kFull, bucket_end, o);
+            if (lane >= o) bucket_end += up;
+        }
+    }
     for (;;) {
         int root = 0, player = 0, d1 = 0, d2 = 0, vw = 0;
         uint32_t only = 0, u = 0;
@@ -411,11 +493,19 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
             }
         }
         if (only == 0) {
-            q = claim(counter, lane);
+            // the first wave is dealt round-robin over the CTAs (neighbouring queue entries land on different SMs:
+            // a run of big doubles must not end up in one CTA, help is intra-CTA); after that, first come first served
+            q = first ? (long long)warp * gridDim.x + blockIdx.x : first_wave + claim(counter, lane);
+            first = false;
             if (q >= n) {                                   // queue empty: help the owners of big doubles
                 helping = true;
                 if (lane == 0) atomicSub(&sm.share->active, 1);
                 continue;
+            }
+            if (region) {                                   // position in the sorted queue -> query
+                const int r = __popc(__ballot_sync(kFull, lane < kOrderBuckets && (uint32_t)q >= bucket_end));
+                const uint32_t before = __shfl_sync(kFull, bucket_end, r > 0 ? r - 1 : 0);
+                q = region[(size_t)(kOrderBuckets - 1 - r) * n + ((uint32_t)q - (r > 0 ? before : 0u))];
             }
             const int b = load_record_byte(queries + q * 32, lane);
             root = lane < 28 ? b : 0;
@@ -483,7 +573,7 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
     ev.T4 = reinterpret_cast<const int4 *>(sm.table);
     StealResult *cta_results = steal + (size_t)blockIdx.x * kWarps * kStealMaxResults;
     const ShareCtx mine = {&sm.share->slot[warp], cta_results + warp * kStealMaxResults, &sm.share->urgent, 1u << warp,
-                           p.counter, (unsigned long long)(p.n_slots - p.n_slots / 4), 8};
+                           p.counter, (unsigned long long)(p.n_slots - p.n_slots / 4), 8, kGiantMinChildren};
 
     unsigned long long *cta_stats = sm.share->stats;    // plies, sequences, scored, finished, p1 wins, truncated, -, tree edges
     const int budget = p.round_mode ? 0x7fffffff : p.n_plies;

@@ -395,6 +395,7 @@ struct ShareCtx {
     const unsigned long long *queue;     // the launch's work-queue counter ...
     unsigned long long urgent_from;      // ... and the position from which big doubles are urgent
     int urgent_min;                      // root origins that make a double "big" for that purpose
+    int giant_min;                       // root origins from which a double is urgent wherever it sits in the queue
 };
 
 __device__ __forceinline__ Choice finish_choice(const uint32_t best_path, float best_key, int best_v, int n_seq, int n_scored,
@@ -449,7 +450,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
                     atomicExch(&slot->legal0, legal);
                     // near the end of the queue a huge double is the tail of the launch: ask for help at once
                     const int kids = __popc(legal);
-                    if (kids >= kGiantMinChildren ||
+                    if (kids >= share->giant_min ||
                         (kids >= share->urgent_min && *(volatile const unsigned long long *)share->queue >= share->urgent_from))
                         atomicOr(share->urgent, share->my_bit);
                 }

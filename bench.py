@@ -282,12 +282,13 @@ def run_ours(args):
     value = plies_all / total_s
 
     # ---- end to end: host-driven self-play through the batched make_move C-ABI call, pinned host buffers.
-    # The population is split into four parts, each on its own asynchronous lane: while the GPU plays
-    # some (H2D of the records, k_select, D2H of the chosen afterstates) the host advances another
+    # The population is split into three parts, each on its own asynchronous lane (a lane's launch occupies half
+    # the SMs, so two are resident at once): while the GPU plays some (H2D of the records, k_select_order + k_select,
+    # D2H of the chosen afterstates) the host advances another
     # (game over?, restart, flip the mover, next dice) - the loop of train.py:99-121 for 65,536 games.
     e2e_steps = max(2, min(args.steps, 8)) * PLIES_PER_STEP
     from bgx import host as bgx_host
-    LANES = 2
+    LANES = 3
     q_pin = torch.zeros((G, 32), dtype=torch.int8).pin_memory()
     ch_pin = torch.zeros((G, 32), dtype=torch.int8).pin_memory()
     val_pin = torch.zeros(G, dtype=torch.float32).pin_memory()
@@ -404,14 +405,18 @@ def run_ours(args):
                 "sequences_per_ply": seqs_all / plies_all, "scored_per_ply": scored_all / plies_all,
                 "tree_edges_per_ply_rank0": edges / max(plies, 1), "ply_warps_per_cta": eng.kernel_config(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 32, "d2h_bytes_per_step": G * 36,
-                        "note": "one step = one ply for all 65,536 games through bgx_select_moves_host_async (four quarter-populations "
-                                "on four lanes, pinned host buffers, H2D + k_select + D2H per ply), bgx_advance_host + numpy restarts "
+                        "note": "one step = one ply for all 65,536 games through bgx_select_moves_host_async (three thirds of the population "
+                                "on three lanes of half the SMs each, pinned host buffers, H2D + k_select_order + k_select + D2H per ply), bgx_advance_host + numpy restarts "
                                 f"on the host between plies; {e2e_steps} timed ply-steps"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "kernel": "k_selfplay",
                              "kernel_ms": k_ms, "peak_source": peak_src,
+                             "fused_dataflow": {"bytes_per_afterstate": 32, "achieved": seq_per_launch * 32 / (k_ms * 1e-3) / 1e9,
+                                                "frac": seq_per_launch * 32 / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                                "note": "SURVEY 8d's second figure: an implementation that fuses encode + evaluate but still "
+                                                        "writes one packed int8 record (32 B) per enumerated afterstate; this kernel writes none"},
                              "note": "algorithmic bytes = sequences enumerated per launch x 1,696 B: what the materialised dataflow "
                                      "of the reference and of SURVEY 8d moves per enumerated afterstate (792 B of features written, "
                                      "792 B read back, 112 B state row).  The fused kernel never materialises them (`traffic` is its "

@@ -171,8 +171,12 @@ int bgx_select_moves_host(bgx_engine *e, const int8_t *queries, int64_t n, float
  * (0 <= lane < BGX_ASYNC_LANES) and the call returns at once; bgx_lane_wait(lane) blocks until
  * that lane's outputs are in the host buffers.  Host buffers should be page-locked and must
  * stay untouched until the wait.  A lane holds one batch at a time (BGX_E_STATE otherwise).
- * With two lanes a host loop (model.py make_move callers: train.py:107, benchmark.py:86)
- * advances one half of its games while the GPU plays the other half. */
+ * With two or three lanes a host loop (model.py make_move callers: train.py:107, benchmark.py:86)
+ * advances one part of its games while the GPU plays the others.  A lane's launch occupies half
+ * the SMs, so the batches of two lanes are resident at once (a one-ply batch cannot be shorter
+ * than its biggest turn tree; BGX_SELECT_LANE_GRID overrides the CTA count, 0 = every SM).
+ * Batches of up to 2^21 queries (BGX_SELECT_ORDER_MAX) are walked heaviest first: the order
+ * never changes a result, only when it is computed. */
 #define BGX_ASYNC_LANES 4
 int bgx_select_moves_host_async(bgx_engine *e, int lane, const int8_t *queries, int64_t n, float epsilon, uint64_t seed,
                                 int8_t *chosen, int8_t *moves, int8_t *moves_len, float *value,

@@ -357,6 +357,52 @@ def test_selfplay_golden_game_ids(eng, golden):
             assert np.array_equal(pre[:, 29:31], g[f"{name}.dice"])
 
 
+def test_thousand_random_games_bit_exact(eng, orc, golden, request):
+    """BASELINE.json configs[0] on the GPU: 1,000 random-vs-random games (epsilon = 1, the policy of
+    benchmark.py:54-61 / model.py:205-206: uniform over the SEQUENCES, duplicates weighted) with the seeded
+    Philox dice.  No floating point decides anything here, so every ply of every game must be bit-exact:
+    dice, sequence count, the sequence the draw selects in reference order, the resulting 28-int state,
+    turn order, game length and winner - against the oracle for all games and against the UNMODIFIED
+    reference engine (oracle/_ref, when it was built) for a subset."""
+    from bgx.synth import START_BOARD
+    from oracle.oracle import RefHarness
+    ref = RefHarness() if RefHarness.available() else None
+    eng.set_weights(*golden_weights(golden("model.npz"), "rand"))
+    n = 1000
+    eng.selfplay_init(n, first_id=0, id_stride=n, seed=SEED, first_mover=1, traj_cap=2048, record_chosen=True)
+    st = eng.selfplay_round(epsilon=1.0)
+    rec, ply, gid = eng.selfplay_read()
+    assert st["games_finished"] == n and st["truncated"] == 0 and st["plies"] == int(ply.sum())
+    wins = 0
+    for slot in range(n):
+        g = int(gid[slot])
+        pre, cho = eng.export_trajectory(slot)
+        assert len(pre) == ply[slot] > 0
+        s = np.zeros(28, np.int32)
+        s[:24] = START_BOARD
+        mover = g & 1                                                   # FIRST_PARITY: first mover = id % 2
+        for t in range(len(pre)):
+            x = orc.philox(SEED, t, g, 0, 0)
+            d1, d2 = orc.die(x[0]), orc.die(x[1])
+            assert np.array_equal(pre[t, :28], s.astype(np.int8)) and (int(pre[t, 28]), int(pre[t, 29]), int(pre[t, 30])) == (mover, d1, d2), (g, t)
+            mv, ln, states = orc.turn_sequences(s, mover, d1, d2)
+            if ref is not None and slot % 50 == 0:
+                rmv, rln, rstates = ref.turn_sequences(s, mover, d1, d2)
+                assert np.array_equal(mv, rmv) and np.array_equal(ln, rln) and np.array_equal(states, rstates), (g, t)
+            if len(ln):
+                e = orc.philox(SEED, t, g, 0, 2)
+                assert np.float32(e[0]) * np.float32(2.3283064365386963e-10) < np.float32(1.0)   # the explore draw
+                s = states[(e[1] * len(ln)) >> 32].astype(np.int32)
+            assert np.array_equal(cho[t, :28], s.astype(np.int8)), (g, t)
+            assert int(cho[t, 31]) == (1 if len(ln) and ln[(e[1] * len(ln)) >> 32] > 0 else 0), (g, t)
+            over = orc.game_over(s)
+            assert (over >= 0) == (t == len(pre) - 1), (g, t)
+            mover ^= 1
+        assert over == int(rec[slot, 31]) - 1
+        wins += over == 0
+    assert wins == st["p1_wins"]
+
+
 def test_selfplay_step_restarts_and_rank_invariance(eng, golden):
     """Slots sharded over 'ranks' play the same games as one big population (ids = first_id + slot, stride = global)."""
     eng.set_weights(*golden_weights(golden("model.npz"), "trained"))
