@@ -10,6 +10,11 @@
 // the CURRENT weights, closed-form gradients of the 2-layer sigmoid net,
 // and the same fp32 roundings torch produces (separate multiply and add, lr*delta formed in
 // float64 then rounded to fp32).  Two __syncthreads per step.
+//
+// Blackwell packed fp32: the two forwards run on FFMA2 (fma.rn.f32x2, x stored as {x, x} pairs).  Measured dead ends
+// (profiles/r1_td_replay_ncu_summary.md): the trace/weight update on FFMA2 with exact unfused roundings (fma(a,b,-0),
+// fma(a,1,b)) is 4 % slower than scalar FMUL/FADD, and visiting only the non-zero rows through a switch costs 25 %:
+// the step is bound by its dependent phases and two barriers, not by issue slots.
 #pragma once
 #include "bgx_device.cuh"
 
@@ -18,7 +23,7 @@ namespace bgx {
 constexpr int kTdThreads = 512;
 constexpr int kTdWarps = kTdThreads / 32;
 constexpr int kTdRows = (kFeatures + kTdWarps - 1) / kTdWarps;      // 13 feature rows per warp
-constexpr int kTdXStride = 200;                    // dense x of one state (198 + pad)
+constexpr int kTdXStride = 400;                    // dense x of one state, every entry twice ({x, x}: an FFMA2 operand), 198 + pad pairs
 // shared memory map (floats)
 constexpr int kTdX = 0;                            // x of three consecutive states, rotating
 constexpr int kTdPart = kTdX + 3 * kTdXStride;     // partial pre-activations [16 warps][2 states][128]
@@ -48,26 +53,39 @@ struct TdParams {
     double *dstats;            // [0] sum of squared TD errors
 };
 
-// one warp turns one 32-byte record into the dense x[198] (model.py:111-144); every entry is written
+// packed fp32 (sm_100): d = a * b + c on two lanes, one rounding each
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long A, B, Cc, D;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(Cc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(Cc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(D));
+    return d;
+}
+// one warp turns one 32-byte record into the dense x[198] (model.py:111-144), every entry stored twice; all are written
 __device__ __forceinline__ void td_features(int b, int lane, float *dense)
 {
     const int v = lane < 28 ? b : 0;
     const int turn = __shfl_sync(kFull, b, 28) ? 1 : 0;
     const int c = v < 0 ? -v : v;
+    float4 *d4 = reinterpret_cast<float4 *>(dense);             // d4[i] = {x[2i], x[2i], x[2i+1], x[2i+1]}
     if (lane < 24) {
-        float2 *d = reinterpret_cast<float2 *>(dense + 8 * lane);
         const float a = c >= 1 ? 1.f : 0.f, bb = c >= 2 ? 1.f : 0.f, cc = c >= 3 ? 1.f : 0.f;
         const float dd = c >= 4 ? (float)(c - 3) * 0.5f : 0.f;
         const bool p1 = v > 0;
-        d[0] = p1 ? make_float2(a, bb) : make_float2(0.f, 0.f);
-        d[1] = p1 ? make_float2(cc, dd) : make_float2(0.f, 0.f);
-        d[2] = p1 ? make_float2(0.f, 0.f) : make_float2(a, bb);
-        d[3] = p1 ? make_float2(0.f, 0.f) : make_float2(cc, dd);
+        const float4 lo = make_float4(a, a, bb, bb), hi = make_float4(cc, cc, dd, dd), z = make_float4(0.f, 0.f, 0.f, 0.f);
+        d4[4 * lane + 0] = p1 ? lo : z;
+        d4[4 * lane + 1] = p1 ? hi : z;
+        d4[4 * lane + 2] = p1 ? z : lo;
+        d4[4 * lane + 3] = p1 ? z : hi;
     } else if (lane < 28) {
-        dense[170 + lane] = lane < 26 ? (float)v * 0.5f : off_feature(v);
+        const float x = lane < 26 ? (float)v * 0.5f : off_feature(v);
+        reinterpret_cast<float2 *>(dense)[170 + lane] = make_float2(x, x);
     } else if (lane == 28) {
-        dense[192] = turn == 0 ? 1.f : 0.f;
-        dense[193] = turn == 0 ? 0.f : 1.f;
+        d4[96] = turn == 0 ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 1.f, 1.f);
     }
 }
 
@@ -85,7 +103,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
 
     unsigned long long steps = 0, games = 0;
     double sq_sum = 0.0;
-    float4 W[kTdRows], E[kTdRows];                  // this thread's slice of W1 and of its traces
+    float2 W[kTdRows][2], E[kTdRows][2];            // this thread's slice of W1 and of its traces (hidden 4l,4l+1 | 4l+2,4l+3)
 
     for (long long g = blockIdx.x; g < p.n_games; g += gridDim.x) {
         const int status = (int)p.slots[g * 32 + 31];
@@ -101,8 +119,9 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
 #pragma unroll
         for (int r = 0; r < kTdRows; r++) {
             const int f = warp + kTdWarps * r;
-            W[r] = f < kFeatures ? wt4[f * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-            E[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 w4 = f < kFeatures ? wt4[f * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            W[r][0] = make_float2(w4.x, w4.y); W[r][1] = make_float2(w4.z, w4.w);
+            E[r][0] = E[r][1] = make_float2(0.f, 0.f);
         }
         if (tid < kHidden) {
             b1[tid] = p.flat[kTableFloats + tid];
@@ -121,29 +140,31 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
             const float *xc = xs + (t % 3) * kTdXStride, *xn = xs + ((t + 1) % 3) * kTdXStride;
             const float *w2c = w2 + (t & 1) * kHidden;
             float *w2n = w2 + ((t + 1) & 1) * kHidden;
-            // (1) both forwards, first layer: this warp's rows against x(s_t) and x(s_t+1)
+            // (1) both forwards, first layer: this warp's rows against x(s_t) and x(s_t+1), two hidden units per FFMA2
             {
-                float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za;
+                float2 z[2][2] = {{make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}};
 #pragma unroll
                 for (int r = 0; r < kTdRows; r++) {
                     const int f = warp + kTdWarps * r;
                     if (f < kFeatures) {
-                        const float xa = xc[f], xb = terminal ? 0.f : xn[f];
-                        if (xa != 0.f) { za.x += xa * W[r].x; za.y += xa * W[r].y; za.z += xa * W[r].z; za.w += xa * W[r].w; }
-                        if (xb != 0.f) { zb.x += xb * W[r].x; zb.y += xb * W[r].y; zb.z += xb * W[r].z; zb.w += xb * W[r].w; }
+                        const float2 xa = *reinterpret_cast<const float2 *>(xc + 2 * f);
+                        const float2 xb = terminal ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2 *>(xn + 2 * f);
+                        z[0][0] = fma2(xa, W[r][0], z[0][0]); z[0][1] = fma2(xa, W[r][1], z[0][1]);
+                        z[1][0] = fma2(xb, W[r][0], z[1][0]); z[1][1] = fma2(xb, W[r][1], z[1][1]);
                     }
                 }
-                reinterpret_cast<float4 *>(part + (warp * 2 + 0) * kHidden)[lane] = za;
-                reinterpret_cast<float4 *>(part + (warp * 2 + 1) * kHidden)[lane] = zb;
+                reinterpret_cast<float4 *>(part + (warp * 2 + 0) * kHidden)[lane] = make_float4(z[0][0].x, z[0][0].y, z[0][1].x, z[0][1].y);
+                reinterpret_cast<float4 *>(part + (warp * 2 + 1) * kHidden)[lane] = make_float4(z[1][0].x, z[1][0].y, z[1][1].x, z[1][1].y);
             }
             __syncthreads();
             // (2) hidden layer and output partials: thread = (state s, hidden unit j); meanwhile warp 8 encodes s_t+2
             if (tid < 2 * kHidden) {
                 const int s = tid >> 7, j = tid & 127;
                 if (s == 0 || !terminal) {
-                    double zd = 0.0;                               // few-term fp32 partials, summed without further rounding
-#pragma unroll 4
-                    for (int w = 0; w < kTdWarps; w++) zd += (double)part[(w * 2 + s) * kHidden + j];
+                    double za4[4] = {0.0, 0.0, 0.0, 0.0};         // few-term fp32 partials, summed in float64 (exact): four short chains
+#pragma unroll
+                    for (int w = 0; w < kTdWarps; w++) za4[w & 3] += (double)part[(w * 2 + s) * kHidden + j];
+                    const double zd = (za4[0] + za4[1]) + (za4[2] + za4[3]);
                     const float h = sigmoid_f32((float)(zd + (double)b1[j]));
                     hs[s * kHidden + j] = h;
                     float y = w2c[j] * h;
@@ -183,15 +204,15 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
             for (int r = 0; r < kTdRows; r++) {
                 const int f = warp + kTdWarps * r;
                 if (f < kFeatures) {
-                    const float xf = xc[f];
-                    E[r].x = __fadd_rn(__fmul_rn(lam, E[r].x), __fmul_rn(gh[0], xf));
-                    E[r].y = __fadd_rn(__fmul_rn(lam, E[r].y), __fmul_rn(gh[1], xf));
-                    E[r].z = __fadd_rn(__fmul_rn(lam, E[r].z), __fmul_rn(gh[2], xf));
-                    E[r].w = __fadd_rn(__fmul_rn(lam, E[r].w), __fmul_rn(gh[3], xf));
-                    W[r].x = __fadd_rn(W[r].x, __fmul_rn(c, E[r].x));
-                    W[r].y = __fadd_rn(W[r].y, __fmul_rn(c, E[r].y));
-                    W[r].z = __fadd_rn(W[r].z, __fmul_rn(c, E[r].z));
-                    W[r].w = __fadd_rn(W[r].w, __fmul_rn(c, E[r].w));
+                    const float xf = xc[2 * f];
+                    E[r][0].x = __fadd_rn(__fmul_rn(lam, E[r][0].x), __fmul_rn(gh[0], xf));
+                    E[r][0].y = __fadd_rn(__fmul_rn(lam, E[r][0].y), __fmul_rn(gh[1], xf));
+                    E[r][1].x = __fadd_rn(__fmul_rn(lam, E[r][1].x), __fmul_rn(gh[2], xf));
+                    E[r][1].y = __fadd_rn(__fmul_rn(lam, E[r][1].y), __fmul_rn(gh[3], xf));
+                    W[r][0].x = __fadd_rn(W[r][0].x, __fmul_rn(c, E[r][0].x));
+                    W[r][0].y = __fadd_rn(W[r][0].y, __fmul_rn(c, E[r][0].y));
+                    W[r][1].x = __fadd_rn(W[r][1].x, __fmul_rn(c, E[r][1].x));
+                    W[r][1].y = __fadd_rn(W[r][1].y, __fmul_rn(c, E[r][1].y));
                 }
             }
             if (warp == 0) {
@@ -232,7 +253,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
                 if (f < kFeatures) {
                     float4 a = acc[f * 32 + lane];
                     const float4 o = wt4[f * 32 + lane];
-                    a.x += W[r].x - o.x; a.y += W[r].y - o.y; a.z += W[r].z - o.z; a.w += W[r].w - o.w;
+                    a.x += W[r][0].x - o.x; a.y += W[r][0].y - o.y; a.z += W[r][1].x - o.z; a.w += W[r][1].y - o.w;
                     acc[f * 32 + lane] = a;
                 }
             }
@@ -247,10 +268,10 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
             for (int r = 0; r < kTdRows; r++) {
                 const int f = warp + kTdWarps * r;
                 if (f < kFeatures) {
-                    p.final_weights[(4 * lane + 0) * kFeatures + f] = W[r].x;
-                    p.final_weights[(4 * lane + 1) * kFeatures + f] = W[r].y;
-                    p.final_weights[(4 * lane + 2) * kFeatures + f] = W[r].z;
-                    p.final_weights[(4 * lane + 3) * kFeatures + f] = W[r].w;
+                    p.final_weights[(4 * lane + 0) * kFeatures + f] = W[r][0].x;
+                    p.final_weights[(4 * lane + 1) * kFeatures + f] = W[r][0].y;
+                    p.final_weights[(4 * lane + 2) * kFeatures + f] = W[r][1].x;
+                    p.final_weights[(4 * lane + 3) * kFeatures + f] = W[r][1].y;
                 }
             }
             if (tid < kHidden) {
