@@ -165,6 +165,19 @@ class BatchEngine:
                                                       L.ptr(out.get("chosen")), L.ptr(out.get("moves")), L.ptr(out.get("moves_len")),
                                                       L.ptr(out.get("value")), L.ptr(out.get("n_seq")), L.ptr(out.get("n_scored"))))
 
+    def play_ply_host_async(self, lane, records, next_ply, game_id, next_records, winner=None, value=None, n_seq=None,
+                            epsilon=0.0, explore_seed=0, dice_seed=0x5EED2026):
+        """One iteration of play_game's loop (train.py:103-121) for a batch of games through (pinned) numpy buffers:
+        make_move + is_game_over + setTurn + roll_dice of ply next_ply[i] of game game_id[i].  wait(lane) completes it."""
+        q = _records(records)
+        n = q.shape[0]
+        assert next_records.dtype == np.int8 and next_records.shape == (n, 32) and next_records.flags["C_CONTIGUOUS"]
+        assert next_ply is None or (next_ply.dtype == np.int32 and next_ply.shape == (n,) and next_ply.flags["C_CONTIGUOUS"])
+        assert game_id is None or (game_id.dtype == np.int64 and game_id.shape == (n,) and game_id.flags["C_CONTIGUOUS"])
+        L.check(self._lib.bgx_play_ply_host_async(self._h, int(lane), q.ctypes.data, L.ptr(next_ply), L.ptr(game_id), n,
+                                                  float(epsilon), int(explore_seed), int(dice_seed),
+                                                  L.ptr(next_records), L.ptr(winner), L.ptr(value), L.ptr(n_seq)))
+
     def wait(self, lane):
         L.check(self._lib.bgx_lane_wait(self._h, int(lane)))
 

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "bgx_select_moves": (C.c_int, [_vp, _vp, _i64, C.c_float, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bgx_select_moves_host": (C.c_int, [_vp, _vp, _i64, C.c_float, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bgx_select_moves_host_async": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_float, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bgx_play_ply_host_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _i64, C.c_float, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
     "bgx_lane_wait": (C.c_int, [_vp, C.c_int]),
     "bgx_advance": (C.c_int, [_vp, _vp, _vp, _i64, C.c_uint64, C.c_int32, _vp, _vp]),
     "bgx_advance_host": (C.c_int, [_vp, _vp, _i64, C.c_uint64, _vp, _vp, _vp]),

@@ -19,12 +19,14 @@ struct bgx_lane {
     cudaEvent_t done = nullptr;
     unsigned long long *counter = nullptr;   // [0] work queue, [8..15] the 16 bucket totals of k_select_order
     StealResult *steal = nullptr;
-    void *buf[8] = {};                       // [7]: sorted queue
-    size_t cap[8] = {};
+    void *buf[11] = {};                      // [7] [10]: sorted queues (two slots), [8] [9]: ply and game id of bgx_play_ply_host_async
+    size_t cap[11] = {};
+    int order_slot = 0;                      // slot holding the queue the previous bgx_play_ply_host_async produced for its successor ...
+    int64_t order_n = -1;                    // ... valid for a batch of exactly this many queries (-1: none)
     bool busy = false;
 };
 constexpr int kLanes = BGX_ASYNC_LANES;
-constexpr size_t kCounterBytes = 128;        // work-queue counter + 16 x uint32 bucket totals at byte 64
+constexpr size_t kCounterBytes = 256;        // work-queue counter; 16 x uint32 bucket totals at byte 64 (slot 0) and 128 (slot 1)
 
 struct bgx_engine {
     int device = 0;
@@ -447,21 +449,40 @@ int bgx_evaluate_host(bgx_engine *e, const int8_t *records, int64_t n, float *V)
 
 // ------------------------------------------------------------------------ batched make_move
 
+// the sorted queue of one launch: read from `slot` (computed here by k_select_order unless the previous launch of the lane left
+// it there), and - in the fused play-ply form - the next launch's queue written to the other slot
+struct OrderPlan {
+    int32_t *region[2] = {nullptr, nullptr};
+    int slot = 0;
+    bool ready = false;          // region[slot] / totals[slot] were produced by the previous launch
+    bool produce = false;        // fill region[1 - slot] for the next launch (adv.next must be set)
+};
+
 static int launch_select(bgx_engine *e, cudaStream_t stream, unsigned long long *counter, StealResult *steal,
-                         const int8_t *queries, int64_t n, float epsilon, uint64_t seed, const SelectOut &out, int32_t *region,
-                         int grid = 0)
+                         const int8_t *queries, int64_t n, float epsilon, uint64_t seed, const SelectOut &out, const OrderPlan &plan,
+                         int grid = 0, AdvanceOut adv = AdvanceOut{})
 {
     if (grid <= 0 || grid > e->sm_count) grid = game_grid(e);
-    CU(cudaMemsetAsync(counter, 0, kCounterBytes, stream));
-    uint32_t *totals = reinterpret_cast<uint32_t *>(counter + 8);
-    if (region) {
+    uint32_t *totals_of[2] = {reinterpret_cast<uint32_t *>(counter) + 16, reinterpret_cast<uint32_t *>(counter) + 32};
+    int32_t *region = plan.region[plan.slot];
+    uint32_t *totals = totals_of[plan.slot];
+    CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    if (region && !plan.ready) {
+        CU(cudaMemsetAsync(totals, 0, kOrderBuckets * sizeof(uint32_t), stream));
         k_select_order<<<(unsigned)((n + kOrderCtaQueries - 1) / kOrderCtaQueries), 256, 0, stream>>>(queries, n, region, totals);
         e->launches++;
+    }
+    adv.next_region = nullptr;
+    adv.next_totals = nullptr;
+    if (plan.produce && adv.next && plan.region[1 - plan.slot]) {
+        adv.next_region = plan.region[1 - plan.slot];
+        adv.next_totals = totals_of[1 - plan.slot];
+        CU(cudaMemsetAsync(adv.next_totals, 0, kOrderBuckets * sizeof(uint32_t), stream));
     }
     const SelectTune tune = {(unsigned long long)(n * (int64_t)e->select_urgent_from_pct / 100), e->select_urgent_min, e->select_giant_min};
 #define BGX_LAUNCH_SELECT(W, S, X)                                                                          \
     k_select<W, S, X><<<grid, W * 32, ply_smem<W, S>(), stream>>>(queries, n, epsilon, (uint32_t)seed, \
-                                                                          (uint32_t)(seed >> 32), out, e->fixed, e->flat, counter, steal, tune, region, totals)
+                                                                          (uint32_t)(seed >> 32), out, e->fixed, e->flat, counter, steal, tune, region, totals, adv)
     const bool ex = epsilon > 0.f;
     if (e->select_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 110, true); else BGX_LAUNCH_SELECT(16, 110, false); }
     else if (e->select_warps == 20) { if (ex) BGX_LAUNCH_SELECT(20, 87, true); else BGX_LAUNCH_SELECT(20, 87, false); }
@@ -486,8 +507,10 @@ int bgx_select_moves(bgx_engine *e, const int8_t *queries, int64_t n, float epsi
         const int rs = scratch(e, 11, (size_t)n * kOrderBuckets * 4, &region);
         if (rs) return rs;
     }
+    OrderPlan plan;
+    plan.region[0] = (int32_t *)region;
     tick(e);
-    const int rc = launch_select(e, e->stream, e->counter, e->steal, queries, n, epsilon, seed, out, (int32_t *)region);
+    const int rc = launch_select(e, e->stream, e->counter, e->steal, queries, n, epsilon, seed, out, plan);
     tock(e);
     return rc;
 }
@@ -572,13 +595,75 @@ int bgx_select_moves_host_async(bgx_engine *e, int lane, const int8_t *queries, 
                            value ? (float *)dv : nullptr, n_seq ? (int32_t *)dn : nullptr, n_scored ? (int32_t *)ds : nullptr};
     void *region = nullptr;
     if (n <= e->select_order_max && (rc = lane_scratch(l, 7, (size_t)n * kOrderBuckets * 4, &region))) return rc;
-    if ((rc = launch_select(e, l.stream, l.counter, l.steal, (const int8_t *)dq, n, epsilon, seed, out, (int32_t *)region, e->lane_grid))) return rc;
+    OrderPlan plan;
+    plan.region[0] = (int32_t *)region;
+    l.order_n = -1;
+    if ((rc = launch_select(e, l.stream, l.counter, l.steal, (const int8_t *)dq, n, epsilon, seed, out, plan, e->lane_grid))) return rc;
     if (chosen) CU(cudaMemcpyAsync(chosen, dc, (size_t)n * 32, cudaMemcpyDeviceToHost, l.stream));
     if (moves) CU(cudaMemcpyAsync(moves, dm, (size_t)n * 8, cudaMemcpyDeviceToHost, l.stream));
     if (moves_len) CU(cudaMemcpyAsync(moves_len, dl, (size_t)n, cudaMemcpyDeviceToHost, l.stream));
     if (value) CU(cudaMemcpyAsync(value, dv, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
     if (n_seq) CU(cudaMemcpyAsync(n_seq, dn, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
     if (n_scored) CU(cudaMemcpyAsync(n_scored, ds, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
+    CU(cudaEventRecord(l.done, l.stream));
+    l.busy = true;
+    return BGX_OK;
+}
+
+// One iteration of play_game's loop (train.py:103-121) for n games through host buffers, asynchronous:
+// make_move, is_game_over, setTurn, roll_dice.  = bgx_select_moves_host_async + bgx_advance_host in one queued call.
+int bgx_play_ply_host_async(bgx_engine *e, int lane, const int8_t *records, const int32_t *next_ply, const int64_t *game_id,
+                            int64_t n, float epsilon, uint64_t explore_seed, uint64_t dice_seed,
+                            int8_t *next_records, int8_t *winner, float *value, int32_t *n_seq)
+{
+    USE(e);
+    NEED(lane >= 0 && lane < kLanes, "lane out of range");
+    NEED(records && next_records && n >= 0, "bad argument");
+    if (!e->have_weights) { set_error("bgx_play_ply_host_async: weights not set"); return BGX_E_STATE; }
+    bgx_lane &l = e->lanes[lane];
+    if (l.busy) { set_error("bgx_play_ply_host_async: lane %d has a batch in flight (bgx_lane_wait first)", lane); return BGX_E_STATE; }
+    if (!l.stream) {
+        CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        CU(cudaMalloc(&l.counter, kCounterBytes));
+        CU(cudaMalloc(&l.steal, (size_t)e->sm_count * 32 * kStealMaxResults * sizeof(StealResult)));
+    }
+    if (n == 0) return BGX_OK;
+    void *dq, *dc, *dw, *dv, *dn, *dp = nullptr, *dg = nullptr, *r0 = nullptr, *r1 = nullptr;
+    int rc;
+    if ((rc = lane_scratch(l, 0, (size_t)n * 32, &dq))) return rc;
+    if ((rc = lane_scratch(l, 1, (size_t)n * 32, &dc))) return rc;
+    if ((rc = lane_scratch(l, 3, (size_t)n, &dw))) return rc;
+    if ((rc = lane_scratch(l, 4, (size_t)n * 4, &dv))) return rc;
+    if ((rc = lane_scratch(l, 5, (size_t)n * 4, &dn))) return rc;
+    if (next_ply && (rc = lane_scratch(l, 8, (size_t)n * 4, &dp))) return rc;
+    if (game_id && (rc = lane_scratch(l, 9, (size_t)n * 8, &dg))) return rc;
+    OrderPlan plan;
+    if (n <= e->select_order_max) {
+        const void *before[2] = {l.buf[7], l.buf[10]};
+        if ((rc = lane_scratch(l, 7, (size_t)n * kOrderBuckets * 4, &r0))) return rc;
+        if ((rc = lane_scratch(l, 10, (size_t)n * kOrderBuckets * 4, &r1))) return rc;
+        if (before[0] != l.buf[7] || before[1] != l.buf[10]) l.order_n = -1;      // reallocated: the stored queue is gone
+        plan.region[0] = (int32_t *)r0;
+        plan.region[1] = (int32_t *)r1;
+        plan.slot = l.order_slot;
+        plan.ready = l.order_n == n;           // the previous call on this lane sorted ITS outputs for us: if the caller's
+        plan.produce = true;                   // queries are something else the order is merely a poor one, never wrong
+    }
+    CU(cudaEventRecord(e->ev_sync, e->stream));
+    CU(cudaStreamWaitEvent(l.stream, e->ev_sync, 0));
+    CU(cudaMemcpyAsync(dq, records, (size_t)n * 32, cudaMemcpyHostToDevice, l.stream));
+    if (dp) CU(cudaMemcpyAsync(dp, next_ply, (size_t)n * 4, cudaMemcpyHostToDevice, l.stream));
+    if (dg) CU(cudaMemcpyAsync(dg, game_id, (size_t)n * 8, cudaMemcpyHostToDevice, l.stream));
+    const SelectOut out = {nullptr, nullptr, nullptr, value ? (float *)dv : nullptr, n_seq ? (int32_t *)dn : nullptr, nullptr};
+    AdvanceOut adv = {(int8_t *)dc, winner ? (int8_t *)dw : nullptr, (const int32_t *)dp, (const long long *)dg,
+                      (uint32_t)dice_seed, (uint32_t)(dice_seed >> 32), nullptr, nullptr};
+    if ((rc = launch_select(e, l.stream, l.counter, l.steal, (const int8_t *)dq, n, epsilon, explore_seed, out, plan, e->lane_grid, adv))) return rc;
+    if (plan.produce) { l.order_slot = 1 - plan.slot; l.order_n = n; }
+    CU(cudaMemcpyAsync(next_records, dc, (size_t)n * 32, cudaMemcpyDeviceToHost, l.stream));
+    if (winner) CU(cudaMemcpyAsync(winner, dw, (size_t)n, cudaMemcpyDeviceToHost, l.stream));
+    if (value) CU(cudaMemcpyAsync(value, dv, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
+    if (n_seq) CU(cudaMemcpyAsync(n_seq, dn, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
     CU(cudaEventRecord(l.done, l.stream));
     l.busy = true;
     return BGX_OK;

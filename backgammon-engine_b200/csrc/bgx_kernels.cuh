@@ -440,6 +440,36 @@ __global__ void __launch_bounds__(256) k_select_order(const int8_t *__restrict__
     }
 }
 
+// bgx_play_ply_host_async: the rest of the ply (k_advance's work) done by the warp that chose the move, and the
+// bucket of the NEXT ply's query appended to the sorted queue of the lane's next launch - one kernel per ply-step,
+// no small kernels that would wait for an SM behind the persistent ones.
+struct AdvanceOut {
+    int8_t *next;                 // [n][32] advanced records (nullptr: plain select)
+    int8_t *winner;               // [n] or nullptr
+    const int32_t *ply_of;        // [n] ply whose dice each game gets, or nullptr (0)
+    const long long *game_id;     // [n] or nullptr (the query index)
+    uint32_t seed_lo, seed_hi;    // dice key
+    int32_t *next_region;         // [16][n] or nullptr
+    uint32_t *next_totals;        // [16], zeroed by the caller
+};
+
+__device__ __forceinline__ void store_advanced(const AdvanceOut &a, long long q, long long n, int v, int lane, int player)
+{
+    const int off1 = __shfl_sync(kFull, v, 26), off2 = __shfl_sync(kFull, v, 27);
+    const int win = off1 == 15 ? 0 : (off2 == 15 ? 1 : -1);                  // game.cpp:388-407
+    const unsigned long long g = a.game_id ? (unsigned long long)a.game_id[q] : (unsigned long long)q;
+    const Philox r = philox4x32_10(a.seed_lo, a.seed_hi, (uint32_t)(a.ply_of ? a.ply_of[q] : 0), (uint32_t)g, (uint32_t)(g >> 32), 0u);
+    const int mover = win < 0 ? player ^ 1 : player, d1 = die_of(r.x[0]), d2 = die_of(r.x[1]);
+    const int tail = lane == 28 ? mover : lane == 29 ? d1 : lane == 30 ? d2 : win + 1;
+    a.next[q * 32 + lane] = (int8_t)(lane < 28 ? v : tail);
+    if (a.winner && lane == 0) a.winner[q] = (int8_t)win;
+    if (a.next_region) {
+        // a finished game is restarted by the caller: an opening position, mid-sized
+        const int b = win < 0 ? order_bucket(lane < 28 ? v : 0, lane, mover, d1, d2) : 6;
+        if (lane == 0) a.next_region[(size_t)b * n + atomicAdd(&a.next_totals[b], 1u)] = (int32_t)q;
+    }
+}
+
 // when the CTA of a published double helps before claiming new queue work (bgx_ply.cuh ShareCtx)
 struct SelectTune {
     unsigned long long urgent_from;      // queue position from which doubles with >= urgent_min root origins are urgent
@@ -451,7 +481,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
 k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_t seed_lo, uint32_t seed_hi,
          SelectOut out, const int32_t *__restrict__ Ti, const float *__restrict__ flat,
          unsigned long long *counter, StealResult *__restrict__ steal, SelectTune tune,
-         const int32_t *__restrict__ region, const uint32_t *__restrict__ totals)
+         const int32_t *__restrict__ region, const uint32_t *__restrict__ totals, AdvanceOut adv)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const PlySmem<kWarps, kSets> sm(smem);
@@ -519,13 +549,17 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
         const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, player, d1, d2, ev, cache, explore, u, only ? only : kFull,
                                                           only ? nullptr : &mine);
         if (only) deliver_child<kWarps>(sm.share, cta_results, vw, only, c, lane);
-        else store_choice(out, q, c, lane, player);
+        else {
+            store_choice(out, q, c, lane, player);
+            if (adv.next) store_advanced(adv, q, n, c.v, lane, player);
+        }
     }
 }
 
 // ---- the rest of a host-driven ply: game over? flip the mover, roll the next dice ---------------
-__global__ void k_advance(const int8_t *__restrict__ chosen, int8_t *__restrict__ next, long long n, uint32_t seed_lo,
-                          uint32_t seed_hi, int ply, const long long *__restrict__ game_id, int8_t *__restrict__ winner)
+__global__ void k_advance(const int8_t *chosen, int8_t *next, long long n, uint32_t seed_lo,
+                          uint32_t seed_hi, int ply, const long long *__restrict__ game_id, int8_t *__restrict__ winner,
+                          const int32_t *__restrict__ ply_of = nullptr)
 {
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -534,7 +568,7 @@ __global__ void k_advance(const int8_t *__restrict__ chosen, int8_t *__restrict_
         const int off1 = __shfl_sync(kFull, b, 26), off2 = __shfl_sync(kFull, b, 27), mover = __shfl_sync(kFull, b, 28) ? 1 : 0;
         const int win = off1 == 15 ? 0 : (off2 == 15 ? 1 : -1);            // game.cpp:388-407
         const unsigned long long g = game_id ? (unsigned long long)game_id[q] : (unsigned long long)q;
-        const Philox r = philox4x32_10(seed_lo, seed_hi, (uint32_t)ply, (uint32_t)g, (uint32_t)(g >> 32), 0u);
+        const Philox r = philox4x32_10(seed_lo, seed_hi, (uint32_t)(ply_of ? ply_of[q] : ply), (uint32_t)g, (uint32_t)(g >> 32), 0u);
         const int tail = lane == 28 ? (win < 0 ? mover ^ 1 : mover) : lane == 29 ? die_of(r.x[0]) : lane == 30 ? die_of(r.x[1]) : win + 1;
         next[q * 32 + lane] = (int8_t)(lane < 28 ? b : tail);
         if (winner && lane == 0) winner[q] = (int8_t)win;

@@ -14,7 +14,9 @@
 // Blackwell packed fp32: the two forwards run on FFMA2 (fma.rn.f32x2, x stored as {x, x} pairs).  Measured dead ends
 // (profiles/r1_td_replay_ncu_summary.md): the trace/weight update on FFMA2 with exact unfused roundings (fma(a,b,-0),
 // fma(a,1,b)) is 4 % slower than scalar FMUL/FADD, and visiting only the non-zero rows through a switch costs 25 %:
-// the step is bound by its dependent phases and two barriers, not by issue slots.
+// the step is bound by its dependent phases and two barriers, not by issue slots.  One game per 2-CTA cluster (64 hidden units
+// per CTA, output partials exchanged through DSMEM, halves of two games resident per SM) was built and measured too: 7 %
+// slower - the overlap of two games' phases gains nothing, the cluster barrier costs ~380 cycles per step.
 #pragma once
 #include "bgx_device.cuh"
 

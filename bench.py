@@ -9,9 +9,10 @@ epsilon = 0, Philox dice, first mover g % 2, finished games restart in place.  O
 game of the population plays PLIES_PER_STEP plies (one k_selfplay launch).
 
   value      plies/s with the population resident in HBM (CUDA events on the launching stream)
-  e2e        plies/s through the batched make_move C-ABI call with HOST buffers: every ply the
-             65,536 (position, dice) records go pinned-host -> device, the chosen afterstates
-             come back, and the host advances the games (bgx_select_moves_host)
+  e2e        plies/s through the C-ABI with HOST buffers: every ply the 65,536 (position, dice) records, ply
+             numbers and game ids go pinned-host -> device, one iteration of play_game's loop runs for all of
+             them (make_move, is_game_over, setTurn, roll_dice: bgx_play_ply_host_async), the next records and
+             the winners come back, and the host restarts finished games
   roofline   the self-play kernel against the measured HBM peak, in the units SURVEY.md §8(d)
              prescribes: 1,696 algorithmic bytes per enumerated afterstate
   cpu_baseline  the reference engine + model.py loop on the host cores (oracle/ref_play.py)
@@ -97,15 +98,42 @@ def run_reference(args):
         procs = 1
         sample = f"oracle/bgx_oracle.c greedy self-play, 1 thread, {tot_t:.1f} s"
     value = tot_p / tot_t
+    direct = cpp_direct_sample()
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus),
             "sequences_per_sec": tot_s / tot_t,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample, "enumeration_only": direct},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def cpp_direct_sample(n=1500):
+    """SURVEY 8d's C++-direct comparator on ONE core, enumeration only (no Python, no model): the reference's own
+    evaluateTurnSequences (oracle/_ref, ~97 % of it mt19937_64 construction in Game::clone) and the oracle port
+    (the same algorithm without that cost = the honest CPU ceiling), on the first n positions of the configs[1] sweep."""
+    import numpy as np
+    from bgx.synth import make_queries
+    from oracle.oracle import Oracle, RefHarness
+    q, _ = make_queries(n, seed=20260101)
+    out = {"positions": n, "cores": 1}
+    try:
+        orc = Oracle()
+        t0 = time.perf_counter()
+        ns, _, _ = orc.turn_summary_batch(q, threads=1)
+        out["oracle_port_sequences_per_sec"] = float(ns.sum()) / (time.perf_counter() - t0)
+        if RefHarness.available():
+            ref = RefHarness()
+            tot = np.zeros(1, np.int64)
+            import ctypes
+            secs = ref.lib.ref_bench_enumerate(np.ascontiguousarray(q[:, :28].astype(np.int32)).reshape(-1), np.ascontiguousarray(q[:, 28]),
+                                               np.ascontiguousarray(q[:, 29:31]).reshape(-1), n, tot.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+            out["reference_sequences_per_sec"] = float(tot[0]) / secs
+    except Exception as exc:
+        out["error"] = str(exc)
+    return out
 
 
 def port_baseline(w, seconds):
@@ -281,34 +309,42 @@ def run_ours(args):
     plies_all, seqs_all, scored_all = (float(x) for x in counts.tolist())
     value = plies_all / total_s
 
-    # ---- end to end: host-driven self-play through the batched make_move C-ABI call, pinned host buffers.
-    # The population is split into three parts, each on its own asynchronous lane (a lane's launch occupies half
-    # the SMs, so two are resident at once): while the GPU plays some (H2D of the records, k_select_order + k_select,
-    # D2H of the chosen afterstates) the host advances another
-    # (game over?, restart, flip the mover, next dice) - the loop of train.py:99-121 for 65,536 games.
+    # ---- end to end: host-driven self-play through the C-ABI with HOST buffers, one call per ply and part of the
+    # population: bgx_play_ply_host_async = one iteration of play_game's loop (train.py:103-121: make_move, is_game_over,
+    # setTurn, roll_dice) for a batch of games.  The population is split into three parts, each on its own asynchronous lane
+    # (a lane's launch occupies half the SMs, so two are resident at once): while the GPU plays some (H2D of records, next ply
+    # numbers and game ids; k_select_order + k_select + k_advance; D2H of the next records and winners) the host handles
+    # another (count the ply, restart finished games in place with the next game id).
     e2e_steps = max(2, min(args.steps, 8)) * PLIES_PER_STEP
     from bgx import host as bgx_host
     LANES = 3
-    q_pin = torch.zeros((G, 32), dtype=torch.int8).pin_memory()
-    ch_pin = torch.zeros((G, 32), dtype=torch.int8).pin_memory()
-    val_pin = torch.zeros(G, dtype=torch.float32).pin_memory()
-    q, ch, val = q_pin.numpy(), ch_pin.numpy(), val_pin.numpy()
+    pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
+    bufs = [pin((G, 32), torch.int8), pin((G, 32), torch.int8)]
+    win = pin((G,), torch.int8)
+    nxt_ply = pin((G,), torch.int32)
+    h_gid_pin = pin((G,), torch.int64)
     rec, h_ply, h_gid = eng.selfplay_read()          # continue the (desynchronised) games of the population from the host
-    q[:] = rec
-    h_win = np.zeros(G, np.int8)
+    h_gid_pin[:] = h_gid
+    h_gid = h_gid_pin
     parts = [(i * G // LANES, (i + 1) * G // LANES) for i in range(LANES)]
+    cur = [0] * LANES
     stride = world * G
+    bufs[0][:] = rec
+    bgx_host.advance(bufs[0], bufs[0], SEED, h_ply, h_gid)   # dice of the current ply for every game (undo the flip below)
+    bufs[0][:, 28] ^= 1
+    bufs[0][:, 31] = 0
 
     def submit(h):
         lo, hi = parts[h]
-        eng.select_moves_host_async(h, q[lo:hi], {"chosen": ch[lo:hi], "value": val[lo:hi]})
+        nxt_ply[lo:hi] = h_ply[lo:hi] + 1
+        eng.play_ply_host_async(h, bufs[cur[h]][lo:hi], nxt_ply[lo:hi], h_gid[lo:hi], bufs[1 - cur[h]][lo:hi], win[lo:hi], dice_seed=SEED)
 
     def advance(h):
         lo, hi = parts[h]
         eng.wait(h)
+        cur[h] ^= 1
         h_ply[lo:hi] += 1
-        bgx_host.advance(ch[lo:hi], q[lo:hi], SEED, h_ply[lo:hi], h_gid[lo:hi], h_win[lo:hi])   # over? flip mover, roll
-        done = np.flatnonzero(h_win[lo:hi] >= 0)
+        done = np.flatnonzero(win[lo:hi] >= 0)
         if done.size:                                   # restart in place with the next game id (first mover: id % 2)
             idx = done + lo
             h_gid[idx] += stride
@@ -316,12 +352,9 @@ def run_ours(args):
             fresh = np.zeros((idx.size, 32), np.int8)
             fresh[:, :24] = START_BOARD
             fresh[:, 28] = (h_gid[idx] & 1) ^ 1         # bgx_advance_host flips it and rolls ply 0
-            q[idx] = bgx_host.advance(fresh, fresh, SEED, h_ply[idx], h_gid[idx])
+            bufs[cur[h]][idx] = bgx_host.advance(fresh, fresh, SEED, h_ply[idx], h_gid[idx])
         return hi - lo
 
-    bgx_host.advance(q, q, SEED, h_ply, h_gid)           # dice of the current ply for every game (undo the flip below)
-    q[:, 28] ^= 1
-    q[:, 31] = 0
     for h in range(LANES):
         submit(h)
     e2e_plies = 0
@@ -357,6 +390,7 @@ def run_ours(args):
         first, n_slots, stride = shard(args.td_games * world, rank, world)
         eng.selfplay_init(n_slots, first_id=first, id_stride=stride, seed=SEED + 1, first_mover=FIRST_ROLLOFF, traj_cap=2048)
         delta = torch.zeros(25604, dtype=torch.float32, device=dev)
+        allreduce_delta(delta, dist if world > 1 else None)      # untimed: NCCL sets this collective up on first use
         barrier()
         e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         e0.record(stream)
@@ -404,10 +438,11 @@ def run_ours(args):
                 "sequences_per_sec": seqs_all / total_s, "afterstates_scored_per_sec": scored_all / total_s,
                 "sequences_per_ply": seqs_all / plies_all, "scored_per_ply": scored_all / plies_all,
                 "tree_edges_per_ply_rank0": edges / max(plies, 1), "ply_warps_per_cta": eng.kernel_config(),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 32, "d2h_bytes_per_step": G * 36,
-                        "note": "one step = one ply for all 65,536 games through bgx_select_moves_host_async (three thirds of the population "
-                                "on three lanes of half the SMs each, pinned host buffers, H2D + k_select_order + k_select + D2H per ply), bgx_advance_host + numpy restarts "
-                                f"on the host between plies; {e2e_steps} timed ply-steps"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 44, "d2h_bytes_per_step": G * 33,
+                        "note": "one step = one ply for all 65,536 games through bgx_play_ply_host_async (= make_move + is_game_over + "
+                                "setTurn + roll_dice of train.py:103-121 for a batch): three thirds of the population on three lanes of half "
+                                "the SMs each, pinned host buffers, H2D (records, ply numbers, game ids) + k_select_order + k_select + "
+                                f"k_advance + D2H (next records, winners) per ply; the host counts plies and restarts finished games; {e2e_steps} timed ply-steps"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -183,6 +183,16 @@ int bgx_select_moves_host_async(bgx_engine *e, int lane, const int8_t *queries, 
                                 int32_t *n_seq, int32_t *n_scored);
 int bgx_lane_wait(bgx_engine *e, int lane);
 
+/* One iteration of play_game's loop (train.py:103-121: make_move, is_game_over, setTurn, roll_dice) for n games,
+ * host buffers in and out, asynchronous on `lane` like the call above.  records[i] = position, mover, the dice
+ * already rolled.  next_records[i] = the chosen afterstate advanced exactly as bgx_advance_host does it: byte 31 =
+ * 1 / 2 when the move ended the game, else 0 and the mover flipped; bytes 29,30 = the dice of ply next_ply[i] of game
+ * game_id[i] (NULL: 0 / i) under dice_seed.  winner[i] = 0 / 1 / -1; winner, value, n_seq may be NULL.
+ * Restarting finished games stays with the caller. */
+int bgx_play_ply_host_async(bgx_engine *e, int lane, const int8_t *records, const int32_t *next_ply, const int64_t *game_id,
+                            int64_t n, float epsilon, uint64_t explore_seed, uint64_t dice_seed,
+                            int8_t *next_records, int8_t *winner, float *value, int32_t *n_seq);
+
 /* The rest of a host-driven ply (train.py:113-121, benchmark.py:88-101) for n games at once, on
  * DEVICE buffers: next[i] = chosen[i] (an afterstate RECORD as bgx_select_moves writes it) with
  *   byte 31 = 1 / 2 when the move ended the game for PLAYER1 / PLAYER2 (game.cpp:388-407, PLAYER1

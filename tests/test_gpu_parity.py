@@ -245,6 +245,60 @@ def test_select_moves_is_a_pure_function_of_the_query(eng, golden, tag):
     eng.wait(2)
 
 
+def test_play_ply_is_select_plus_advance(eng, golden):
+    """bgx_play_ply_host_async (one iteration of play_game's loop, train.py:103-121) = bgx_select_moves_host followed by
+    bgx_advance_host, byte for byte, whatever the lane and the batch split."""
+    from bgx import host as H
+    from bgx.synth import make_queries
+    eng.set_weights(*golden_weights(golden("model.npz"), "trained"))
+    q, _ = make_queries(20000, seed=99)
+    # a few positions one move from the end, so that winners occur
+    rng = np.random.default_rng(3)
+    n = len(q)
+    ply = rng.integers(0, 400, n).astype(np.int32)
+    gid = rng.integers(0, 2 ** 40, n).astype(np.int64)
+    ref = eng.select_moves_host(q)
+    want = np.zeros((n, 32), np.int8)
+    want_win = np.zeros(n, np.int8)
+    H.advance(ref["chosen"], want, 777, ply, gid, want_win)
+    got = np.zeros((n, 32), np.int8)
+    win = np.full(n, 9, np.int8)
+    val = np.zeros(n, np.float32)
+    nseq = np.zeros(n, np.int32)
+    cuts = [0, 1, 7000, 7001, n]
+    for lane, (lo, hi) in enumerate(zip(cuts[:-1], cuts[1:])):
+        eng.play_ply_host_async(lane, q[lo:hi], ply[lo:hi], gid[lo:hi], got[lo:hi], win[lo:hi], val[lo:hi], nseq[lo:hi], dice_seed=777)
+    for lane in range(4):
+        eng.wait(lane)
+    ok = ref["n_seq"] > 0
+
+    def check():
+        assert np.array_equal(got, want)
+        assert np.array_equal(win, want_win) and (want_win >= 0).any()
+        assert np.array_equal(nseq, ref["n_seq"])
+        assert np.array_equal(val[ok].view(np.uint32), ref["value"][ok].view(np.uint32))
+    check()
+    # the same batches again on the same lanes: each launch now walks its queue in the order the previous call left
+    # for its OUTPUTS (a poor order for these inputs) - results must not depend on it
+    for rep in range(2):
+        got[:] = 0; win[:] = 9; val[:] = 0; nseq[:] = 0
+        for lane, (lo, hi) in enumerate(zip(cuts[:-1], cuts[1:])):
+            eng.play_ply_host_async(lane, q[lo:hi], ply[lo:hi], gid[lo:hi], got[lo:hi], win[lo:hi], val[lo:hi], nseq[lo:hi], dice_seed=777)
+        for lane in range(4):
+            eng.wait(lane)
+        check()
+    # and a follow-up ply on the advanced records (the order left by the previous call is now the right one)
+    live = want_win < 0
+    q2 = np.ascontiguousarray(want[live][:7000])
+    ref2 = eng.select_moves_host(q2)
+    want2 = np.zeros_like(q2)
+    H.advance(ref2["chosen"], want2, 777, ply[:7000] + 1, gid[:7000])
+    got2 = np.zeros_like(q2)
+    eng.play_ply_host_async(0, q2, ply[:7000] + 1, gid[:7000], got2, dice_seed=777)
+    eng.wait(0)
+    assert np.array_equal(got2, want2)
+
+
 def test_select_moves_golden_games(eng, orc, golden):
     """The reference's own greedy games (model.make_move on the reference engine), ply by ply."""
     g = golden("games.npz")

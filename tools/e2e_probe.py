@@ -19,25 +19,38 @@ for n in (() if os.environ.get('QUICK') else (G, G // 2, G // 4)):
         eng.select_moves(q, chosen=chosen); torch.cuda.synchronize(); ms.append(eng.last_kernel_ms())
     print(f"k_select({n}): {np.mean(ms[2:]):.3f} ms", flush=True)
 from bgx import host as bgx_host
-q = torch.zeros((G, 32), dtype=torch.int8).pin_memory().numpy(); q[:] = rec
-ch = torch.zeros((G, 32), dtype=torch.int8).pin_memory().numpy()
-_, h_ply, h_gid = eng.selfplay_read()
-h_win = np.zeros(G, np.int8)
+pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
+FUSED = os.environ.get("FUSED", "1") == "1"
+q = pin((G, 32), torch.int8); q[:] = rec
+ch = pin((G, 32), torch.int8)
+bufs = [q, ch]
+win = pin((G,), torch.int8); nxt_ply = pin((G,), torch.int32); h_gid = pin((G,), torch.int64)
+_, h_ply, gid0 = eng.selfplay_read(); h_gid[:] = gid0
 for lanes in [int(x) for x in os.environ.get("LANES", "2,3,4").split(",")]:
     parts = [(i * G // lanes, (i + 1) * G // lanes) for i in range(lanes)]
+    cur = [0] * lanes
+    bufs[0][:] = rec
     def submit(h):
         lo, hi = parts[h]
-        eng.select_moves_host_async(h, q[lo:hi], {"chosen": ch[lo:hi]})
+        if FUSED:
+            nxt_ply[lo:hi] = h_ply[lo:hi] + 1
+            eng.play_ply_host_async(h, bufs[cur[h]][lo:hi], nxt_ply[lo:hi], h_gid[lo:hi], bufs[1 - cur[h]][lo:hi], win[lo:hi], dice_seed=1)
+        else:
+            eng.select_moves_host_async(h, bufs[0][lo:hi], {"chosen": bufs[1][lo:hi]})
     def advance(h):
         lo, hi = parts[h]
         h_ply[lo:hi] += 1
-        bgx_host.advance(ch[lo:hi], q[lo:hi], 1, h_ply[lo:hi], h_gid[lo:hi], h_win[lo:hi])
-        done = np.flatnonzero(h_win[lo:hi] >= 0)
+        if FUSED:
+            cur[h] ^= 1
+        else:
+            bgx_host.advance(bufs[1][lo:hi], bufs[0][lo:hi], 1, h_ply[lo:hi], h_gid[lo:hi], win[lo:hi])
+        out = bufs[cur[h]] if FUSED else bufs[0]
+        done = np.flatnonzero(win[lo:hi] >= 0)
         if done.size:
             idx = done + lo
             h_gid[idx] += G; h_ply[idx] = 0
             fresh = np.zeros((idx.size, 32), np.int8); fresh[:, :24] = START_BOARD; fresh[:, 28] = (h_gid[idx] & 1) ^ 1
-            q[idx] = bgx_host.advance(fresh, fresh, 1, h_ply[idx], h_gid[idx])
+            out[idx] = bgx_host.advance(fresh, fresh, 1, h_ply[idx], h_gid[idx])
     for h in range(lanes): submit(h)
     for it in range(-3, 60):
         if it == 0: t0 = time.perf_counter(); th = 0.0; tw = 0.0
@@ -46,4 +59,4 @@ for lanes in [int(x) for x in os.environ.get("LANES", "2,3,4").split(",")]:
             if it >= 0: th += b - a; tw += a - a0
     for h in range(lanes): eng.wait(h)
     dt = time.perf_counter() - t0
-    print(f"{lanes} lanes: {dt/60*1e3:.3f} ms per ply-step ({G*60/dt/1e6:.1f} M plies/s), host advance+submit {th/60*1e3:.3f} ms, waiting {tw/60*1e3:.3f} ms per step", flush=True)
+    print(f"{'fused' if FUSED else 'split'} {lanes} lanes: {dt/60*1e3:.3f} ms per ply-step ({G*60/dt/1e6:.1f} M plies/s), host advance+submit {th/60*1e3:.3f} ms, waiting {tw/60*1e3:.3f} ms per step", flush=True)
