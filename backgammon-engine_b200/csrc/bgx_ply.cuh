@@ -247,6 +247,7 @@ struct PlyWalk : Mover {
     int c_me;             // feature block of the mover inside a point's 8 features (0 or 4)
     int dieA, dieB;       // die of even / odd depths
     uint32_t root_only;   // restricts the root's origins (all ones: no restriction)
+    uint32_t twin_root;   // non-doubles, second pass: the root origins of the FIRST pass' first die (0 in the first pass)
     int4 zroot;
     // result
     float best_key;       // value, negated for PLAYER2 (who minimises): always maximised, strict > keeps the first
@@ -259,6 +260,7 @@ struct PlyWalk : Mover {
     {
         c_me = pl ? 4 : 0;
         root_only = kFull;
+        twin_root = 0;
         best_key = __int_as_float(0xff800000);          // -inf
         best_v = 0; best_path = 0;
         n_seq = n_scored = n_visited = 0;
@@ -310,14 +312,28 @@ struct PlyWalk : Mover {
         if (key > best_key) { best_key = key; best_v = v; best_path = path_and_len; }
     }
 
+    // Twins.  Two on-board moves of one turn commute: played in either order they remove the same two checkers, land on the
+    // same two points and hit the same blots (walls do not change during a turn, only bar entry and bearing off depend on the
+    // rest of the board).  So under a node reached by the on-board move o, the last move o' leads to the position that
+    // (.., o', o) leads to whenever o' was already playable BEFORE o: in a double when o' is a smaller origin of the parent
+    // node, in the second pass of a non-double when o' is a root origin of the first pass.  The reference visits that twin
+    // EARLIER (ascending origins; first pass first), it has the same value, and the strict first-index arg-best can never
+    // prefer the later copy: such leaves are counted, not walked.  `legal_par` = all origins of the parent node.
     template <int D, bool kDbl>
-    __device__ __forceinline__ void visit(int v, const int4 &zpar, int vpar, int o, int d, int dval, uint32_t path)
+    __device__ __forceinline__ void visit(int v, const int4 &zpar, int vpar, int o, int d, int dval, uint32_t path, uint32_t legal_par = 0)
     {
         constexpr int kMax = kDbl ? 4 : 2;
         uint32_t legal = 0;
         if constexpr (D < kMax) {
             legal = legal_here(v, (D & 1) ? dieB : dieA);
             if (D == 0) legal &= root_only;
+        }
+        uint32_t twins = 0;
+        if constexpr (D == kMax - 1 && D > 0) {
+            const int die = (D & 1) ? dieB : dieA;
+            twins = legal & (kDbl ? legal_par & ((1u << o) - 1u) : twin_root);
+            twins &= player ? ~((2u << die) - 1u) : (1u << (25 - die)) - 1u;      // the last move stays on the board ...
+            if (d == (player ? 0 : 25)) twins = 0;                               // ... and so did the one before it
         }
         if (legal == 0) {
             // a node without a move ends the sequence (game.cpp:117-121, 148-151); the root of a
@@ -331,8 +347,15 @@ struct PlyWalk : Mover {
                 const int below = cache.lookup(v, D, lane);
                 if (below >= 0) { n_seq += below; return; }
             }
-            const int4 z = D == 0 ? zroot : child_z(zpar, vpar, o, d, dval);
             const int entered = n_seq;
+            const uint32_t legal_all = legal;
+            n_seq += __popc(twins);                          // counted, not walked (the count below stays path-independent)
+            legal &= ~twins;
+            if (D == kMax - 1 && legal == 0) {               // every sequence below is an earlier one's twin
+                if constexpr (kDbl && D >= 2) cache.store(v, D, n_seq - entered, lane);
+                return;
+            }
+            const int4 z = D == 0 ? zroot : child_z(zpar, vpar, o, d, dval);
             const int die = (D & 1) ? dieB : dieA;
             do {
                 const int oc = lowest_bit(legal);
@@ -341,7 +364,7 @@ struct PlyWalk : Mover {
                 int dv;
                 const int child = apply(v, oc, dc, dv);
                 n_visited++;
-                visit<D + 1, kDbl>(child, z, v, oc, dc, dv, path | ((uint32_t)oc << (5 * D)));
+                visit<D + 1, kDbl>(child, z, v, oc, dc, dv, path | ((uint32_t)oc << (5 * D)), legal_all);
             } while (legal);
             if constexpr (kDbl && D >= 2) cache.store(v, D, n_seq - entered, lane);
         }
@@ -487,7 +510,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
         for (int pass = 0; pass < 2; pass++) {          // game.cpp:143-188: d1 first, then d2 first
             w.dieA = pass ? d2 : d1;
             w.dieB = pass ? d1 : d2;
-            if (pass) key1 = w.best_key;
+            if (pass) { key1 = w.best_key; w.twin_root = w.legal_here(root, d1); }
             w.template visit<0, false>(root, w.zroot, root, 0, 0, 0, 0u);
         }
         best_pass = w.best_key > key1 ? 1u : 0u;
