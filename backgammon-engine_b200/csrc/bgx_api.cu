@@ -65,7 +65,7 @@ struct bgx_engine {
                                              // batches are resident at once (0: one per SM; BGX_SELECT_LANE_GRID)
     long long select_order_max = 1 << 21;    // launches up to this many queries get a sorted queue (BGX_SELECT_ORDER_MAX; 64 B of scratch per query)
     int select_urgent_min = 7, select_giant_min = kGiantMinChildren, select_urgent_from_pct = 0;   // k_select help policy (BGX_SELECT_*)
-    int selfplay_warps = 24, select_warps = 20;   // warps per CTA of k_selfplay / k_select (measured best; BGX_*_WARPS override)
+    int selfplay_warps = 24, select_warps = 24;   // warps per CTA of k_selfplay / k_select (measured best; BGX_*_WARPS override)
     // bookkeeping
     long long launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;

@@ -248,6 +248,8 @@ struct PlyWalk : Mover {
     int dieA, dieB;       // die of even / odd depths
     uint32_t root_only;   // restricts the root's origins (all ones: no restriction)
     uint32_t twin_root;   // non-doubles, second pass: the root origins of the FIRST pass' first die (0 in the first pass)
+    bool nd;              // a pass of a NON-double: walked by the last two levels (2, 3 -> leaves at 4) of the one walk there is,
+                          // so that the kernel carries one copy of the per-depth code instead of two (instruction cache)
     int4 zroot;
     // result
     float best_key;       // value, negated for PLAYER2 (who minimises): always maximised, strict > keeps the first
@@ -261,6 +263,7 @@ struct PlyWalk : Mover {
         c_me = pl ? 4 : 0;
         root_only = kFull;
         twin_root = 0;
+        nd = false;
         best_key = __int_as_float(0xff800000);          // -inf
         best_v = 0; best_path = 0;
         n_seq = n_scored = n_visited = 0;
@@ -319,19 +322,20 @@ struct PlyWalk : Mover {
     // node, in the second pass of a non-double when o' is a root origin of the first pass.  The reference visits that twin
     // EARLIER (ascending origins; first pass first), it has the same value, and the strict first-index arg-best can never
     // prefer the later copy: such leaves are counted, not walked.  `legal_par` = all origins of the parent node.
-    template <int D, bool kDbl>
+    template <int D>
     __device__ __forceinline__ void visit(int v, const int4 &zpar, int vpar, int o, int d, int dval, uint32_t path, uint32_t legal_par = 0)
     {
-        constexpr int kMax = kDbl ? 4 : 2;
+        constexpr int kMax = 4;
         uint32_t legal = 0;
         if constexpr (D < kMax) {
-            legal = legal_here(v, (D & 1) ? dieB : dieA);
+            if (D == 1 && nd) legal = 1u;                    // a non-double pass enters at level 2: level 1 hands the root through
+            else legal = legal_here(v, (D & 1) ? dieB : dieA);
             if (D == 0) legal &= root_only;
         }
         uint32_t twins = 0;
-        if constexpr (D == kMax - 1 && D > 0) {
+        if constexpr (D == kMax - 1) {
             const int die = (D & 1) ? dieB : dieA;
-            twins = legal & (kDbl ? legal_par & ((1u << o) - 1u) : twin_root);
+            twins = legal & (nd ? twin_root : legal_par & ((1u << o) - 1u));
             twins &= player ? ~((2u << die) - 1u) : (1u << (25 - die)) - 1u;      // the last move stays on the board ...
             if (d == (player ? 0 : 25)) twins = 0;                               // ... and so did the one before it
         }
@@ -339,34 +343,36 @@ struct PlyWalk : Mover {
             // a node without a move ends the sequence (game.cpp:117-121, 148-151); the root of a
             // non-double pass emits nothing
             if constexpr (D == kMax) leaf<D>(v, zpar, vpar, o, d, dval, path);
-            else if (kDbl || D > 0) early_leaf(v, path | ((uint32_t)D << 20));
+            else if (!(D == 2 && nd)) early_leaf(v, path | ((uint32_t)D << 20));
             return;
         }
         if constexpr (D < kMax) {
-            if constexpr (kDbl && D >= 2) {                  // same position, same dice left: seen before?
-                const int below = cache.lookup(v, D, lane);
-                if (below >= 0) { n_seq += below; return; }
+            if constexpr (D >= 2) {                          // doubles: same position, same dice left: seen before?
+                if (!nd) {
+                    const int below = cache.lookup(v, D, lane);
+                    if (below >= 0) { n_seq += below; return; }
+                }
             }
             const int entered = n_seq;
             const uint32_t legal_all = legal;
             n_seq += __popc(twins);                          // counted, not walked (the count below stays path-independent)
             legal &= ~twins;
             if (D == kMax - 1 && legal == 0) {               // every sequence below is an earlier one's twin
-                if constexpr (kDbl && D >= 2) cache.store(v, D, n_seq - entered, lane);
+                if constexpr (D >= 2) { if (!nd) cache.store(v, D, n_seq - entered, lane); }
                 return;
             }
-            const int4 z = D == 0 ? zroot : child_z(zpar, vpar, o, d, dval);
+            int4 z = zroot;                                  // the root of the turn: of a double at depth 0, of a non-double pass at 2
+            if (D != 0 && !(D <= 2 && nd)) z = child_z(zpar, vpar, o, d, dval);
             const int die = (D & 1) ? dieB : dieA;
             do {
                 const int oc = lowest_bit(legal);
                 legal &= legal - 1;
                 const int dc = destination(player, oc, die);
-                int dv;
-                const int child = apply(v, oc, dc, dv);
-                n_visited++;
-                visit<D + 1, kDbl>(child, z, v, oc, dc, dv, path | ((uint32_t)oc << (5 * D)), legal_all);
+                int dv = 0, child = v;
+                if (!(D == 1 && nd)) { child = apply(v, oc, dc, dv); n_visited++; }
+                visit<D + 1>(child, z, v, oc, dc, dv, path | ((uint32_t)oc << (5 * D)), legal_all);
             } while (legal);
-            if constexpr (kDbl && D >= 2) cache.store(v, D, n_seq - entered, lane);
+            if constexpr (D >= 2) { if (!nd) cache.store(v, D, n_seq - entered, lane); }
         }
     }
 };
@@ -457,9 +463,16 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
     w.zroot = ev.preactivation(root, lane, player);
     uint32_t best_pass = 0;
     bool shared = false;
-    if (d1 == d2) {
-        w.dieA = w.dieB = d1;
-        uint32_t legal = w.legal_here(root, d1) & root_only;
+    // One loop, ONE call site of the walk (every call site would be another inlined copy of all its levels): a double
+    // iterates over its root origins (its own, or the ones its helpers leave it), a non-double over its two passes.
+    const bool dbl = d1 == d2;
+    uint32_t legal = 0;
+    float key1 = 0.f;
+    int pass = 0;
+    w.dieA = d1; w.dieB = d2;
+    w.nd = !dbl;
+    if (dbl) {
+        legal = w.legal_here(root, d1) & root_only;
         if (legal == 0) {
             w.early_leaf(root, 0u);                                      // no move at all: the empty sequence
         } else {
@@ -478,42 +491,46 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
                         atomicOr(share->urgent, share->my_bit);
                 }
             }
-            for (;;) {
-                uint32_t bit = 0;
-                if (shared) {                                            // pop the lowest origin still there
-                    if (lane == 0) {
-                        for (;;) {
-                            const uint32_t old = *(volatile uint32_t *)&slot->legal0;
-                            if (old == 0) break;
-                            const uint32_t low = old & (0u - old);
-                            if (atomicAnd(&slot->legal0, ~low) & low) { bit = low; break; }
-                        }
-                    }
-                    bit = __shfl_sync(kFull, bit, 0);
-                } else {
-                    bit = legal & (0u - legal);
-                    legal &= legal - 1;
-                }
-                if (bit == 0) break;
-                const int oc = lowest_bit(bit);
-                const int dc = destination(player, oc, d1);
-                int dv;
-                const int child = w.apply(root, oc, dc, dv);
-                w.n_visited++;
-                w.template visit<1, true>(child, w.zroot, root, oc, dc, dv, (uint32_t)oc);
-            }
-            if (shared && lane == 0) atomicAnd(share->urgent, ~share->my_bit);
         }
-    } else {
-        float key1 = 0.f;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; pass++) {          // game.cpp:143-188: d1 first, then d2 first
+    }
+    for (;;) {
+        int child = root, oc = 0, dc = 0, dv = 0;
+        if (dbl) {
+            uint32_t bit = 0;
+            if (shared) {                                                // pop the lowest origin still there
+                if (lane == 0) {
+                    for (;;) {
+                        const uint32_t old = *(volatile uint32_t *)&slot->legal0;
+                        if (old == 0) break;
+                        const uint32_t low = old & (0u - old);
+                        if (atomicAnd(&slot->legal0, ~low) & low) { bit = low; break; }
+                    }
+                }
+                bit = __shfl_sync(kFull, bit, 0);
+            } else {
+                bit = legal & (0u - legal);
+                legal &= legal - 1;
+            }
+            if (bit == 0) break;
+            oc = lowest_bit(bit);
+            dc = destination(player, oc, d1);
+            child = w.apply(root, oc, dc, dv);
+            w.n_visited++;
+        } else {                                                         // game.cpp:143-188: d1 first, then d2 first
+            if (pass == 2) break;
             w.dieA = pass ? d2 : d1;
             w.dieB = pass ? d1 : d2;
             if (pass) { key1 = w.best_key; w.twin_root = w.legal_here(root, d1); }
-            w.template visit<0, false>(root, w.zroot, root, 0, 0, 0, 0u);
+            pass++;
         }
+        w.template visit<1>(child, w.zroot, root, oc, dc, dv, (uint32_t)oc);
+    }
+    if (dbl) {
+        if (shared && lane == 0) atomicAnd(share->urgent, ~share->my_bit);
+    } else {
         best_pass = w.best_key > key1 ? 1u : 0u;
+        // levels 2, 3 wrote the origins at bits 10.. and counted the two levels above into the length
+        w.best_path = ((w.best_path & 0xFFFFFu) >> 10) | (((w.best_path >> 20) - 2u) << 20);
     }
     Choice best = finish_choice(w.best_path, w.best_key, w.best_v, w.n_seq, w.n_scored, w.n_visited, root, player, d1, d2, best_pass);
     if (shared) {
