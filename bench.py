@@ -415,7 +415,8 @@ def run_ours(args):
               "truncated": int(cnt[3]), "play_ms": ms[0], "td_replay_ms": ms[1], "allreduce_apply_ms": ms[2], "round_ms": ms[3],
               "plies_per_sec_incl_update": cnt[0] / (ms[3] * 1e-3), "td_steps_per_sec": cnt[1] / (ms[1] * 1e-3),
               "note": "one round: every game played to its end from one snapshot (k_selfplay), exact online TD(lambda) replay "
-                      "per game (k_td_replay), NCCL all-reduce of fp32[25604], apply"}
+                      "per game (k_td_replay), NCCL all-reduce of fp32[25604], apply; allreduce_apply_ms includes waiting for the "
+                      "slowest rank's replay (max over ranks)"}
 
     if rank == 0:
         peaks, peak_src = peak_json()

@@ -59,7 +59,7 @@ orders = {
     "kids_desc": np.argsort(-kids, kind="stable"),
 }
 eng.close()
-policies = [(8, 10, 0), (7, 10, 0), (6, 10, 0)]
+policies = [(8, 10, 0), (7, 10, 0), (6, 10, 0), (5, 10, 0), (7, 8, 0)]
 for n in (G, G // 2):
     for (umin, gmin, pct) in policies:
         os.environ.update(BGX_SELECT_URGENT_MIN=str(umin), BGX_SELECT_GIANT_MIN=str(gmin), BGX_SELECT_URGENT_FROM_PCT=str(pct))
