@@ -476,3 +476,66 @@ long orc_greedy_ply(const float *W1, const float *b1, const float *w2, const flo
     free(X); free(V); free(st);
     return best;
 }
+
+/* orc_greedy_ply over a batch of 32-byte records on `threads` POSIX threads, returning also the first-index sequence
+ * itself (model.py:212-220): lets the GPU tests compare choice, value, N AND the reported moves on 10^5 positions. */
+typedef struct {
+    const float *W1, *b1, *w2, *b2;
+    const int8_t *rec; long lo, hi;
+    int8_t *after, *moves, *len; float *value; int64_t *n_seq;
+} greedy_job;
+
+static void *greedy_worker(void *arg)
+{
+    greedy_job *j = (greedy_job *)arg;
+    long cap = 16384;
+    int32_t *st = malloc((size_t)cap * 28 * 4);
+    int8_t *mv = malloc((size_t)cap * 8), *ln = malloc((size_t)cap);
+    float *X = malloc((size_t)cap * ORC_FEATS * sizeof(float)), *V = malloc((size_t)cap * sizeof(float));
+    for (long i = j->lo; i < j->hi; i++) {
+        const int8_t *r = j->rec + 32 * i;
+        int32_t s[28];
+        for (int k = 0; k < 28; k++) s[k] = r[k];
+        const int player = r[28];
+        long n = orc_turn_sequences(s, player, r[29], r[30], cap, mv, ln, st);
+        if (n < 0) {                                   /* more than cap sequences: grow and redo */
+            cap = -n;
+            free(st); free(mv); free(ln); free(X); free(V);
+            st = malloc((size_t)cap * 28 * 4); mv = malloc((size_t)cap * 8); ln = malloc((size_t)cap);
+            X = malloc((size_t)cap * ORC_FEATS * sizeof(float)); V = malloc((size_t)cap * sizeof(float));
+            n = orc_turn_sequences(s, player, r[29], r[30], cap, mv, ln, st);
+        }
+        j->n_seq[i] = n;
+        j->len[i] = 0; j->value[i] = 0.f;
+        memset(j->moves + 8 * i, 0, 8);
+        for (int k = 0; k < 28; k++) j->after[28 * i + k] = (int8_t)s[k];
+        if (n <= 0) continue;
+        orc_encode(st, n, player, X);
+        orc_forward(j->W1, j->b1, j->w2, j->b2, X, n, V, NULL);
+        long best = 0;
+        for (long k = 1; k < n; k++)
+            if (player == 0 ? V[k] > V[best] : V[k] < V[best]) best = k;
+        for (int k = 0; k < 28; k++) j->after[28 * i + k] = (int8_t)st[28 * best + k];
+        memcpy(j->moves + 8 * i, mv + 8 * best, 8);
+        j->len[i] = ln[best];
+        j->value[i] = V[best];
+    }
+    free(st); free(mv); free(ln); free(X); free(V);
+    return NULL;
+}
+
+void orc_greedy_batch(const float *W1, const float *b1, const float *w2, const float *b2,
+                      const int8_t *records, long n, int threads,
+                      int8_t *after, float *value, int64_t *n_seq, int8_t *moves, int8_t *len)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t tid[256];
+    greedy_job job[256];
+    for (int t = 0; t < threads; t++) {
+        greedy_job g = {W1, b1, w2, b2, records, n * t / threads, n * (t + 1) / threads, after, moves, len, value, n_seq};
+        job[t] = g;
+        pthread_create(&tid[t], NULL, greedy_worker, &job[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(tid[t], NULL);
+}

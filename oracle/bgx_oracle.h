@@ -93,6 +93,11 @@ long orc_greedy_ply(const float *W1, const float *b1, const float *w2, const flo
                     const int32_t *s, int player, int d1, int d2,
                     int32_t *out, float *v_best, int64_t *n_seq);
 
+/* the same over n 32-byte records on `threads` threads; moves[n][4][2] / len[n] = the chosen (first-index) sequence */
+void orc_greedy_batch(const float *W1, const float *b1, const float *w2, const float *b2,
+                      const int8_t *records, long n, int threads,
+                      int8_t *after /*[n][28]*/, float *value, int64_t *n_seq, int8_t *moves, int8_t *len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,9 @@ class Oracle(_SeqAPI):
                                              np.ctypeslib.ndpointer(np.int64, flags="C"),
                                              np.ctypeslib.ndpointer(np.uint64, flags="C")]
         L.orc_turn_summary_batch.restype = None
+        L.orc_greedy_batch.argtypes = [_f32p, _f32p, _f32p, _f32p, _i8p, C.c_long, C.c_int, _i8p, _f32p,
+                                       np.ctypeslib.ndpointer(np.int64, flags="C"), _i8p, _i8p]
+        L.orc_greedy_batch.restype = None
         L.orc_encode.argtypes = [_i32p, C.c_long, C.c_int, _f32p]
         L.orc_encode.restype = None
         L.orc_forward.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_long, _f32p, C.c_void_p]
@@ -183,6 +186,18 @@ class Oracle(_SeqAPI):
         idx = self.lib.orc_greedy_ply(*self._w(weights), _state(s), int(player), int(d1), int(d2),
                                       out, C.byref(v), C.byref(n))
         return idx, out, v.value, n.value
+
+
+    def greedy_batch(self, weights, records, threads=None):
+        """-> dict(after int8[n,28], value f32[n], n_seq int64[n], moves int8[n,4,2], moves_len int8[n])"""
+        r = np.ascontiguousarray(records, dtype=np.int8).reshape(-1, 32)
+        n = r.shape[0]
+        out = {"after": np.zeros((n, 28), np.int8), "value": np.zeros(n, np.float32), "n_seq": np.zeros(n, np.int64),
+               "moves": np.zeros((n, 4, 2), np.int8), "moves_len": np.zeros(n, np.int8)}
+        if n:
+            self.lib.orc_greedy_batch(*self._w(weights), r.reshape(-1), n, int(threads or os.cpu_count() or 1),
+                                      out["after"].reshape(-1), out["value"], out["n_seq"], out["moves"].reshape(-1), out["moves_len"])
+        return out
 
 
 class RefHarness(_SeqAPI):
