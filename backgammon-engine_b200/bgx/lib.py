@@ -77,6 +77,7 @@ _SIGNATURES = {
     # section 5
     "bgx_td_replay": (C.c_int, [_vp, C.c_float, C.c_float, _vp, C.POINTER(Stats)]),
     "bgx_apply_delta": (C.c_int, [_vp, _vp, C.c_float]),
+    "bgx_td_round_host": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, _vp, C.POINTER(Stats)]),
     "bgx_td_replay_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     # section 6
     "bgx_launch_count": (C.c_int, [_vp, C.POINTER(_i64)]),

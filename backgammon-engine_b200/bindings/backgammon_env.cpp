@@ -291,8 +291,109 @@ class BatchEngine {
         return V;
     }
 
+    py::tuple get_weights()
+    {
+        py::array_t<float> W1({128, 198}), b1(128), w2({1, 128}), b2(1);
+        Game::check(bgx_get_weights(e_, W1.mutable_data(), b1.mutable_data(), w2.mutable_data(), b2.mutable_data()));
+        return py::make_tuple(W1, b1, w2, b2);
+    }
+    // batched evaluateTurnSequences (backgammon_bindings.cpp:27-39 for n positions): offsets[n+1], moves[N,4,2], lens[N], states[N,32]
+    py::tuple evaluate_turn_sequences(I8 q)
+    {
+        int64_t n = rows(q);
+        py::array_t<int32_t> n_seq(n), n_unique(n);
+        py::array_t<uint64_t> digest(n);
+        Game::check(bgx_enumerate_summary_host(e_, q.data(), n, n_seq.mutable_data(), n_unique.mutable_data(), digest.mutable_data()));
+        int64_t total = 0;
+        for (int64_t i = 0; i < n; i++) total += n_seq.data()[i];
+        py::array_t<int64_t> offsets(n + 1);
+        py::array_t<int8_t> moves({(py::ssize_t)total, (py::ssize_t)4, (py::ssize_t)2}), lens(total), states({(py::ssize_t)total, (py::ssize_t)32});
+        {
+            py::gil_scoped_release nogil;
+            int64_t got = 0;
+            Game::check(bgx_enumerate_host(e_, q.data(), n, total > 0 ? total : 1, offsets.mutable_data(), moves.mutable_data(), lens.mutable_data(),
+                                           states.mutable_data(), &got));
+        }
+        return py::make_tuple(offsets, moves, lens, states);
+    }
+    // one iteration of play_game's loop for n games (train.py:103-121): (next_records[n,32], winner[n], value[n], n_seq[n])
+    py::tuple play_ply(I8 q, py::array_t<int32_t, py::array::c_style | py::array::forcecast> next_ply,
+                       py::array_t<int64_t, py::array::c_style | py::array::forcecast> game_id, float epsilon, uint64_t explore_seed, uint64_t dice_seed)
+    {
+        int64_t n = rows(q);
+        if (next_ply.size() != n || game_id.size() != n) throw std::invalid_argument("next_ply and game_id are [n]");
+        py::array_t<int8_t> next({(py::ssize_t)n, (py::ssize_t)32}), winner(n);
+        py::array_t<float> value(n);
+        py::array_t<int32_t> n_seq(n);
+        {
+            py::gil_scoped_release nogil;
+            Game::check(bgx_play_ply_host_async(e_, 0, q.data(), next_ply.data(), game_id.data(), n, epsilon, explore_seed, dice_seed,
+                                                next.mutable_data(), winner.mutable_data(), value.mutable_data(), n_seq.mutable_data()));
+            Game::check(bgx_lane_wait(e_, 0));
+        }
+        return py::make_tuple(next, winner, value, n_seq);
+    }
+    // ---- the self-play population and the TD(lambda) round (train.py:64-172, 527-547)
+    static py::dict stats_dict(const bgx_stats &s)
+    {
+        py::dict d;
+        d["plies"] = s.plies; d["sequences"] = s.sequences; d["scored"] = s.scored; d["games_finished"] = s.games_finished;
+        d["p1_wins"] = s.p1_wins; d["truncated"] = s.truncated; d["td_steps"] = s.td_steps; d["td_sq_error"] = s.td_sq_error;
+        d["tree_edges"] = s.tree_edges;
+        return d;
+    }
+    void selfplay_init(int64_t n_slots, int64_t first_id, int64_t id_stride, uint64_t seed, int first_mover, int traj_cap, bool record_chosen)
+    {
+        n_slots_ = n_slots; traj_cap_ = traj_cap; record_chosen_ = record_chosen;
+        Game::check(bgx_selfplay_record_chosen(e_, record_chosen ? 1 : 0));
+        Game::check(bgx_selfplay_init(e_, n_slots, first_id, id_stride > 0 ? id_stride : n_slots, seed, first_mover, traj_cap));
+    }
+    py::dict selfplay_step(int n_plies, float epsilon)
+    {
+        bgx_stats s;
+        { py::gil_scoped_release nogil; Game::check(bgx_selfplay_step(e_, n_plies, epsilon, &s)); }
+        return stats_dict(s);
+    }
+    py::dict selfplay_round(float epsilon)
+    {
+        bgx_stats s;
+        { py::gil_scoped_release nogil; Game::check(bgx_selfplay_round(e_, epsilon, &s)); }
+        return stats_dict(s);
+    }
+    void selfplay_next_round() { Game::check(bgx_selfplay_next_round(e_)); }
+    py::tuple selfplay_read()
+    {
+        py::array_t<int8_t> rec({(py::ssize_t)n_slots_, (py::ssize_t)32});
+        py::array_t<int32_t> ply(n_slots_);
+        py::array_t<int64_t> gid(n_slots_);
+        Game::check(bgx_selfplay_read(e_, rec.mutable_data(), ply.mutable_data(), gid.mutable_data()));
+        return py::make_tuple(rec, ply, gid);
+    }
+    py::tuple export_trajectory(int64_t slot)
+    {
+        const int cap = traj_cap_ > 0 ? traj_cap_ : 1;
+        std::vector<int8_t> pre((size_t)cap * 32), cho(record_chosen_ ? (size_t)cap * 32 : 0);
+        int32_t T = 0;
+        Game::check(bgx_export_trajectory(e_, slot, cap, pre.data(), record_chosen_ ? cho.data() : nullptr, &T));
+        py::array_t<int8_t> p({(py::ssize_t)T, (py::ssize_t)32}), c({(py::ssize_t)(record_chosen_ ? T : 0), (py::ssize_t)32});
+        std::memcpy(p.mutable_data(), pre.data(), (size_t)T * 32);
+        if (record_chosen_) std::memcpy(c.mutable_data(), cho.data(), (size_t)T * 32);
+        return py::make_tuple(p, c);
+    }
+    // exact online TD(lambda) replay of every finished game from the current weights, summed; weights += scale * delta
+    py::tuple td_round(float lr, float lambda, float scale)
+    {
+        bgx_stats s;
+        py::array_t<float> delta(BGX_NPARAMS);
+        { py::gil_scoped_release nogil; Game::check(bgx_td_round_host(e_, lr, lambda, scale, delta.mutable_data(), &s)); }
+        return py::make_tuple(delta, stats_dict(s));
+    }
+
   private:
     bgx_engine *e_ = nullptr;
+    int64_t n_slots_ = 0;
+    int traj_cap_ = 0;
+    bool record_chosen_ = false;
 };
 
 PYBIND11_MODULE(backgammon_env, m)
@@ -340,5 +441,17 @@ PYBIND11_MODULE(backgammon_env, m)
         .def("evaluate_turn_sequences_summary", &BatchEngine::evaluate_turn_sequences_summary)
         .def("make_moves", &BatchEngine::make_moves, py::arg("queries"), py::arg("epsilon") = 0.0f, py::arg("seed") = 0)
         .def("encode", &BatchEngine::encode)
-        .def("evaluate", &BatchEngine::evaluate);
+        .def("evaluate", &BatchEngine::evaluate)
+        .def("get_weights", &BatchEngine::get_weights)
+        .def("evaluate_turn_sequences", &BatchEngine::evaluate_turn_sequences)
+        .def("play_ply", &BatchEngine::play_ply, py::arg("records"), py::arg("next_ply"), py::arg("game_id"), py::arg("epsilon") = 0.0f,
+             py::arg("explore_seed") = 0, py::arg("dice_seed") = 0x5EED2026ull)
+        .def("selfplay_init", &BatchEngine::selfplay_init, py::arg("n_slots"), py::arg("first_id") = 0, py::arg("id_stride") = 0,
+             py::arg("seed") = 0x5EED2026ull, py::arg("first_mover") = BGX_FIRST_ROLLOFF, py::arg("traj_cap") = 0, py::arg("record_chosen") = false)
+        .def("selfplay_step", &BatchEngine::selfplay_step, py::arg("n_plies"), py::arg("epsilon") = 0.0f)
+        .def("selfplay_round", &BatchEngine::selfplay_round, py::arg("epsilon") = 0.0f)
+        .def("selfplay_next_round", &BatchEngine::selfplay_next_round)
+        .def("selfplay_read", &BatchEngine::selfplay_read)
+        .def("export_trajectory", &BatchEngine::export_trajectory)
+        .def("td_round", &BatchEngine::td_round, py::arg("lr"), py::arg("lambda_decay"), py::arg("scale"));
 }

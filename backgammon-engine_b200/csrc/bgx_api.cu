@@ -60,6 +60,7 @@ struct bgx_engine {
     long long *game_id = nullptr;
     // TD
     float *td_partial = nullptr;             // [td_grid][25604] per-CTA delta accumulators
+    float *td_delta = nullptr;               // [25604] summed delta of bgx_td_round_host
     int td_grid = 0;
     int lane_grid = -1;                      // CTAs of a k_select launch on an asynchronous lane: half the SMs, so that two lanes'
                                              // batches are resident at once (0: one per SM; BGX_SELECT_LANE_GRID)
@@ -205,7 +206,7 @@ int bgx_destroy(bgx_engine *e)
     for (int i = 0; i < bgx_engine::kScratch; i++) cudaFree(e->dbuf[i]);
     cudaFree(e->flat); cudaFree(e->wt); cudaFree(e->fixed); cudaFree(e->aux); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats); cudaFree(e->steal);
     cudaFree(e->uniq_tables); cudaFree(e->uniq_gens); cudaFree(e->slots); cudaFree(e->traj_pre); cudaFree(e->traj_chosen);
-    cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial);
+    cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial); cudaFree(e->td_delta);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_sync);
     for (bgx_lane &l : e->lanes) {
         if (l.stream) cudaStreamDestroy(l.stream);
@@ -831,6 +832,7 @@ static int ensure_td(bgx_engine *e)
     if (e->td_partial) return BGX_OK;
     e->td_grid = e->sm_count;
     CU(cudaMalloc(&e->td_partial, (size_t)e->td_grid * BGX_NPARAMS_PADDED * sizeof(float)));
+    CU(cudaMalloc(&e->td_delta, (size_t)BGX_NPARAMS_PADDED * sizeof(float)));
     return BGX_OK;
 }
 
@@ -891,6 +893,21 @@ int bgx_apply_delta(bgx_engine *e, const float *delta_dev, float scale)
     e->launches++;
     CU(cudaGetLastError());
     return rebuild_table(e);
+}
+
+// bgx_td_replay + bgx_apply_delta for a single-GPU caller without device buffers of its own (the pybind11 module)
+int bgx_td_round_host(bgx_engine *e, float lr, float lambda, float scale, float *delta_host, bgx_stats *out)
+{
+    USE(e);
+    int rc = ensure_td(e);
+    if (rc) return rc;
+    float *dd = e->td_delta;
+    if ((rc = bgx_td_replay(e, lr, lambda, dd, out))) return rc;
+    if (delta_host) {
+        CU(cudaMemcpyAsync(delta_host, dd, (size_t)BGX_NPARAMS * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    return scale != 0.f ? bgx_apply_delta(e, dd, scale) : BGX_OK;
 }
 
 int bgx_td_replay_host(bgx_engine *e, const int8_t *records, int32_t T, int player1_won, float lr, float lambda,

@@ -263,6 +263,9 @@ int bgx_export_trajectory(bgx_engine *e, int64_t slot, int32_t cap, int8_t *pre,
 int bgx_td_replay(bgx_engine *e, float lr, float lambda, float *delta_dev, bgx_stats *out);
 /* weights += scale * delta   (after the caller's allreduce over ranks) */
 int bgx_apply_delta(bgx_engine *e, const float *delta_dev, float scale);
+/* both in one call for a single-GPU caller: delta_host[BGX_NPARAMS] (may be NULL) receives the summed weight
+ * change, then weights += scale * delta (scale 0: weights untouched).  One round of train.py:527-547. */
+int bgx_td_round_host(bgx_engine *e, float lr, float lambda, float scale, float *delta_host, bgx_stats *out);
 /* one external trajectory (host buffers): records[T][32] with byte 28 = the turn flag of each
  * pre-move state; new_* receive the weights after the replay; sq_errors[T-1] may be NULL */
 int bgx_td_replay_host(bgx_engine *e, const int8_t *records, int32_t T, int player1_won,
