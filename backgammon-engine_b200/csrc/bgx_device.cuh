@@ -27,7 +27,7 @@ constexpr int kFixedInts = kFixedRows * kHidden;                  // 29 568
 constexpr int kFixedBytes = kFixedInts * 4;                       // 118 272
 constexpr int kRowB1 = kFeatures + 30;                            // round(b1 S)
 constexpr int kRowW2 = kFeatures + 31;                            // w2 (fp32 bit patterns)
-constexpr int kRowConst = kFeatures + 32;                         // every float4: {S, 1/S, b2, 0}
+constexpr int kRowConst = kFeatures + 32;                         // every float4: {S, -log2(e)/S, b2, Y}
 
 // status byte (record byte 31) of a self-play slot
 enum { kRunning = 0, kP1Won = 1, kP2Won = 2, kTruncated = 3 };

@@ -61,16 +61,26 @@ __global__ void k_fixed_scale(const float *__restrict__ flat, float *__restrict_
         bound += worst;
     }
     bound += fmaxf(fabsf(w[192]), fabsf(w[193])) + 7.5f * (fabsf(w[194]) + fabsf(w[195])) + fabsf(w[196]) + fabsf(w[197]);
-    for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(kFull, bound, o));
-    if ((j & 31) == 0) red[j >> 5] = bound;
+    // the output sum y = w2 . h (|y| <= sum |w2_j|, h in (0, 1)) is reduced over the warp as an INTEGER too (one REDUX.SUM,
+    // order-independent like z): scale Y = the largest power of two with sum_j |w2_j| * Y <= 2^30
+    float w2sum = fabsf(flat[kTableFloats + kHidden + j]);
+    for (int o = 16; o > 0; o >>= 1) {
+        bound = fmaxf(bound, __shfl_xor_sync(kFull, bound, o));
+        w2sum += __shfl_xor_sync(kFull, w2sum, o);
+    }
+    __shared__ float red2[kHidden / 32];
+    if ((j & 31) == 0) { red[j >> 5] = bound; red2[j >> 5] = w2sum; }
     __syncthreads();
     if (j == 0) {
-        for (int k = 1; k < kHidden / 32; k++) bound = fmaxf(bound, red[k]);
+        for (int k = 1; k < kHidden / 32; k++) { bound = fmaxf(bound, red[k]); w2sum += red2[k]; }
         int e = 30 - (ilogbf(fmaxf(bound, 1e-30f)) + 1);      // bound < 2^(ilogb+1)  =>  bound * 2^e < 2^30
         e = e > 60 ? 60 : (e < -60 ? -60 : e);
         aux[0] = ldexpf(1.f, e);
         aux[1] = ldexpf(1.f, -e);
         aux[2] = bound;
+        int ey = 30 - (ilogbf(fmaxf(w2sum, 1e-30f)) + 1);
+        ey = ey > 40 ? 40 : (ey < -60 ? -60 : ey);
+        aux[3] = ldexpf(1.f, ey);
     }
 }
 
@@ -94,7 +104,7 @@ __global__ void k_build_fixed(const float *__restrict__ flat, const float *__res
     } else if (f == kRowW2) {
         Ti[idx] = __float_as_int(flat[kTableFloats + kHidden + j]);
     } else {                                       // constants, the same float4 for every lane
-        const float c[4] = {S, aux[1], flat[kTableFloats + 2 * kHidden], 0.f};
+        const float c[4] = {S, -1.4426950408889634f * aux[1], flat[kTableFloats + 2 * kHidden], aux[3]};
         Ti[idx] = __float_as_int(c[j & 3]);
     }
 }

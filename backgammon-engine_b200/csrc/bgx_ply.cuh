@@ -48,6 +48,15 @@ __device__ __forceinline__ float fast_sigmoid(float z)
     return r;
 }
 
+// the same with the 2^x argument already formed: 1 / (1 + 2^a)
+__device__ __forceinline__ float sigmoid_exp2(float a)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+
 // off/15.0 for off = 0..16 (model.py:143-144: float64 divide, stored as float32); [16] pads the k+1 read
 __device__ __constant__ float kOffFeature[17] = {
     (float)(0 / 15.0), (float)(1 / 15.0), (float)(2 / 15.0), (float)(3 / 15.0), (float)(4 / 15.0), (float)(5 / 15.0),
@@ -113,16 +122,18 @@ struct PlyEvaluator {
         if (off2) add(z, off_term(off2, 1, lane));
         return z;
     }
+    // hidden layer -> output.  The sigmoid's 2^x argument is z * (-log2(e) / S) in ONE multiply; the 32 lane sums of w2 . h are
+    // added as integers at scale Y (one REDUX.SUM instead of five shuffle + add rounds; order-independent, so V stays a pure
+    // function of the position).  Resolution 2^-30 of sum |w2|: ~1e-7 of V in the worst case.
     __device__ __forceinline__ float finish(const int4 &zi, int lane) const
     {
         const int4 wi = T4[kRowW2 * 32 + lane], ci = T4[kRowConst * 32 + lane];
-        const float inv_scale = __int_as_float(ci.y), b2 = __int_as_float(ci.z);
-        const float zx = (float)zi.x * inv_scale, zy = (float)zi.y * inv_scale, zz = (float)zi.z * inv_scale, zw = (float)zi.w * inv_scale;
-        float y = __int_as_float(wi.x) * fast_sigmoid(zx) + __int_as_float(wi.y) * fast_sigmoid(zy) +
-                  __int_as_float(wi.z) * fast_sigmoid(zz) + __int_as_float(wi.w) * fast_sigmoid(zw);
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) y += __shfl_xor_sync(kFull, y, s);
-        return fast_sigmoid(y + b2);
+        const float c = __int_as_float(ci.y), b2 = __int_as_float(ci.z), Y = __int_as_float(ci.w);
+        const float y = __int_as_float(wi.x) * sigmoid_exp2((float)zi.x * c) + __int_as_float(wi.y) * sigmoid_exp2((float)zi.y * c) +
+                        __int_as_float(wi.z) * sigmoid_exp2((float)zi.z * c) + __int_as_float(wi.w) * sigmoid_exp2((float)zi.w * c);
+        const int total = __reduce_add_sync(kFull, __float2int_rn(y * Y));
+        const float inv_y = __int_as_float(0x7F000000 - ci.w);                    // Y is a power of two
+        return fast_sigmoid(fmaf((float)total, inv_y, b2));
     }
 };
 
