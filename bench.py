@@ -437,6 +437,8 @@ def run_ours(args):
                 "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world),
                 "sequences_per_sec": seqs_all / total_s, "afterstates_scored_per_sec": scored_all / total_s,
+                "legal_afterstates_per_sec": seqs_all / total_s,     # BASELINE.json's second metric: every legal turn sequence's afterstate,
+                                                                     # enumerated and evaluated (duplicates and twins scored once, counted all)
                 "sequences_per_ply": seqs_all / plies_all, "scored_per_ply": scored_all / plies_all,
                 "tree_edges_per_ply_rank0": edges / max(plies, 1), "ply_warps_per_cta": eng.kernel_config(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 44, "d2h_bytes_per_step": G * 33,
