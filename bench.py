@@ -44,7 +44,7 @@ def workload_config(n_gpus):
     return {"workload": "greedy 1-ply self-play, 198-128-1 net random-init (seed 0), eps=0, Philox dice, "
                         "first mover g%2, in-place restart (BASELINE.json configs[2])",
             "games_per_gpu": GAMES_PER_GPU, "plies_per_step": PLIES_PER_STEP, "n_gpus": n_gpus,
-            "parallelism": f"games sharded over {n_gpus} GPU(s), no data-path collective",
+            "parallelism": f"games sharded over {n_gpus} GPU(s), no data-path collective; one process per GPU, pinned to the GPU's local CPUs",
             "l2": "256 MiB scratch written between timed steps (L2 flush); population 2 MiB"}
 
 
@@ -250,6 +250,24 @@ def side_legs(eng, dev, peaks, n_positions):
             "evaluate": {"kernel": "k_evaluate", "ms": t_ev * 1e3, "rows_per_sec": n / t_ev}}
 
 
+def pin_to_gpu_cpus(index):
+    """Several ranks on one box: keep this rank's host threads (and its pinned buffers, first-touch) on the CPUs NVML lists as
+    local to its GPU, so that the per-ply host<->device traffic of the end-to-end leg does not cross sockets.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -262,6 +280,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_cpus(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
