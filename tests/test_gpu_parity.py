@@ -722,3 +722,30 @@ def test_pybind_batch_engine_matches_the_c_abi(eng, golden):
         assert np.array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1))
     be.selfplay_next_round()
     assert not be.selfplay_read()[1].any()
+
+
+# ------------------------------------------------------------------ the whole training loop, end to end
+
+def test_gpu_trainer_learns_to_beat_the_random_policy():
+    """BASELINE configs[3] as a function, not only as a throughput: rounds of self-play from one snapshot + exact TD(lambda)
+    replay + mean of the per-game weight changes (bgx.train.GpuTrainer), from the reference's random initialisation
+    (model.py:55-61), turn a net that is even with the random policy into one that beats it - a few seconds on a B200."""
+    import torch
+    from bgx.evaluate import Arena, play_vs_random
+    from bgx.model import TDLGammonModel
+    from bgx.train import GpuTrainer
+    torch.manual_seed(0)
+    m = TDLGammonModel()
+    arena = Arena(0)
+    try:
+        before, _ = play_vs_random(arena, m.weights_np(), 1024)
+        tr = GpuTrainer(m, 256, delta_scale=2.0 / 256)
+        for _ in range(2000):
+            st = tr.round(epsilon=0.0)
+        tr.sync_model()
+        after, avg_len = play_vs_random(arena, m.weights_np(), 1024)
+    finally:
+        arena.close()
+    assert st["games_finished"] == 256 and st["truncated"] == 0
+    assert before < 0.7 and after > 0.95, (before, after)
+    assert avg_len < 90                               # it learnt to race: random-init games last ~109 plies
