@@ -8,20 +8,31 @@
 // arithmetic; only the two forward passes exchange data (per-warp partial pre-activations through
 // shared memory, 16 KB).  The replay is the reference's, step for step: two forwards per step with
 // the CURRENT weights, closed-form gradients of the 2-layer sigmoid net,
-// and the same fp32 roundings torch produces (separate multiply and add, lr*delta formed in
-// float64 then rounded to fp32).  Two __syncthreads per step.
+// lr*delta formed in float64 then rounded to fp32 as torch does.  Two __syncthreads per step.
 //
 // Blackwell packed fp32: the two forwards run on FFMA2 (fma.rn.f32x2, x stored as {x, x} pairs).  Measured dead ends
 // (profiles/r1_td_replay_ncu_summary.md): the trace/weight update on FFMA2 with exact unfused roundings (fma(a,b,-0),
-// fma(a,1,b)) is 4 % slower than scalar FMUL/FADD, and visiting only the non-zero rows through a switch costs 25 %:
+// fma(a,1,b)) is 4 % slower than scalar FMUL/FADD (the FUSED packed update below is 15 % faster), and visiting only the non-zero rows through a switch costs 25 %:
 // the step is bound by its dependent phases and two barriers, not by issue slots.  One game per 2-CTA cluster (64 hidden units
 // per CTA, output partials exchanged through DSMEM, halves of two games resident per SM) was built and measured too: 7 %
-// slower - the overlap of two games' phases gains nothing, the cluster barrier costs ~380 cycles per step.
+// slower - the overlap of two games' phases gains nothing, the cluster barrier costs ~380 cycles per step.  So was the
+// transposed ownership (a warp owns 8 hidden units for all features, the first-layer sums completed inside the warp by a
+// transposing shuffle butterfly, one sigmoid per lane, ONE barrier per step): 61.9 against 68.7 M TD steps/s - its chain
+// of ~12 dependent shuffles per step is longer than the barrier it removes (gpurun_out/td2).
 #pragma once
 #include "bgx_device.cuh"
 
 namespace bgx {
 
+// Trace / weight update arithmetic.  1 (default): packed FMAs, e = fma(lambda, e, g*x), w = fma(c, e, w) - one rounding where
+// torch's separate multiply and add have two.  0: torch's unfused roundings (__fmul_rn / __fadd_rn).  Neither is bit-identical
+// to torch (the forward sums are ordered differently, and a TD error is a difference of two nearly equal values); measured
+// against the oracle on the same games both give the same relative error of the weight change (tools/td_err_probe.py:
+// 2e-6 .. 1.3e-5 of max|dw| over 12 games either way), and the fused form needs 6 packed instructions per row instead of
+// 20 scalar ones: 59.6 -> 68.7 M TD steps/s (gpurun_out/tdfma).
+#ifndef BGX_TD_FMA
+#define BGX_TD_FMA 1
+#endif
 constexpr int kTdThreads = 512;
 constexpr int kTdWarps = kTdThreads / 32;
 constexpr int kTdRows = (kFeatures + kTdWarps - 1) / kTdWarps;      // 13 feature rows per warp
@@ -63,6 +74,16 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
     asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b.x), "f"(b.y));
     asm("mov.b64 %0, {%1, %2};" : "=l"(Cc) : "f"(c.x), "f"(c.y));
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(Cc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(D));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    unsigned long long A, B, D;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
     float2 d;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(D));
     return d;
@@ -202,6 +223,23 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
                 gh[k] = __fmul_rn(__fmul_rn(__fmul_rn(gv, w2c[4 * lane + k]), __fsub_rn(1.0f, hh[k])), hh[k]);
             }
             // (4) e <- lambda*e + grad ; p <- p + c*e   (train.py:141-147), all 25 601 parameters
+#if BGX_TD_FMA
+            {
+                const float2 lam2 = make_float2(lam, lam), c2 = make_float2(c, c);
+                const float2 g01 = make_float2(gh[0], gh[1]), g23 = make_float2(gh[2], gh[3]);
+#pragma unroll
+                for (int r = 0; r < kTdRows; r++) {
+                    const int f = warp + kTdWarps * r;
+                    if (f < kFeatures) {
+                        const float2 x2 = *reinterpret_cast<const float2 *>(xc + 2 * f);
+                        E[r][0] = fma2(lam2, E[r][0], mul2(g01, x2));
+                        E[r][1] = fma2(lam2, E[r][1], mul2(g23, x2));
+                        W[r][0] = fma2(c2, E[r][0], W[r][0]);
+                        W[r][1] = fma2(c2, E[r][1], W[r][1]);
+                    }
+                }
+            }
+#else
 #pragma unroll
             for (int r = 0; r < kTdRows; r++) {
                 const int f = warp + kTdWarps * r;
@@ -217,6 +255,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
                     W[r][1].y = __fadd_rn(W[r][1].y, __fmul_rn(c, E[r][1].y));
                 }
             }
+#endif
             if (warp == 0) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {

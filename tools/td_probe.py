@@ -4,6 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "backgammon-engine_b200")]
 import numpy as np, torch
 from bench import init_weights
+from bgx import lib as L
+if os.environ.get('BGX_LIB'): L.load(os.environ['BGX_LIB'])
 from bgx.engine import BatchEngine
 G = int(os.environ.get("TD_GAMES", "65536"))
 eng = BatchEngine(0); eng.set_weights(*init_weights())
