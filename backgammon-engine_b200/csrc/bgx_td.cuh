@@ -33,6 +33,14 @@ namespace bgx {
 #ifndef BGX_TD_FMA
 #define BGX_TD_FMA 1
 #endif
+// Sum of the 16 per-warp partial pre-activations of a hidden unit.  0: all in float64 (16 F2F + 16 DADD per thread, on the
+// step's critical path).  1 (default): four fp32 chains of four, the four chain sums and b1 added in float64 (4 F2F).
+// 2: all fp32.  Measured (gpurun_out/td3): 68.4 / 71.6 / 72.3 M TD steps/s; worst |dw - dw_ref| / tolerance over the five
+// reference-played golden games 0.75 / 0.75 / 0.85.  Forming c = (float)(lr * delta) without float64 (lr split in two floats,
+// one FMA for the exact product error) is bit-identical and 1.5 % slower: the conversions are not what the step waits for.
+#ifndef BGX_TD_SUM
+#define BGX_TD_SUM 1
+#endif
 constexpr int kTdThreads = 512;
 constexpr int kTdWarps = kTdThreads / 32;
 constexpr int kTdRows = (kFeatures + kTdWarps - 1) / kTdWarps;      // 13 feature rows per warp
@@ -184,11 +192,24 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
             if (tid < 2 * kHidden) {
                 const int s = tid >> 7, j = tid & 127;
                 if (s == 0 || !terminal) {
+#if BGX_TD_SUM == 0
                     double za4[4] = {0.0, 0.0, 0.0, 0.0};         // few-term fp32 partials, summed in float64 (exact): four short chains
 #pragma unroll
                     for (int w = 0; w < kTdWarps; w++) za4[w & 3] += (double)part[(w * 2 + s) * kHidden + j];
                     const double zd = (za4[0] + za4[1]) + (za4[2] + za4[3]);
                     const float h = sigmoid_f32((float)(zd + (double)b1[j]));
+#elif BGX_TD_SUM == 1
+                    float zf4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int w = 0; w < kTdWarps; w++) zf4[w & 3] += part[(w * 2 + s) * kHidden + j];
+                    const double zd = ((double)zf4[0] + (double)zf4[1]) + ((double)zf4[2] + (double)zf4[3]);
+                    const float h = sigmoid_f32((float)(zd + (double)b1[j]));
+#else
+                    float zf4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int w = 0; w < kTdWarps; w++) zf4[w & 3] += part[(w * 2 + s) * kHidden + j];
+                    const float h = sigmoid_f32(((zf4[0] + zf4[1]) + (zf4[2] + zf4[3])) + b1[j]);
+#endif
                     hs[s * kHidden + j] = h;
                     float y = w2c[j] * h;
 #pragma unroll
@@ -203,18 +224,19 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
             // (3) TD error, gradients w.r.t. the pre-update weights
             const float b2c = red[8 + (t & 1)];
             const float v_cur = sigmoid_f32(red[0] + red[1] + red[2] + red[3] + b2c);
-            double delta;
+            float c;                                                         // (float)(lr * delta), lr a double: train.py:147
             if (!terminal) {
                 const float v_next = sigmoid_f32(red[4] + red[5] + red[6] + red[7] + b2c);
-                delta = (double)__fsub_rn(v_next, v_cur);                    // train.py:160
+                const float d = __fsub_rn(v_next, v_cur);                    // train.py:160
                 if (tid == 0) {
+                    const double delta = (double)d;
                     sq_sum += delta * delta;
                     if (p.sq_errors) p.sq_errors[t] = delta * delta;         // train.py:162
                 }
+                c = (float)(p.lr * (double)d);
             } else {
-                delta = (p1_won ? 1.0 : 0.0) - (double)v_cur;               // train.py:168
+                c = (float)(p.lr * ((p1_won ? 1.0 : 0.0) - (double)v_cur));  // train.py:168
             }
-            const float c = (float)(p.lr * delta);                           // train.py:147
             const float gv = __fmul_rn(__fsub_rn(1.0f, v_cur), v_cur);
             float gh[4], hh[4];
 #pragma unroll
