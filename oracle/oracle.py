@@ -20,6 +20,37 @@ _i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
 
+def td_replay_f64(weights, X, player1_won, lr, lam):
+    """apply_td_updates (train.py:124-172) in float64, with the closed-form gradients of the 2-layer sigmoid net
+    (model.py:63-67): the exact arithmetic that every fp32 implementation - torch, the C oracle,
+    the GPU kernel - approximates.  A yardstick, not a parity target: a TD error is the difference of two fp32 values
+    and fp32 implementations scatter around this result by ~1e-5 of max|dw| (more with large trained weights).
+    -> (W1, b1, w2, b2) float64 after the replay."""
+    W1, b1, w2, b2 = (np.asarray(a, np.float64).copy() for a in weights)
+    W1 = W1.reshape(128, 198); w2 = w2.reshape(-1); b2 = b2.reshape(-1)
+    X = np.asarray(X, np.float64).reshape(-1, 198)
+    eW1 = np.zeros_like(W1); eb1 = np.zeros_like(b1); ew2 = np.zeros_like(w2); eb2 = 0.0
+
+    def sig(z):
+        return 1.0 / (1.0 + np.exp(-z))
+    T = len(X)
+    for t in range(T):
+        x = X[t]
+        h = sig(W1 @ x + b1)
+        v = sig(w2 @ h + b2[0])
+        if t < T - 1:                                   # train.py:153-160: v' with the CURRENT weights
+            d = sig(w2 @ sig(W1 @ X[t + 1] + b1) + b2[0]) - v
+        else:                                           # train.py:165-168
+            d = (1.0 if player1_won else 0.0) - v
+        gv = v * (1.0 - v)
+        gh = gv * w2 * h * (1.0 - h)
+        eW1 = lam * eW1 + np.outer(gh, x); eb1 = lam * eb1 + gh      # train.py:141-147
+        ew2 = lam * ew2 + gv * h; eb2 = lam * eb2 + gv
+        c = lr * d
+        W1 += c * eW1; b1 += c * eb1; w2 += c * ew2; b2[0] += c * eb2
+    return W1, b1, w2.reshape(1, -1), b2
+
+
 ERR_STRINGS = {
     0: "",
     1: "Invalid origin",

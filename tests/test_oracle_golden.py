@@ -205,6 +205,30 @@ def test_td_replay_golden(orc, golden):
         assert np.max(np.abs(np.sqrt(sq) - np.sqrt(ref_l))) <= 1e-5, name
 
 
+def test_td_replay_f64_yardstick(orc, golden):
+    """The float64 replay (oracle.td_replay_f64) is the same algorithm: torch's own results (the golden vectors) and the
+    fp32 C oracle both scatter around it at the fp32 noise level, and neither is systematically closer."""
+    from oracle.oracle import td_replay_f64
+    g = golden("games.npz")
+    gm = golden("model.npz")
+    for name in g["names"]:
+        name = str(name)
+        rand = name.startswith("rand")
+        w0 = golden_weights(gm, "rand" if rand else "trained")
+        args = (g[f"{name}.enc"], int(g[f"{name}.winner"]) == 0, float(g[f"{name}.lr"]), float(g[f"{name}.lam"]))
+        new32, _ = orc.td_replay(w0, *args)
+        new64 = td_replay_f64(w0, *args)
+        for a32, a64, b, k in zip(new32, new64, w0, ("W1", "b1", "w2", "b2")):
+            b = np.asarray(b, np.float64).reshape(-1)
+            d64 = np.asarray(a64).reshape(-1) - b
+            e_torch = np.max(np.abs(g[f"{name}.new_{k}"].reshape(-1) - b - d64)) / np.max(np.abs(d64))
+            e_orc = np.max(np.abs(np.asarray(a32, np.float64).reshape(-1) - b - d64)) / np.max(np.abs(d64))
+            bound = 1e-4 if rand else 2e-3          # trained |w| reaches 6: the weight's own fp32 quantum dominates
+            assert e_torch <= bound and e_orc <= bound, (name, k, e_torch, e_orc)
+            if k == "W1":                             # 25,344 entries: a stable statistic (b2 is a single number)
+                assert e_orc <= 3 * e_torch and e_torch <= 3 * e_orc, (name, k, e_torch, e_orc)
+
+
 def test_greedy_games_golden(orc, golden):
     """Replay the reference's greedy games ply by ply: dice spec, legal set, chosen afterstate."""
     g = golden("games.npz")
