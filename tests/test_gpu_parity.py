@@ -160,6 +160,34 @@ def test_values_golden(eng, golden, tag):
         assert np.array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1))
 
 
+@pytest.mark.parametrize("tag", ["trained", "rand"])
+def test_values_hundred_thousand_afterstates(eng, orc, golden, tag):
+    """value parity <= 1e-5 relative on a 10^5-afterstate sample - the afterstates the engine itself
+    enumerates for 3,000 seeded sweep positions (mover's turn flag, model.py:139-140), scored by k_evaluate and by the
+    oracle's dense fp32 forward (model.py:63-67)."""
+    from bgx.synth import make_queries
+    w = golden_weights(golden("model.npz"), tag)
+    eng.set_weights(*w)
+    q, _ = make_queries(3000, seed=4242)
+    offsets, mv, ln, st = eng.enumerate_host(q)
+    counts = np.diff(offsets)
+    player = np.repeat(q[:, 28], counts)
+    rows = records_from(st[:, :28], player)
+    keep = np.random.default_rng(5).permutation(len(rows))[:100000]
+    assert len(keep) == 100000
+    rows = rows[keep]
+    V = eng.evaluate_host(rows)
+    ref = np.zeros(len(rows), np.float32)
+    for pl in (0, 1):
+        m = rows[:, 28] == pl
+        ref[m] = orc.forward(w, orc.encode(rows[m, :28].astype(np.int32), pl))
+    assert np.max(np.abs(V - ref) / np.abs(ref)) <= 1e-5
+    X = eng.encode_host(rows[:20000])
+    for pl in (0, 1):
+        m = rows[:20000, 28] == pl
+        assert np.array_equal(X[m], orc.encode(rows[:20000][m, :28].astype(np.int32), pl))
+
+
 # ------------------------------------------------------------------ batched make_move
 
 def check_choice(orc, w, rec, chosen, value=None, n_seq=None):
