@@ -411,6 +411,8 @@ def run_ours(args):
         delta = torch.zeros(25604, dtype=torch.float32, device=dev)
         allreduce_delta(delta, dist if world > 1 else None)      # untimed: NCCL sets this collective up on first use
         barrier()
+        td_sampler = ClockSampler(local)                         # every rank watches its own GPU over the round
+        td_sampler.start()
         e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         e0.record(stream)
         play = eng.selfplay_round(0.0)
@@ -421,6 +423,14 @@ def run_ours(args):
         eng.apply_delta(delta, 1.0 / (args.td_games * world))
         e3.record(stream)
         barrier()
+        td_sampler.stop_flag.set()
+        td_sampler.join(timeout=3)
+        tcl = td_sampler.summary()
+        watts = [float(r[2]) for r in td_sampler.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        lo = torch.tensor([-(tcl["sm_mhz"] or 0.0), max(watts) if watts else 0.0, float("sw_power_cap" in tcl["reasons"]),
+                           float(bool(set(tcl["reasons"]) - {"sw_power_cap"}))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MAX)
         ms = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), e0.elapsed_time(e3)], dtype=torch.float64, device=dev)
         cnt = torch.tensor([play["plies"], tdst["td_steps"], play["games_finished"], play["truncated"]], dtype=torch.float64, device=dev)
         if world > 1:
@@ -433,6 +443,11 @@ def run_ours(args):
               "games": int(args.td_games * world), "plies": int(cnt[0]), "td_steps": int(cnt[1]), "games_finished": int(cnt[2]),
               "truncated": int(cnt[3]), "play_ms": ms[0], "td_replay_ms": ms[1], "allreduce_apply_ms": ms[2], "round_ms": ms[3],
               "plies_per_sec_incl_update": cnt[0] / (ms[3] * 1e-3), "td_steps_per_sec": cnt[1] / (ms[1] * 1e-3),
+              "replay_ms_this_rank": e1.elapsed_time(e2),
+              "clocks": {"sm_mhz_min_over_ranks": -float(lo[0]), "power_w_max_over_ranks": float(lo[1]),
+                         "sw_power_cap_on_some_rank": bool(lo[2] > 0), "other_slowdown_on_some_rank": bool(lo[3] > 0),
+                         "samples_rank0": tcl["samples"],
+                         "note": "each rank samples its own GPU (nvidia-smi, 0.2 s) over the whole round; median SM clock per rank, min over ranks"},
               "note": "one round: every game played to its end from one snapshot (k_selfplay), exact online TD(lambda) replay "
                       "per game (k_td_replay), NCCL all-reduce of fp32[25604], apply; allreduce_apply_ms includes waiting for the "
                       "slowest rank's replay (max over ranks)"}
