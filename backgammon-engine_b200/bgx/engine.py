@@ -232,6 +232,16 @@ class BatchEngine:
                                                 cho.ctypes.data if cho is not None else None, C.byref(T)))
         return pre[: T.value], (cho[: T.value] if cho is not None else None)
 
+    def selfplay_sample_host(self, per_game, seed=0):
+        """-> int8[n_slots * per_game, 32]: pre-move records of every slot's current game at uniformly drawn plies"""
+        out = np.zeros((self.n_slots * int(per_game), 32), np.int8)
+        L.check(self._lib.bgx_selfplay_sample_host(self._h, int(per_game), int(seed), out.ctypes.data))
+        return out
+
+    def selfplay_sample(self, per_game, seed, out):
+        """device tensor int8[n_slots * per_game, 32]"""
+        L.check(self._lib.bgx_selfplay_sample(self._h, int(per_game), int(seed), L.ptr(out)))
+
     # ------------------------------------------------------------------ TD(lambda)
     def td_replay(self, lr, lam, delta, want_stats=True):
         """delta: device fp32[25604] (torch tensor or raw pointer), overwritten with the summed weight change"""
@@ -241,6 +251,12 @@ class BatchEngine:
 
     def apply_delta(self, delta, scale=1.0):
         L.check(self._lib.bgx_apply_delta(self._h, L.ptr(delta), float(scale)))
+
+    def td_profile(self, on=True):
+        """Switch the instrumented k_td_replay on/off; -> uint64[16] phase cycles of the last instrumented launch (CTA 0)"""
+        out = np.zeros(16, np.uint64)
+        L.check(self._lib.bgx_td_profile(self._h, int(bool(on)), out.ctypes.data))
+        return out
 
     def td_replay_host(self, records, player1_won, lr, lam):
         """One trajectory (records int8[T,32], byte 28 = turn flag) from the engine's current weights.

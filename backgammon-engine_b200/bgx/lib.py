@@ -74,6 +74,8 @@ _SIGNATURES = {
     "bgx_selfplay_next_round": (C.c_int, [_vp]),
     "bgx_selfplay_read": (C.c_int, [_vp, _vp, _vp, _vp]),
     "bgx_export_trajectory": (C.c_int, [_vp, _i64, C.c_int32, _vp, _vp, C.POINTER(C.c_int32)]),
+    "bgx_selfplay_sample": (C.c_int, [_vp, C.c_int32, C.c_uint64, _vp]),
+    "bgx_selfplay_sample_host": (C.c_int, [_vp, C.c_int32, C.c_uint64, _vp]),
     # section 5
     "bgx_td_replay": (C.c_int, [_vp, C.c_float, C.c_float, _vp, C.POINTER(Stats)]),
     "bgx_apply_delta": (C.c_int, [_vp, _vp, C.c_float]),
@@ -83,6 +85,7 @@ _SIGNATURES = {
     "bgx_launch_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "bgx_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "bgx_kernel_config": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bgx_td_profile": (C.c_int, [_vp, C.c_int, _vp]),
     "bgx_device_props": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64)]),
 }
 

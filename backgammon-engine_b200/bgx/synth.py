@@ -124,3 +124,30 @@ def make_queries(n, seed=20260101, classes=CLASSES):
     out[:, 29] = rng.integers(1, 7, n)
     out[:, 30] = rng.integers(1, 7, n)
     return out, cls
+
+
+SWEEP_SEED = 20260101
+PLAYOUT_SAMPLES_PER_GAME = 8
+
+
+def make_sweep_queries(eng, n, seed=SWEEP_SEED):
+    """The enumeration sweep of BASELINE.json configs[1] as SURVEY.md 8(d) config 2 defines it: half of the n positions are
+    constructive (make_queries), half are sampled from random-vs-random playouts (config 1: benchmark.py:54-96, epsilon = 1
+    self-play on `eng`, Philox dice under `seed`, first mover id % 2) at uniformly drawn plies, with the dice the playout
+    rolled there.  `eng` is a BatchEngine with weights set (the random policy never looks at them); its self-play
+    population is replaced.  -> int8[n, 32] queries, class ids int8[n] (len(CLASSES) = playout)."""
+    from .lib import FIRST_PARITY
+    n_con = n - n // 2
+    q, cls = make_queries(n_con, seed=seed)
+    n_play = n - n_con
+    if n_play:
+        per = PLAYOUT_SAMPLES_PER_GAME
+        games = (n_play + per - 1) // per
+        eng.selfplay_init(games, first_id=0, id_stride=games, seed=seed, first_mover=FIRST_PARITY, traj_cap=1024)
+        st = eng.selfplay_round(epsilon=1.0)
+        if st["truncated"]:
+            raise RuntimeError(f"{st['truncated']} random playouts exceeded 1024 plies")
+        rec = eng.selfplay_sample_host(per, seed=seed)[:n_play]
+        q = np.concatenate([q, rec])
+        cls = np.concatenate([cls, np.full(n_play, len(CLASSES), np.int8)])
+    return q, cls

@@ -1,8 +1,9 @@
 """Self-play and TD(lambda) training: the reference's train.py entry points on the compat API,
 plus the population trainer that runs whole rounds on the GPU.
 
-`play_game` / `apply_td_updates` keep the reference's signatures and semantics
-(train.py:64-121, 124-172) so its sequential and pool trainers can import them from here.
+The reference's own `play_game` / `apply_td_updates` (train.py:64-121, 124-172) run unmodified on the
+compat module and on `TDLGammonModel`; their torch restatement used as a checker lives in tests/ref_td.py.
+`play_games_batch` is `play_game` for a whole population on the GPU.
 `GpuTrainer` replaces the multiprocessing pool + sequential replay (train.py:305-354, 527-547):
 one round = every game of the population played to its end from one weight snapshot
 (k_selfplay), every trajectory replayed with exact online TD(lambda) from that snapshot
@@ -13,34 +14,8 @@ the other is the one deliberate divergence from the reference (SURVEY.md §7.3-5
 import numpy as np
 import torch
 
-import backgammon_env as bg
-
 from . import lib as L
 from .parallel import allreduce_delta, shard
-
-
-def play_game(model, game_idx, epsilon=0.0):
-    """One self-play game on a compat Game. Returns (winner, states, total_moves) like train.py:64-121."""
-    model.eval()
-    game = bg.Game(0)
-    white = bg.Player("White", bg.PlayerType.PLAYER1)
-    black = bg.Player("Black", bg.PlayerType.PLAYER2)
-    game.setPlayers(white, black)
-    while True:                                       # opening roll-off by dice sums (train.py:89-97)
-        a, b = sum(game.roll_dice()), sum(game.roll_dice())
-        if a != b:
-            break
-    game.setTurn(bg.PlayerType.PLAYER1 if a > b else bg.PlayerType.PLAYER2)
-    states, total_moves = [], 0
-    while True:
-        states.append(model.encode_state_np(game))    # pre-move encoding with the mover's flag
-        game.roll_dice()
-        model.make_move(game, game_idx, epsilon=epsilon)
-        over, winner = game.is_game_over()
-        if over:
-            return winner, states, total_moves
-        game.setTurn(bg.PlayerType.PLAYER2 if game.getTurn() == bg.PlayerType.PLAYER1 else bg.PlayerType.PLAYER1)
-        total_moves += 1
 
 
 def play_games_batch(model, n_games, epsilon=0.0, seed=0x5EED2026, device=0, first_id=0):
@@ -60,38 +35,6 @@ def play_games_batch(model, n_games, epsilon=0.0, seed=0x5EED2026, device=0, fir
         X = eng.encode_host(pre)                                     # _encode_states_np with the mover's flag
         games.append((int(rec[slot, 31]) - 1, [x for x in X], len(pre) - 1))
     return games
-
-
-def apply_td_updates(model, optimizer, states, player1_won):
-    """Online TD(lambda) over one recorded game (train.py:124-172): traces reset by the caller,
-    weights and model.eligibility_traces updated in place, returns the squared TD errors."""
-    device = next(model.parameters()).device
-    sq_errors = []
-
-    def step(value, td_error):
-        optimizer.zero_grad()
-        value.backward()
-        with torch.no_grad():
-            for name, p in model.named_parameters():
-                if p.requires_grad and p.grad is not None:
-                    model.eligibility_traces[name] = model.lambda_decay * model.eligibility_traces[name] + p.grad.data
-                    p.add_(model.learning_rate * td_error * model.eligibility_traces[name])
-
-    tensors = [torch.from_numpy(s).to(device).unsqueeze(0) for s in states]
-    for t in range(len(tensors) - 1):
-        model.eval()
-        with torch.no_grad():
-            v_next = model(tensors[t + 1])
-        model.train()
-        v = model(tensors[t])
-        delta = (v_next - v).item()
-        step(v, delta)
-        sq_errors.append(delta ** 2)
-    if tensors:
-        model.train()
-        v = model(tensors[-1])
-        step(v, (1.0 if player1_won else 0.0) - v.item())
-    return sq_errors
 
 
 class GpuTrainer:

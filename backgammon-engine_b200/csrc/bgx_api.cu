@@ -5,6 +5,7 @@
 #include "bgx_internal.h"
 #include "bgx_kernels.cuh"
 #include "bgx_td.cuh"
+#include "bgx_td_dense.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -61,6 +62,8 @@ struct bgx_engine {
     // TD
     float *td_partial = nullptr;             // [td_grid][25604] per-CTA delta accumulators
     float *td_delta = nullptr;               // [25604] summed delta of bgx_td_round_host
+    unsigned long long *td_prof = nullptr;   // [16] phase cycles of the profiling variant of k_td_replay
+    bool td_profile = false;
     int td_grid = 0;
     int lane_grid = -1;                      // CTAs of a k_select launch on an asynchronous lane: half the SMs, so that two lanes'
                                              // batches are resident at once (0: one per SM; BGX_SELECT_LANE_GRID)
@@ -193,7 +196,9 @@ static_assert(ply_smem<16, 110>() <= 232448 && ply_smem<20, 87>() <= 232448 && p
     BGX_SMEM_ATTR(24, 73)
     BGX_SMEM_ATTR(32, 54)
 #undef BGX_SMEM_ATTR
-    CU(cudaFuncSetAttribute(k_td_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
+    CU(cudaFuncSetAttribute(k_td_replay<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
+    CU(cudaFuncSetAttribute(k_td_replay<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
+    CU(cudaFuncSetAttribute(k_td_replay_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdDSmem));
     *out = e;
     return BGX_OK;
 }
@@ -206,7 +211,7 @@ int bgx_destroy(bgx_engine *e)
     for (int i = 0; i < bgx_engine::kScratch; i++) cudaFree(e->dbuf[i]);
     cudaFree(e->flat); cudaFree(e->wt); cudaFree(e->fixed); cudaFree(e->aux); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats); cudaFree(e->steal);
     cudaFree(e->uniq_tables); cudaFree(e->uniq_gens); cudaFree(e->slots); cudaFree(e->traj_pre); cudaFree(e->traj_chosen);
-    cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial); cudaFree(e->td_delta);
+    cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial); cudaFree(e->td_delta); cudaFree(e->td_prof);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_sync);
     for (bgx_lane &l : e->lanes) {
         if (l.stream) cudaStreamDestroy(l.stream);
@@ -825,6 +830,32 @@ int bgx_export_trajectory(bgx_engine *e, int64_t slot, int32_t cap, int8_t *pre,
     return BGX_OK;
 }
 
+int bgx_selfplay_sample(bgx_engine *e, int32_t per_game, uint64_t seed, int8_t *records)
+{
+    USE(e);
+    NEED(records && per_game > 0, "bad argument");
+    if (e->n_slots == 0 || !e->traj_pre) { set_error("bgx_selfplay_sample: needs a population created with traj_cap > 0"); return BGX_E_STATE; }
+    k_traj_sample<<<e->sm_count * 8, 256, 0, e->stream>>>(e->traj_pre, e->ply, e->n_slots, e->traj_cap, per_game,
+                                                         (uint32_t)seed, (uint32_t)(seed >> 32), records);
+    e->launches++;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
+int bgx_selfplay_sample_host(bgx_engine *e, int32_t per_game, uint64_t seed, int8_t *records)
+{
+    USE(e);
+    NEED(records && per_game > 0, "bad argument");
+    void *d;
+    int rc;
+    const size_t bytes = (size_t)e->n_slots * per_game * 32;
+    if ((rc = scratch(e, 0, bytes, &d))) return rc;
+    if ((rc = bgx_selfplay_sample(e, per_game, seed, (int8_t *)d))) return rc;
+    CU(cudaMemcpyAsync(records, d, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return BGX_OK;
+}
+
 // ------------------------------------------------------------------------ TD(lambda)
 
 static int ensure_td(bgx_engine *e)
@@ -833,6 +864,7 @@ static int ensure_td(bgx_engine *e)
     e->td_grid = e->sm_count;
     CU(cudaMalloc(&e->td_partial, (size_t)e->td_grid * BGX_NPARAMS_PADDED * sizeof(float)));
     CU(cudaMalloc(&e->td_delta, (size_t)BGX_NPARAMS_PADDED * sizeof(float)));
+    CU(cudaMalloc(&e->td_prof, 16 * sizeof(unsigned long long)));
     return BGX_OK;
 }
 
@@ -841,6 +873,7 @@ static int launch_td(bgx_engine *e, const int8_t *traj, const int8_t *slots, con
 {
     int rc = ensure_td(e);
     if (rc) return rc;
+    if (traj_cap > kTdMaxSteps) { set_error("TD replay: trajectories of up to %d recorded plies (traj_cap %d)", kTdMaxSteps, traj_cap); return BGX_E_INVALID; }
     int grid = e->td_grid;
     if (grid > n_games) grid = (int)n_games;
     TdParams p;
@@ -849,10 +882,16 @@ static int launch_td(bgx_engine *e, const int8_t *traj, const int8_t *slots, con
     p.flat = e->flat; p.wt = e->wt; p.partial = e->td_partial;
     p.final_weights = final_weights; p.sq_errors = sq_errors;
     p.stats = e->stats; p.dstats = e->dstats;
+    p.sched = nullptr; p.episode_first = 0; p.queue = e->counter;
+    p.prof = e->td_prof;
+    if (e->td_profile) CU(cudaMemsetAsync(e->td_prof, 0, 16 * sizeof(unsigned long long), e->stream));
+    CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->dstats, 0, 2 * sizeof(double), e->stream));
     tick(e);
-    k_td_replay<<<grid, kTdThreads, kTdSmem, e->stream>>>(p);
+    if (getenv("BGX_TD_DENSE")) k_td_replay_dense<<<grid, kTdDThreads, kTdDSmem, e->stream>>>(p);
+    else if (e->td_profile) k_td_replay<true><<<grid, kTdThreads, kTdSmem, e->stream>>>(p);
+    else k_td_replay<false><<<grid, kTdThreads, kTdSmem, e->stream>>>(p);
     e->launches++;
     CU(cudaGetLastError());
     if (delta_dev) {
@@ -872,6 +911,7 @@ static int launch_td(bgx_engine *e, const int8_t *traj, const int8_t *slots, con
         out->games_finished = (int64_t)h[3];
         out->truncated = (int64_t)h[5];
         out->td_sq_error = d[0];
+        out->tree_edges = (int64_t)h[7];           // row-steps replayed lazily (k_td_replay)
     }
     return BGX_OK;
 }
@@ -944,6 +984,19 @@ int bgx_td_replay_host(bgx_engine *e, const int8_t *records, int32_t T, int play
 }
 
 // ------------------------------------------------------------------------ introspection
+
+int bgx_td_profile(bgx_engine *e, int on, uint64_t *cycles)
+{
+    USE(e);
+    int rc = ensure_td(e);
+    if (rc) return rc;
+    e->td_profile = on != 0;
+    if (cycles) {
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpy(cycles, e->td_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    return BGX_OK;
+}
 
 int bgx_launch_count(bgx_engine *e, int64_t *n)
 {

@@ -770,4 +770,26 @@ __global__ void k_selfplay_reset(int8_t *slots, int32_t *ply, long long *game_id
     }
 }
 
+// `per_game` recorded pre-move records of every slot's current game, each at a uniformly drawn ply (Philox stream 3):
+// the playout half of the enumeration sweep (BASELINE.json configs[1])
+__global__ void k_traj_sample(const int8_t *__restrict__ traj, const int32_t *__restrict__ ply, long long n_slots, int traj_cap,
+                              int per_game, uint32_t seed_lo, uint32_t seed_hi, int8_t *__restrict__ out)
+{
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5), total = n_slots * per_game;
+    const int lane = threadIdx.x & 31;
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < total; i += warps) {
+        const long long slot = i / per_game;
+        const int j = (int)(i % per_game);
+        int T = ply[slot];
+        if (T > traj_cap) T = traj_cap;
+        int b = 0;
+        if (T > 0) {
+            const Philox r = philox4x32_10(seed_lo, seed_hi, (uint32_t)j, (uint32_t)slot, (uint32_t)((unsigned long long)slot >> 32), 3u);
+            const int t = (int)mulhi32(r.x[0], (uint32_t)T);
+            b = load_record_byte(traj + ((size_t)slot * traj_cap + t) * 32, lane);
+        }
+        out[i * 32 + lane] = (int8_t)(lane == 31 ? 0 : b);
+    }
+}
+
 } // namespace bgx

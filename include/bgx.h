@@ -252,6 +252,13 @@ int bgx_selfplay_read(bgx_engine *e, int8_t *records, int32_t *ply, int64_t *gam
  * (bytes 29,30), chosen[T][32] afterstates (byte 31 = sequence played flag); *T plies. */
 int bgx_export_trajectory(bgx_engine *e, int64_t slot, int32_t cap, int8_t *pre, int8_t *chosen, int32_t *T);
 
+/* records[n_slots * per_game][32]: `per_game` pre-move RECORDs (dice included) of every slot's current game, each taken at
+ * a ply drawn uniformly from the plies recorded so far (Philox key = seed, counter = (j, slot lo, slot hi, 3)); all-zero
+ * records for a slot with no recorded ply.  The "positions sampled from playouts at a uniform ply" of the enumeration
+ * sweep (benchmark.py:64-96 plays such games with _random_move, benchmark.py:54-61).  Device / host buffer. */
+int bgx_selfplay_sample(bgx_engine *e, int32_t per_game, uint64_t seed, int8_t *records);
+int bgx_selfplay_sample_host(bgx_engine *e, int32_t per_game, uint64_t seed, int8_t *records);
+
 /* ------------------------------------------------------------------------------------
  * 5. TD(lambda)  (replaces apply_td_updates, train.py:124-172)
  * ---------------------------------------------------------------------------------- */
@@ -280,6 +287,11 @@ int bgx_launch_count(bgx_engine *e, int64_t *n);
 /* CUDA-event duration (ms) of the last self-play / select / enumerate kernel launch */
 int bgx_last_kernel_ms(bgx_engine *e, float *ms);
 int bgx_device_props(bgx_engine *e, int *sm_count, int *clock_khz, int64_t *global_mem);
+/* on != 0: later TD replays run the instrumented variant of k_td_replay.  cycles[16] (may be NULL) receives what the last
+ * instrumented launch recorded on CTA 0: [0..7] SM cycles one worker thread spent in each phase of the step (first-layer
+ * store, worker barrier, hidden layer, lazy catch-up, step barrier, values + gradients, row pass, end of game), [8] [9] the
+ * lister's list building and barrier wait, [10] the TD steps of that CTA. */
+int bgx_td_profile(bgx_engine *e, int on, uint64_t *cycles);
 /* warps per CTA of the fused ply kernels as configured (defaults or BGX_*_WARPS) */
 int bgx_kernel_config(bgx_engine *e, int *selfplay_warps, int *select_warps);
 

@@ -252,7 +252,20 @@ class RefHarness(_SeqAPI):
         L.ref_turn_sequences.restype = C.c_long
         L.ref_bench_enumerate.argtypes = [_i32p, _i8p, _i8p, C.c_long, C.POINTER(C.c_int64)]
         L.ref_bench_enumerate.restype = C.c_double
+        L.ref_turn_summary_batch.argtypes = [_i8p, C.c_long, C.c_int, np.ctypeslib.ndpointer(np.int64, flags="C"),
+                                             np.ctypeslib.ndpointer(np.uint64, flags="C")]
+        L.ref_turn_summary_batch.restype = None
         self._turn = L.ref_turn_sequences
+
+    def turn_summary_batch(self, records, threads=None):
+        """The reference's own evaluateTurnSequences over records int8[n,32] -> (N int64[n], digest uint64[n]); the digest
+        of the ordered (sequence, state) list is computed in the harness from the reference's output."""
+        r = np.ascontiguousarray(records, dtype=np.int8).reshape(-1, 32)
+        n = r.shape[0]
+        ns, dg = np.zeros(n, np.int64), np.zeros(n, np.uint64)
+        if n:
+            self.lib.ref_turn_summary_batch(r.reshape(-1), n, int(threads or os.cpu_count() or 1), ns, dg)
+        return ns, dg
 
     def legal_moves(self, s, player, die):
         out = np.zeros(64, np.int8)

@@ -10,7 +10,10 @@
 #include "game.hpp"
 #include <cstdint>
 #include <cstring>
+#include <atomic>
 #include <chrono>
+#include <thread>
+#include <vector>
 
 namespace {
 struct Fixture {
@@ -122,6 +125,64 @@ double ref_bench_enumerate(const int32_t *states, const int8_t *player, const in
     auto t1 = std::chrono::steady_clock::now();
     if (total_sequences) *total_sequences = tot;
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Game::evaluateTurnSequences over a batch of 32-byte records (28 state bytes, mover, d1, d2, pad) on `threads` threads:
+// per query the number of sequences and the enumeration digest (D <- D * 0x9E3779B97F4A7C15 + h(leaf), h = four
+// splitmix64 rounds over the state's five bit-planes and the packed moves) computed HERE from the reference's own output,
+// so that the 10^6-position sweep can be compared with the reference itself without moving 1.4 GB of sequences.
+static inline uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+    x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+    x ^= x >> 31;
+    return x;
+}
+
+void ref_turn_summary_batch(const int8_t *records, long n, int threads, int64_t *n_seq, uint64_t *digest)
+{
+    std::atomic<long> next{0};
+    auto work = [&]() {
+        Fixture &f = fx();
+        int32_t s[28];
+        for (;;) {
+            const long lo = next.fetch_add(64);
+            if (lo >= n) break;
+            const long hi = lo + 64 < n ? lo + 64 : n;
+            for (long i = lo; i < hi; i++) {
+                const int8_t *r = records + 32 * i;
+                for (int j = 0; j < 28; j++) s[j] = r[j];
+                f.load(s);
+                TurnEval ev = f.game.evaluateTurnSequences(r[28], r[29], r[30]);
+                uint64_t dg = 0;
+                for (size_t k = 0; k < ev.sequences.size(); k++) {
+                    uint32_t w[5] = {0, 0, 0, 0, 0};
+                    for (int j = 0; j < 28; j++) {
+                        const int v = ev.states[k][j];
+                        const uint32_t mag = (uint32_t)(v < 0 ? -v : v);
+                        for (int b = 0; b < 4; b++) w[b] |= ((mag >> b) & 1u) << j;
+                        if (v < 0) w[4] |= 1u << j;
+                    }
+                    const auto &q = ev.sequences[k];
+                    uint64_t m = (uint64_t)q.size() << 40;
+                    for (size_t j = 0; j < q.size(); j++)
+                        m |= ((uint64_t)(uint8_t)q[j].first | ((uint64_t)(uint8_t)q[j].second << 5)) << (10 * j);
+                    uint64_t h = mix64((uint64_t)w[0] | ((uint64_t)w[1] << 32));
+                    h = mix64(h ^ ((uint64_t)w[2] | ((uint64_t)w[3] << 32)));
+                    h = mix64(h ^ (uint64_t)w[4]);
+                    h = mix64(h ^ m);
+                    dg = dg * 0x9E3779B97F4A7C15ULL + h;
+                }
+                n_seq[i] = (int64_t)ev.sequences.size();
+                digest[i] = dg;
+            }
+        }
+    };
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
 }
 
 } // extern "C"

@@ -271,5 +271,99 @@ def main():
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 
+
+
+# ---------------------------------------------------------------- G: TD(lambda) per-game parity fixture
+#   python tests/golden/make_golden.py td_parity
+# Input: tests/golden/td_traj.npz = 1,024 greedy self-play trajectories per weight set EXPORTED FROM THE GPU ENGINE
+# (tools/export_td_trajectories.py, run on the B200 box).  Every trajectory is replayed here by the reference's UNMODIFIED
+# apply_td_updates (train.py:124-172) from the round snapshot, exactly as train.py:538-542 calls it (update_learning_params(1):
+# lr 0.1, lambda 0.9; traces zeroed).  The full per-game weight change is 25,601 floats; the fixture keeps, per game and
+# tensor, max|dw|, and dw at 320 coordinates: the 64 largest |dw| of that game (where a relative error is decided), the 64
+# largest |w0| (where fp32 rounding of w is coarsest) and 192 fixed random ones; plus every per-step squared TD error.
+
+TD_FIXED = 192
+TD_TOP = 64
+
+
+def _td_one(args):
+    tag, sd, X, p1_won = args
+    torch.set_num_threads(1)
+    m = ref_model.TDLGammonModel()
+    m.load_state_dict(sd)
+    m.update_learning_params(1)
+    for name in m.eligibility_traces:
+        m.eligibility_traces[name].zero_()
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    m.train()
+    losses = ref_train.apply_td_updates(m, opt, [x for x in X], bool(p1_won))
+    new = np.concatenate([a.reshape(-1) for a in weights_of(m)])
+    return new, np.array(losses, np.float64)
+
+
+def td_coords(w0_flat):
+    rng = np.random.default_rng(20261018)
+    # every tensor is represented: 128 coordinates of W1, 31 of b1, 32 of w2, and b2
+    fixed = np.concatenate([np.sort(rng.choice(25344, 128, replace=False)), 25344 + np.sort(rng.choice(128, 31, replace=False)),
+                            25472 + np.sort(rng.choice(128, 32, replace=False)), [25600]]).astype(np.int32)
+    assert fixed.size == TD_FIXED
+    big_w = np.argsort(-np.abs(w0_flat), kind="stable")[:TD_TOP].astype(np.int32)
+    return fixed, big_w
+
+
+def td_parity():
+    import multiprocessing as mp
+    src = os.path.join(HERE, "td_traj.npz")
+    with np.load(src) as z:
+        traj = {k: z[k] for k in z.files}
+    with np.load(os.path.join(HERE, "model.npz")) as z:
+        gm = {k: z[k] for k in z.files}
+    enc = ref_model.TDLGammonModel()
+    out = {}
+    for tag in ("rand", "trained"):
+        w0 = tuple(gm[f"{tag}_{k}"] for k in ("W1", "b1", "w2", "b2"))
+        w0_flat = np.concatenate([a.reshape(-1) for a in w0]).astype(np.float32)
+        sd = {"fc1.weight": torch.from_numpy(w0[0].copy()), "fc1.bias": torch.from_numpy(w0[1].copy()),
+              "fc2.weight": torch.from_numpy(w0[2].copy()), "fc2.bias": torch.from_numpy(w0[3].copy())}
+        rec, offs, won = traj[f"{tag}.records"], traj[f"{tag}.offsets"], traj[f"{tag}.p1_won"]
+        n = len(won)
+        jobs = []
+        for g in range(n):
+            r = rec[offs[g]:offs[g + 1]]
+            X = np.zeros((len(r), 198), np.float32)
+            for t in (0, 1):                                     # the reference's own encoder, mover's flag (train.py:105-106)
+                sel = r[:, 28] == t
+                if sel.any():
+                    X[sel] = enc._encode_states_np(r[sel, :28].astype(np.int32), t)
+            jobs.append((tag, sd, X, int(won[g])))
+        with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+            res = pool.map(_td_one, jobs, chunksize=8)
+        fixed, big_w = td_coords(w0_flat)
+        bounds = (0, 25344, 25472, 25600, 25601)
+        dmax = np.zeros((n, 4), np.float32)
+        top_idx = np.zeros((n, TD_TOP), np.int32)
+        vals = np.zeros((n, TD_TOP + TD_TOP + TD_FIXED), np.float32)   # new weights at [top |dw| of the game, top |w0|, fixed]
+        losses, loff = [], [0]
+        for g, (new, ls) in enumerate(res):
+            dw = new.astype(np.float64) - w0_flat
+            for k in range(4):
+                dmax[g, k] = np.max(np.abs(dw[bounds[k]:bounds[k + 1]]))
+            top_idx[g] = np.argsort(-np.abs(dw), kind="stable")[:TD_TOP]
+            vals[g] = new[np.concatenate([top_idx[g], big_w, fixed])]
+            losses.append(ls)
+            loff.append(loff[-1] + len(ls))
+        out.update({f"{tag}.dmax": dmax, f"{tag}.top_idx": top_idx, f"{tag}.new_at": vals, f"{tag}.fixed_idx": fixed,
+                    f"{tag}.big_w_idx": big_w, f"{tag}.losses": np.concatenate(losses), f"{tag}.loss_offsets": np.array(loff, np.int64)})
+        print(tag, n, "games,", int(offs[-1]), "TD steps; median max|dW1|", float(np.median(dmax[:, 0])))
+    out["lr"] = np.float64(0.1)
+    out["lam"] = np.float64(0.9)
+    out["torch_version"] = np.array(torch.__version__)
+    np.savez_compressed(os.path.join(HERE, "td_parity.npz"), **out)
+    print("td_parity.npz", os.path.getsize(os.path.join(HERE, "td_parity.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "td_parity":
+        td_parity()
+    else:
+        main()

@@ -62,10 +62,11 @@ def test_reference_pytests_reexpressed(golden):
 
 
 def test_play_game_and_td_updates_compat(golden):
-    """bgx.train.play_game / apply_td_updates keep the reference contract (train.py:64-172)."""
+    """The torch restatement of play_game / apply_td_updates (tests/ref_td.py, the checker of the GPU TD tests) keeps
+    the reference contract (train.py:64-172) on the compat module and is bit-identical to the reference's own run."""
     import torch
     from bgx.model import TDLGammonModel
-    from bgx.train import apply_td_updates, play_game
+    from ref_td import apply_td_updates, play_game
     torch.manual_seed(1)
     m = TDLGammonModel()
     winner, states, total = play_game(m, 1)

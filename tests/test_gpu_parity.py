@@ -114,18 +114,34 @@ def test_enumerate_million_position_properties(eng):
     assert int(n.sum()) > 30_000_000
 
 
-def test_enumerate_million_positions_bit_exact_vs_oracle(eng, orc):
+def test_enumerate_million_positions_bit_exact_vs_reference(eng, orc, golden):
     """BASELINE north_star: "bit-exact move sets against the reference on 10^6 seeded positions".
-    EVERY position of the configs[1] sweep: sequence count, exact number of distinct afterstates and
-    the ordered digest (which pins every move of every sequence, its order and its resulting 28-int
-    state) against the CPU oracle (threaded C restatement, itself pinned to the reference)."""
-    from bgx.synth import make_queries
-    q, _ = make_queries(1_000_000, seed=20260101)
+    The configs[1] sweep as SURVEY 8(d) config 2 defines it: 500,000 constructive positions + 500,000 positions
+    sampled at uniform plies from random-vs-random playouts (config 1), dice over all 36 ordered pairs.  EVERY position:
+    sequence count and the ordered digest (which pins every move of every sequence, its order and its resulting
+    28-int state) against the UNMODIFIED reference engine's evaluateTurnSequences (game.cpp:193-222, oracle/_ref,
+    all host cores; ~50 M sequences), and count, exact number of distinct afterstates and digest against the C oracle."""
+    from bgx.synth import CLASSES, make_sweep_queries
+    from oracle.oracle import RefHarness
+    eng.set_weights(*golden_weights(golden("model.npz"), "rand"))
+    q, cls = make_sweep_queries(eng, 1_000_000)
+    play = q[cls == len(CLASSES)]
+    assert len(play) == 500_000
+    b = play[:, :24].astype(np.int64)
+    assert np.array_equal(np.where(b > 0, b, 0).sum(1) + play[:, 24] + play[:, 26], np.full(len(play), 15))
+    assert np.array_equal(np.where(b < 0, -b, 0).sum(1) + play[:, 25] + play[:, 27], np.full(len(play), 15))
+    assert ((play[:, 29] >= 1) & (play[:, 29] <= 6) & (play[:, 30] >= 1) & (play[:, 30] <= 6)).all()
+    assert len(np.unique(play, axis=0)) > 400_000                 # beyond the opening plies the playouts do not repeat
     n, u, d = eng.enumerate_summary_host(q)
     on, ou, od = orc.turn_summary_batch(q)
     assert np.array_equal(n.astype(np.int64), on)
     assert np.array_equal(u.astype(np.int64), ou)
     assert np.array_equal(d.astype(np.uint64), od)
+    if not RefHarness.available():
+        pytest.skip("GPU = oracle on all 10^6 positions; oracle/_ref was not built (no /root/reference at build time)")
+    rn, rd = RefHarness().turn_summary_batch(q)
+    assert np.array_equal(n.astype(np.int64), rn)
+    assert np.array_equal(d.astype(np.uint64), rd)
 
 
 # ------------------------------------------------------------------ encoding (bit-exact) and values
@@ -721,7 +737,8 @@ def test_play_games_batch_feeds_the_reference_td_update(eng, golden):
     CPU) on those states and the GPU replay of the same trajectory give the same weights."""
     import torch
     from bgx.model import TDLGammonModel
-    from bgx.train import apply_td_updates, play_games_batch
+    from bgx.train import play_games_batch
+    from ref_td import apply_td_updates
     W1, b1, w2, b2 = golden_weights(golden("model.npz"), "trained")
     sd = {"fc1.weight": torch.from_numpy(W1), "fc1.bias": torch.from_numpy(b1),
           "fc2.weight": torch.from_numpy(w2), "fc2.bias": torch.from_numpy(b2)}

@@ -4,6 +4,8 @@ Three anchors: the known answers of the reference's own cppsrc/tests.cpp, the
 golden vectors generated from the reference itself (tests/golden/make_golden.py),
 and — where oracle/_ref is present — the live reference engine on fresh seeds.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -268,3 +270,64 @@ def test_fuzz_against_live_reference(orc, ref):
         a = orc.turn_sequences(s, r[28], r[29], r[30])
         b = ref.turn_sequences(s, r[28], r[29], r[30])
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+# ------------------------------------------------------------------ TD(lambda) per-game parity fixture
+
+# max|dw - dw_ref| / max|dw_ref| per game of the fp32 C restatement (oracle/bgx_oracle.c: the reference's arithmetic step for
+# step, ascending-index fp32 sums) against the reference's own apply_td_updates (torch) on the 1,024 fixture games:
+# (p50, p99, max) as measured in the build container.  This is how far apart two faithful fp32 implementations of
+# train.py:124-172 are - the noise floor under every "1e-5" statement about TD updates - and the yardstick the GPU kernel's
+# distance from torch is printed beside (tests/test_gpu_parity.py, bench.py td_round.parity).
+RESTATEMENT_VS_TORCH = {
+    "rand": {"W1": (3.31e-6, 1.07e-5, 1.61e-5), "b1": (2.79e-6, 1.21e-5, 1.76e-5), "w2": (1.00e-6, 3.77e-6, 5.50e-6), "b2": (7.68e-7, 3.38e-6, 5.40e-6)},
+    "trained": {"W1": (1.14e-5, 4.72e-5, 8.39e-5), "b1": (7.43e-6, 4.21e-5, 9.73e-5), "w2": (3.57e-6, 1.57e-5, 2.54e-5), "b2": (6.19e-7, 2.62e-5, 1.81e-4)},
+}
+
+
+@pytest.mark.parametrize("tag", ["rand", "trained"])
+def test_td_parity_fixture_vs_c_restatement(orc, golden, tag):
+    """The C oracle replays all 1,024 fixture trajectories; its distance from the reference's torch results is the
+    documented fp32 noise floor (measured + 20 %), and the per-step TD errors agree at the value tolerance."""
+    from concurrent.futures import ThreadPoolExecutor
+    from td_fixture import TdFixture, flat, quantiles
+    fx = TdFixture(golden, tag)
+
+    def one(g):
+        r = fx.trajectory(g)
+        X = np.concatenate([orc.encode(r[t:t + 1, :28].astype(np.int32), int(r[t, 28])) for t in range(len(r))])
+        new, sq = orc.td_replay(fx.w0, X, fx.p1_won[g], fx.lr, fx.lam)
+        return fx.rel_error(g, flat(new)), float(np.max(np.abs(np.sqrt(sq) - np.sqrt(fx.ref_losses(g))))) if len(sq) else 0.0
+    with ThreadPoolExecutor(os.cpu_count() or 4) as ex:
+        res = list(ex.map(one, range(fx.n)))
+    err = np.array([r[0] for r in res])
+    assert max(r[1] for r in res) <= 1e-5
+    q = quantiles(err)
+    for name, want in RESTATEMENT_VS_TORCH[tag].items():
+        for got, w, what in zip(q[name], want, ("p50", "p99", "max")):
+            assert got <= 1.2 * w, (tag, name, what, got, w)
+    # the headline: a faithful fp32 restatement does NOT stay within 1e-5 of torch on every game
+    assert q["W1"][2] > 1e-5
+
+
+@pytest.mark.parametrize("tag", ["rand", "trained"])
+def test_td_parity_fixture_vs_torch_restatement(golden, tag):
+    """tests/ref_td.py (the torch checker the GPU tests run live) against the fixture made by the reference's own
+    apply_td_updates: same torch ops, so the same numbers up to the CPU's sgemv kernel choice."""
+    from ref_td import replay_many
+    from td_fixture import TdFixture
+    fx = TdFixture(golden, tag)
+    games = list(range(0, fx.n, 64))
+    enc = _reference_encoder()
+    jobs = [(fx.w0, enc(fx.trajectory(g)), int(fx.p1_won[g]), fx.lr, fx.lam) for g in games]
+    for g, (new, sq) in zip(games, replay_many(jobs, procs=1)):
+        e = fx.rel_error(g, new)
+        assert np.all(e <= np.array([RESTATEMENT_VS_TORCH[tag][k][2] for k in ("W1", "b1", "w2", "b2")])), (tag, g, e)
+        assert np.allclose(sq, fx.ref_losses(g), rtol=1e-3, atol=1e-12)
+
+
+def _reference_encoder():
+    """_encode_states_np (model.py:111-144) through the oracle's bit-exact restatement: records int8[T,32] -> X float32[T,198]"""
+    from oracle.oracle import Oracle
+    o = Oracle()
+    return lambda r: np.concatenate([o.encode(r[t:t + 1, :28].astype(np.int32), int(r[t, 28])) for t in range(len(r))])
