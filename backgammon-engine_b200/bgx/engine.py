@@ -253,8 +253,8 @@ class BatchEngine:
         L.check(self._lib.bgx_apply_delta(self._h, L.ptr(delta), float(scale)))
 
     def td_profile(self, on=True):
-        """Switch the instrumented k_td_replay on/off; -> uint64[16] phase cycles of the last instrumented launch (CTA 0)"""
-        out = np.zeros(16, np.uint64)
+        """Switch the instrumented k_td_replay on/off; -> uint64[8, 16] phase cycles per warp of the last instrumented launch (CTA 0)"""
+        out = np.zeros((8, 16), np.uint64)
         L.check(self._lib.bgx_td_profile(self._h, int(bool(on)), out.ctypes.data))
         return out
 

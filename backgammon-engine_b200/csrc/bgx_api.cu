@@ -864,7 +864,7 @@ static int ensure_td(bgx_engine *e)
     e->td_grid = e->sm_count;
     CU(cudaMalloc(&e->td_partial, (size_t)e->td_grid * BGX_NPARAMS_PADDED * sizeof(float)));
     CU(cudaMalloc(&e->td_delta, (size_t)BGX_NPARAMS_PADDED * sizeof(float)));
-    CU(cudaMalloc(&e->td_prof, 16 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&e->td_prof, 128 * sizeof(unsigned long long)));
     return BGX_OK;
 }
 
@@ -884,7 +884,7 @@ static int launch_td(bgx_engine *e, const int8_t *traj, const int8_t *slots, con
     p.stats = e->stats; p.dstats = e->dstats;
     p.sched = nullptr; p.episode_first = 0; p.queue = e->counter;
     p.prof = e->td_prof;
-    if (e->td_profile) CU(cudaMemsetAsync(e->td_prof, 0, 16 * sizeof(unsigned long long), e->stream));
+    if (e->td_profile) CU(cudaMemsetAsync(e->td_prof, 0, 128 * sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->dstats, 0, 2 * sizeof(double), e->stream));
@@ -993,7 +993,7 @@ int bgx_td_profile(bgx_engine *e, int on, uint64_t *cycles)
     e->td_profile = on != 0;
     if (cycles) {
         CU(cudaStreamSynchronize(e->stream));
-        CU(cudaMemcpy(cycles, e->td_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(cycles, e->td_prof, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     }
     return BGX_OK;
 }

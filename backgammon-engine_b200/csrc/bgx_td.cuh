@@ -1,28 +1,32 @@
 // bgx_td.cuh — exact online TD(lambda) replay, apply_td_updates (train.py:124-172).
 //
-// One game per CTA, weights AND eligibility traces of the 198 x 128 first layer in SHARED MEMORY (2 x 101,376 B of the
-// 227 KB a CTA may own), visited SPARSELY: a backgammon position has ~24 of its 198 features non-zero, and of the
-// reference's dense per-step work - two forwards, e <- lambda*e + grad, p <- p + (lr*delta)*e over all 25,344 parameters -
-// only the rows of the non-zero features are needed NOW:
+// One game per CTA.  A backgammon position has ~24 of its 198 features non-zero, and of the reference's dense per-step work
+// - two forwards, e <- lambda*e + grad, p <- p + (lr*delta)*e over all 25,344 first-layer parameters - only the rows of the
+// non-zero features are needed NOW:
 //   * the forwards of s_t and s_t+1 read the rows of their non-zero features;
 //   * the gradient is non-zero only in the rows of s_t's features;
 //   * every other row merely decays (e <- lambda*e) and drifts (w <- w + c_k*e) and is not looked at until its feature
 //     fires again.  Such a row is brought up to date LAZILY, when it enters the window of the next states, by replaying
 //     the steps it missed one by one with the recorded c_k = (float)(lr*delta_k): the same fp32 operations in the same
 //     order as the dense update, so the result is bit-identical to updating all 198 rows every step (which is what
-//     torch does), not an algebraic shortcut.  The arithmetic per row and step is 2 packed instructions (FMUL2, FFMA2);
-//     shared-memory traffic per row is one load and one store however long it slept.
+//     torch does), not an algebraic shortcut.  Per row and missed step: 2 packed instructions (FMUL2, FFMA2).
 //
-// Roles (288 threads): 8 worker warps + 1 lister warp, ONE block-wide barrier per step.
-//   worker thread = (pair of hidden units, row class): lane = u + 8q, the pair is 8*warp + u, the class q = 0..3 is a fixed
-//     4-colouring of the 198 feature rows (td_class: the four features of a point land in four different classes, so a
-//     position's ~45 live rows split evenly).  Element (row f, unit j) of W and E belongs to exactly one thread for the
-//     whole kernel - nobody else reads or writes it - so the window update of step t, the lazy catch-up and the forward of
-//     step t+1 need no synchronisation between them.  The four class partial sums of a pre-activation meet in two
-//     xor-shuffles; the 8 per-warp partial output sums cross warps through 64 bytes of shared memory: the one barrier.
-//   lister warp: decodes the trajectory records two states ahead and writes, per step, the compact list of live rows
-//     (feature values of s_t and s_t+1, first missed step of rows that re-enter the window), class by class in ascending
-//     feature order; at the end of the game the list of every touched row for the final catch-up / accumulate / restore.
+// Layout (256 threads, 8 warps): the 198 feature rows are 8-coloured (td_class: the eight features of a point land in
+// eight different classes, rotated by the point, so a position's ~35 live rows spread evenly); warp = class, lane = four
+// hidden units.  A thread owns element (row, 4 units) of every row of its class for the whole kernel, so update, lazy
+// replay and the next forward need no synchronisation.
+//   * Weights and traces of all 198 rows have their home in SHARED MEMORY (2 x 101,376 B of the 227 KB a CTA may own), but
+//     the LIVE rows of a class sit in REGISTERS: 8 slots x (float4 trace + float4 weight) per thread.  A row is loaded into
+//     a free slot when it enters the window (replaying what it slept through on the way) and written back when it leaves;
+//     while it stays - a checker configuration lasts many plies - its per-step update touches no memory at all.  (With
+//     the live rows updated in shared memory the window update moves ~80 KB per step through a 128 B/cycle port: measured
+//     887 of 2,800 cycles per step; with static per-class registers for ALL rows the 25 is-it-live tests per warp and
+//     step cost as much.)  More than 8 live rows in one class - rare - are updated in place in shared memory.
+//   * Every warp lists the live rows of its own class itself, lane r = row r of the class, from the three records of the
+//     window kept in a shared-memory ring: one ballot gives the live set, the feature values travel by shuffle.
+//   * ONE pass over the slots per step updates trace and weight AND accumulates, with the new weights, the first-layer
+//     partial sums of the next step's two forwards (s_t+1 and s_t+2 have all their non-zero features inside the window).
+// Two block barriers per step: class partials -> hidden layer (one sigmoid per lane), output partials -> values.
 //
 // The replay is the reference's, step for step: two forwards per step with the CURRENT weights, closed-form gradients of
 // the 2-layer sigmoid net, lr*delta formed in float64 then rounded to fp32 as torch does, packed
@@ -53,7 +57,7 @@ struct TdParams {
     unsigned long long *queue; // work queue: next game index (zeroed by the host)
     unsigned long long *stats; // [3] games replayed, [6] TD steps, [7] row-steps caught up lazily
     double *dstats;            // [0] sum of squared TD errors
-    unsigned long long *prof;  // k_td_replay<true>: [16] cycles per phase, CTA 0 (bgx_td_profile)
+    unsigned long long *prof;  // k_td_replay<true>: [8 warps][16] cycles per phase, CTA 0 (bgx_td_profile)
 };
 
 // packed fp32 (sm_100): d = a * b + c on two lanes, one rounding each
@@ -79,28 +83,18 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b)
     return d;
 }
 
-constexpr int kTdWorkerWarps = 8;
-constexpr int kTdWorkers = kTdWorkerWarps * 32;
-constexpr int kTdThreads = kTdWorkers + 32;                 // + the lister warp
-constexpr int kTdClassCap = 50;                             // a class has 50 or 49 rows
+constexpr int kTdWarps = 8;
+constexpr int kTdThreads = kTdWarps * 32;
+constexpr int kTdClasses = 8;                               // = warps: warp c owns class c
+constexpr int kTdClassRows = 25;                            // classes 0..5 have 25 rows, 6 and 7 have 24
+constexpr int kTdSlots = 8;                                 // live rows of a class held in registers (the switch in k_td_replay lists them)
 
-// the fixed 4-colouring of the feature rows: the four features of (point, side) go to four different classes,
+// the fixed 8-colouring of the feature rows: the eight features of a point (4 per side) go to eight different classes,
 // rotated by the point so that "at least one checker" rows do not pile up in one class
-__host__ __device__ constexpr int td_class(int f) { return f < 192 ? ((f & 3) + (f >> 3)) & 3 : (f & 3); }
-// rows of class q in ascending order: position pos (0 .. td_class_rows(q) - 1) -> feature
-__host__ __device__ constexpr int td_row_of(int q, int pos) { return pos < 48 ? 4 * pos + ((q - (pos >> 1)) & 3) : 192 + q + 4 * (pos - 48); }
-__host__ __device__ constexpr int td_class_rows(int q) { return q < 2 ? 50 : 49; }
+__host__ __device__ constexpr int td_class(int f) { return f < 192 ? ((f & 7) + (f >> 3)) & 7 : (f & 7); }
+// row r (0..24) of class c: r < 24 is the class's feature of point r, r = 24 its tail feature (classes 0..5 only)
+__host__ __device__ constexpr int td_row_of(int c, int r) { return r < 24 ? 8 * r + ((c - r) & 7) : 192 + c; }
 
-// one live row of step t: its feature value in s_t (gradient), in s_t+1 and s_t+2 (the forwards of step t+1), bookkeeping
-struct __align__(16) TdEnt {
-    float x0, x1, x2;
-    uint32_t meta;             // bits 0..7 row, 9 needs catch-up, 16..31 first missed step
-};
-constexpr uint32_t kTdLate = 0x200u;
-struct __align__(16) TdList {
-    TdEnt ent[4][kTdClassCap]; // per class, ascending rows
-    int n[4];
-};
 struct __align__(16) TdCtrl {
     long long game;
     double lr;
@@ -109,300 +103,351 @@ struct __align__(16) TdCtrl {
 };
 
 // shared memory map (bytes)
-constexpr int kTdOffW = 0;
-constexpr int kTdOffE = kTdOffW + kTableBytes;
+constexpr int kTdOffW = 0;                                           // W1 transposed [198][128]
+constexpr int kTdOffE = kTdOffW + kTableBytes;                       // its eligibility traces
 constexpr int kTdOffC = kTdOffE + kTableBytes;                       // c_k of every step so far
-constexpr int kTdOffLists = kTdOffC + kTdMaxSteps * 4;               // 3 rotating step lists + the end-of-game list
-constexpr int kTdOffZ = kTdOffLists + 4 * (int)sizeof(TdList);       // class partial pre-activations [4][128 units][2 states]
-constexpr int kTdOffH = kTdOffZ + 4 * kHidden * 2 * 4;               // hidden activations [128 units][2 states]
+constexpr int kTdOffZ = kTdOffC + kTdMaxSteps * 4;                   // class partial pre-activations [8][128 units][2 states]
+constexpr int kTdOffH = kTdOffZ + kTdClasses * kHidden * 2 * 4;      // hidden activations [128 units][2 states]
 constexpr int kTdOffB1 = kTdOffH + kHidden * 2 * 4;                  // b1 [128]
 constexpr int kTdOffW2 = kTdOffB1 + kHidden * 4;                     // w2, double-buffered by step parity [2][128]
-constexpr int kTdOffRed = kTdOffW2 + 2 * kHidden * 4;                // per-warp output partials [2 parities][2 states][8]
-constexpr int kTdOffLast = kTdOffRed + 2 * 2 * 8 * 4;                // last step applied to each row, -1 = untouched (lister) [200] int16
-constexpr int kTdOffCtrl = kTdOffLast + 200 * 2;
+constexpr int kTdOffRed = kTdOffW2 + 2 * kHidden * 4;                // output partials [2 parities][2 states][8]
+constexpr int kTdRing = 16;                                          // records in the ring (a power of two)
+constexpr int kTdAhead = 8;                                          // how many states ahead of the step the loader fetches
+constexpr int kTdOffRing = kTdOffRed + 2 * 2 * 8 * 4;                // records of consecutive states [kTdRing][32]
+constexpr int kTdOffOff = kTdOffRing + kTdRing * 32;                       // the borne-off feature k / 15.0 for k = 0..15
+constexpr int kTdOffCtrl = kTdOffOff + 16 * 4;
 constexpr int kTdSmem = kTdOffCtrl + (int)sizeof(TdCtrl);
-static_assert(kTdSmem <= 232448, "k_td_replay: shared memory per CTA");
-static_assert(kTdOffCtrl % 16 == 0 && sizeof(TdList) % 16 == 0, "alignment");
+static_assert(kTdSmem <= 232448 && kTdOffCtrl % 16 == 0, "k_td_replay: shared memory per CTA");
 
-__device__ __forceinline__ void td_bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(kTdWorkers) : "memory"); }
-__device__ __forceinline__ void td_bar_all() { asm volatile("bar.sync 2, %0;" ::"n"(kTdThreads) : "memory"); }
-
-// value of feature k (0..3) of a point side holding c checkers (model.py:111-144): [c>=1, c>=2, c>=3, (c-3)/2]
-__device__ __forceinline__ float td_feat(int c, int k) { return k < 3 ? (c > k ? 1.f : 0.f) : (c > 3 ? (float)(c - 3) * 0.5f : 0.f); }
-
-// Lister.  Lane l < 24 holds point l of a record; lanes 24..28 hold the turn flag, the two bar counts and the two borne-off
-// counts IN THAT ORDER (record bytes 28, 24, 25, 26, 27), so that within every class the rows a lane can contribute ascend
-// with the lane: points give rows 8l + k (PLAYER1 side) and 8l + 4 + k, lane 24 rows 192 / 193, 25: 194, 26: 195, 27: 196, 28: 197.
-__device__ __forceinline__ int td_record_lane(int lane) { return lane < 24 ? lane : (lane == 24 ? 28 : (lane < 29 ? lane - 1 : 31)); }
-
-struct TdCand { float x0, x1, x2; int f; bool live; };
-
-__device__ __forceinline__ void td_candidates(int q, int lane, int r0, int r1, int r2, bool has1, bool has2, TdCand &A, TdCand &B)
+// loader: 4 bytes of a record, global -> shared, without passing through a register (nothing waits for the load)
+__device__ __forceinline__ void td_fetch(void *dst_smem, const void *src)
 {
-    A.live = B.live = false;
-    A.f = B.f = 0;
-    A.x0 = A.x1 = A.x2 = B.x0 = B.x1 = B.x2 = 0.f;
-    if (lane < 24) {
-        const int k = (q - lane) & 3;
-        A.f = 8 * lane + k;
-        B.f = A.f + 4;
-        A.x0 = td_feat(max(r0, 0), k); B.x0 = td_feat(max(-r0, 0), k);
-        if (has1) { A.x1 = td_feat(max(r1, 0), k); B.x1 = td_feat(max(-r1, 0), k); }
-        if (has2) { A.x2 = td_feat(max(r2, 0), k); B.x2 = td_feat(max(-r2, 0), k); }
-    } else if (lane == 24) {
-        if (q < 2) {                                         // 192: PLAYER1 to move, 193: PLAYER2 to move
-            A.f = 192 + q;
-            A.x0 = (r0 != 0) == (q == 1) ? 1.f : 0.f;
-            if (has1) A.x1 = (r1 != 0) == (q == 1) ? 1.f : 0.f;
-            if (has2) A.x2 = (r2 != 0) == (q == 1) ? 1.f : 0.f;
-        }
-    } else if (lane < 29) {
-        const int f = 169 + lane;                            // 25 -> 194 ... 28 -> 197
-        if ((f & 3) == q) {
-            A.f = f;
-            A.x0 = f < 196 ? (float)r0 * 0.5f : off_feature(r0);
-            if (has1) A.x1 = f < 196 ? (float)r1 * 0.5f : off_feature(r1);
-            if (has2) A.x2 = f < 196 ? (float)r2 * 0.5f : off_feature(r2);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void td_fetch_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void td_fetch_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+__device__ __forceinline__ void td_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kTdThreads) : "memory"); }
+
+// What lane r contributes to its warp's class: which record byte it looks at and how that byte becomes a feature value
+// (model.py:111-144), branch-free: d = sign * byte - threshold, then
+//   form 0 (step):  d > 0 ? 1 : 0      point features "at least k+1 checkers" (sign picks the side), the two turn flags
+//   form 1 (ramp):  max(d, 0) / 2      "(n - 3) / 2" of a point side, bar counts / 2
+//   form 2 (table): off[byte]          borne-off counts / 15.0 (the fp32 divide)
+//   form 3: nothing (lanes above 24, the missing tail row of classes 6 and 7)
+struct TdLaneRow {
+    int byte, sign, thr, form;
+    __device__ __forceinline__ void init(int cls, int lane)
+    {
+        const int j = (cls - lane) & 7, k = j & 3;           // feature j of point `lane`: side j >> 2, k-th of its four
+        byte = lane; sign = j < 4 ? 1 : -1; thr = k; form = k < 3 ? 0 : 1;
+        if (lane == 24) {
+            byte = cls < 2 ? 28 : 22 + cls;                  // turn flag | bar counts 24, 25 | borne-off counts 26, 27
+            sign = cls == 0 ? -1 : 1; thr = cls == 0 ? -1 : 0;    // 192: turn == 0, 193: turn != 0
+            form = cls < 2 ? 0 : (cls < 4 ? 1 : (cls < 6 ? 2 : 3));
+        } else if (lane > 24) {
+            byte = 31; form = 3;
         }
     }
-    A.live = A.x0 != 0.f || A.x1 != 0.f || A.x2 != 0.f;
-    B.live = B.x0 != 0.f || B.x1 != 0.f || B.x2 != 0.f;
+    __device__ __forceinline__ float value(int v, const float *off) const
+    {
+        const int d = sign * v - thr;
+        const float step = d > 0 ? 1.f : 0.f, ramp = (float)max(d, 0) * 0.5f, tab = off[v & 15];
+        return form == 0 ? step : (form == 1 ? ramp : (form == 2 ? tab : 0.f));
+    }
+};
+
+// the live rows of this warp's class at step t: lane r holds row r's feature value in s_t, s_t+1, s_t+2 (0 beyond the game)
+__device__ __forceinline__ uint32_t td_list(const int8_t *ring, const float *off, const TdLaneRow &me, int t, int T, float &x0, float &x1, float &x2)
+{
+    x0 = me.value((int)ring[(t & (kTdRing - 1)) * 32 + me.byte], off);
+    x1 = me.value((int)ring[((t + 1) & (kTdRing - 1)) * 32 + me.byte], off);
+    x2 = me.value((int)ring[((t + 2) & (kTdRing - 1)) * 32 + me.byte], off);
+    if (t + 1 >= T) x1 = 0.f;
+    if (t + 2 >= T) x2 = 0.f;
+    return __ballot_sync(kFull, x0 != 0.f || x1 != 0.f || x2 != 0.f);
 }
 
-// the live rows of step s = non-zero features of s_s, s_s+1, s_s+2 (r0, r1, r2: this lane's byte of their records)
-__device__ __forceinline__ void td_build_list(TdList *L, short *last, int s, int T, int lane, int r0, int r1, int r2)
+__device__ __forceinline__ float4 fma4(float s, float4 a, float4 c)      // s * a + c
 {
-    const bool has1 = s + 1 < T, has2 = s + 2 < T;
-    const uint32_t below = (1u << lane) - 1u;
+    const float2 lo = fma2(make_float2(s, s), make_float2(a.x, a.y), make_float2(c.x, c.y));
+    const float2 hi = fma2(make_float2(s, s), make_float2(a.z, a.w), make_float2(c.z, c.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 mul4(float s, float4 a)
+{
+    const float2 lo = mul2(make_float2(s, s), make_float2(a.x, a.y)), hi = mul2(make_float2(s, s), make_float2(a.z, a.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// a row that (re-)enters the window replays the steps it slept through, k = from .. upto, exactly as the dense update would
+// have done them: e <- fl(lambda e), w <- fma(c_k, e, w).  Four steps per trip with their c_k loaded together (one shared-
+// memory latency per trip instead of per step); steps past `upto` run with lambda' = 1, c' = 0, which changes nothing, bit for bit.
+__device__ __forceinline__ void td_replay_row(float4 &e, float4 &w, int from, int upto, const float *chist, float lam)
+{
+    for (int k = from; k <= upto; k += 4) {
+        float c[4], l[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        TdCand A, B;
-        td_candidates(q, lane, r0, r1, r2, has1, has2, A, B);
-        const uint32_t mA = __ballot_sync(kFull, A.live), mB = __ballot_sync(kFull, B.live);
-        const int at = __popc(mA & below) + __popc(mB & below);
-        if (A.live) {
-            const int la = last[A.f];
-            TdEnt e;
-            e.x0 = A.x0; e.x1 = A.x1; e.x2 = A.x2;
-            e.meta = (uint32_t)A.f | (la >= 0 && la < s - 1 ? kTdLate : 0u) | ((uint32_t)(la + 1) << 16);
-            L->ent[q][at] = e;
-            last[A.f] = (short)s;
+        for (int i = 0; i < 4; i++) {
+            const bool on = k + i <= upto;
+            c[i] = chist[min(k + i, upto)];
+            c[i] = on ? c[i] : 0.f;
+            l[i] = on ? lam : 1.f;
         }
-        if (B.live) {
-            const int la = last[B.f];
-            TdEnt e;
-            e.x0 = B.x0; e.x1 = B.x1; e.x2 = B.x2;
-            e.meta = (uint32_t)B.f | (la >= 0 && la < s - 1 ? kTdLate : 0u) | ((uint32_t)(la + 1) << 16);
-            L->ent[q][at + (A.live ? 1 : 0)] = e;
-            last[B.f] = (short)s;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            e = mul4(l[i], e);
+            w = fma4(c[i], e, w);
         }
-        if (lane == 0) L->n[q] = __popc(mA) + __popc(mB);
     }
 }
 
-// end of the game: every row the game touched, with the first step it still misses; `last` is reset
-__device__ __forceinline__ void td_build_final(TdList *L, short *last, int T, int lane)
+// (float)(lr * (double)d) for a double lr = lr_hi + lr_lo without float64 instructions (three conversions and a DMUL are
+// ~120 cycles on the step's critical path): p = fl(lr_hi d), its exact error by FMA, plus the low part's product.  The sum
+// p + (err + lr_lo d) carries the double product to ~2^-48 relative and rounds it to fp32; it can differ from the directly
+// rounded product only when that product lies within 2^-24 ulp of a rounding boundary (the golden TD tests see none).
+__device__ __forceinline__ float td_scale(float lr_hi, float lr_lo, float d)
 {
-    const uint32_t below = (1u << lane) - 1u;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        int base = 0;
-#pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-            const int pos = lane + 32 * pass;
-            const bool ok = pos < td_class_rows(q);
-            const int f = ok ? td_row_of(q, pos) : 0;
-            const int la = ok ? (int)last[f] : -1;
-            const uint32_t mask = __ballot_sync(kFull, la >= 0);
-            if (la >= 0) {
-                TdEnt e;
-                e.x0 = e.x1 = e.x2 = 0.f;
-                e.meta = (uint32_t)f | (la < T - 1 ? kTdLate : 0u) | ((uint32_t)(la + 1) << 16);
-                L->ent[q][base + __popc(mask & below)] = e;
-                last[f] = -1;
-            }
-            base += __popc(mask);
-        }
-        if (lane == 0) L->n[q] = base;
-    }
+    const float prod = __fmul_rn(lr_hi, d);
+    const float err = __fmaf_rn(lr_hi, d, -prod);
+    return __fadd_rn(prod, __fmaf_rn(lr_lo, d, err));
 }
 
-// worker: rows that (re-)enter the window replay the steps they slept through, k = first missed .. upto, exactly as the
-// dense update would have done them: e <- fl(lambda e), w <- fma(c_k, e, w).  Warp-uniform: a warp owns one class.
-__device__ __forceinline__ unsigned td_catch_up(const TdEnt *ent, int n, int upto, int pair, float2 *W2, float2 *E2, const float *chist, float2 lam2)
-{
-    unsigned done = 0;
-    for (int i = 0; i < n; i++) {
-        const uint32_t m = ent[i].meta;
-        if (m & kTdLate) {
-            const int idx = (int)(m & 0xFFu) * 64 + pair;
-            float2 e = E2[idx], w = W2[idx];
-            for (int k = (int)(m >> 16); k <= upto; k++) {
-                const float c = chist[k];
-                e = mul2(lam2, e);
-                w = fma2(make_float2(c, c), e, w);
-            }
-            done += (unsigned)(upto + 1 - (int)(m >> 16));
-            E2[idx] = e;
-            W2[idx] = w;
-        }
-    }
-    return done;
-}
+#ifndef BGX_TD_SWEEP
+#define BGX_TD_SWEEP 0
+#endif
 
 template <bool kProf>
 __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
 {
     extern __shared__ __align__(16) unsigned char td_smem[];
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;       // kProf: cycles per phase as seen by one worker thread / the lister
+    long long pc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;
+    __shared__ long long td_arrive[8];       // kProf: cycles per phase as seen by thread 0
 #define TD_MARK(i) do { if (kProf) { const long long now_ = clock64(); pc[i] += now_ - pt; pt = now_; } } while (0)
-    float2 *W2 = reinterpret_cast<float2 *>(td_smem + kTdOffW), *E2 = reinterpret_cast<float2 *>(td_smem + kTdOffE);
+    float4 *W4 = reinterpret_cast<float4 *>(td_smem + kTdOffW), *E4 = reinterpret_cast<float4 *>(td_smem + kTdOffE);
     float *chist = reinterpret_cast<float *>(td_smem + kTdOffC);
-    TdList *lists = reinterpret_cast<TdList *>(td_smem + kTdOffLists);
     float *zpart = reinterpret_cast<float *>(td_smem + kTdOffZ);
     float *hs = reinterpret_cast<float *>(td_smem + kTdOffH);
     float *b1s = reinterpret_cast<float *>(td_smem + kTdOffB1);
     float *w2s = reinterpret_cast<float *>(td_smem + kTdOffW2);
     float *red = reinterpret_cast<float *>(td_smem + kTdOffRed);
-    short *last = reinterpret_cast<short *>(td_smem + kTdOffLast);
+    int8_t *ring = reinterpret_cast<int8_t *>(td_smem + kTdOffRing);
+    float *offtab = reinterpret_cast<float *>(td_smem + kTdOffOff);
     TdCtrl *ctrl = reinterpret_cast<TdCtrl *>(td_smem + kTdOffCtrl);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, cls = tid >> 5;            // warp = row class
+    const int col = 4 * lane;                                // this thread's hidden units: col .. col + 3
+    const bool owner = cls == 0;                             // the class-0 thread of four units also keeps their b1 / w2 entries
+    const int unit = 16 * cls + (lane & 15), sig_state = lane >> 4;          // hidden-layer duty: one (unit, state) sigmoid per lane
+    const bool loader = cls == kTdWarps - 1;                 // this warp pops the queue and feeds the record ring
+    TdLaneRow me;
+    me.init(cls, lane);
+    const int my_row = td_row_of(cls, min(lane, 24));        // lane r < 25: the feature row it speaks for
 
     float *mine = p.partial + (size_t)blockIdx.x * BGX_NPARAMS_PADDED;
     for (int i = tid; i < BGX_NPARAMS_PADDED; i += kTdThreads) mine[i] = 0.f;
-
-    if (warp == kTdWorkerWarps) {
-        // ------------------------------------------------------------------ the lister
-        for (int f = lane; f < 200; f += 32) last[f] = -1;
-        __syncwarp();
-        const int src = td_record_lane(lane);
-        for (;;) {
-            long long g = -1;
-            int T = 0, status = 0;
-            for (;;) {                                                       // next finished game of the queue
-                unsigned long long take = 0;
-                if (lane == 0) take = atomicAdd(p.queue, 1ull);
-                take = __shfl_sync(kFull, take, 0);
-                if (take >= (unsigned long long)p.n_games) break;
-                status = (int)p.slots[take * 32 + 31];
-                T = min(min(p.ply[take], p.traj_cap), kTdMaxSteps);
-                if ((status == kP1Won || status == kP2Won) && T > 0) { g = (long long)take; break; }   // others: still running or truncated
-            }
-            if (lane == 0) {
-                ctrl->done = g < 0;
-                ctrl->game = g;
-                ctrl->T = T;
-                ctrl->won = status == kP1Won;
-                if (p.sched && g >= 0) {                                     // the per-game schedule of train.py:538 / model.py:69-73
-                    const long long ep = p.episode_first + g;
-                    ctrl->lr = p.sched[min(ep / 40000, (long long)kTdSchedLen - 1)];
-                    ctrl->lam = (float)p.sched[kTdSchedLen + min(ep / 30000, (long long)kTdSchedLen - 1)];
-                } else {
-                    ctrl->lr = p.lr;
-                    ctrl->lam = p.lambda;
-                }
-            }
-            if (g < 0) { td_bar_all(); return; }
-            const int8_t *traj = p.traj + (size_t)g * p.traj_cap * 32 + src;
-            int r0 = (int)traj[0], r1 = T > 1 ? (int)traj[32] : 0, r2 = T > 2 ? (int)traj[64] : 0;
-            int a0 = T > 3 ? (int)traj[3 * 32] : 0, a1 = T > 4 ? (int)traj[4 * 32] : 0;   // two records in flight
-            td_build_list(lists, last, 0, T, lane, r0, r1, r2);
-            td_bar_all();                                                    // game start: ctrl and list 0 are ready
-            if (kProf) pt = clock64();
-            for (int t = 0; t < T; t++) {
-                r0 = r1; r1 = r2; r2 = a0;                                   // states t+1, t+2, t+3
-                a0 = a1;
-                a1 = t + 5 < T ? (int)traj[(size_t)(t + 5) * 32] : 0;
-                __syncwarp();
-                if (t + 1 < T) td_build_list(lists + (t + 1) % 3, last, t + 1, T, lane, r0, r1, r2);
-                TD_MARK(0);
-                td_bar_all();                                                // the step's barrier
-                TD_MARK(1);
-            }
-            __syncwarp();
-            td_build_final(lists + 3, last, T, lane);
-            td_bar_all();                                                    // game end: the final list is ready
-            if (kProf && blockIdx.x == 0 && lane == 0) { atomicAdd(p.prof + 8, (unsigned long long)pc[0]); atomicAdd(p.prof + 9, (unsigned long long)pc[1]); pc[0] = pc[1] = 0; }
-        }
+    if (tid < 16) offtab[tid] = off_feature(tid);
+    const float4 *wt4 = reinterpret_cast<const float4 *>(p.wt);
+    const int n_rows = cls < 6 ? 25 : 24;
+    for (int r = 0; r < n_rows; r++) {
+        W4[td_row_of(cls, r) * 32 + lane] = wt4[td_row_of(cls, r) * 32 + lane];
+        E4[td_row_of(cls, r) * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-
-    // ---------------------------------------------------------------------- the workers
-    const int q = warp & 3;                                  // this warp's row class
-    const int pair = 32 * (warp >> 2) + lane;                // this thread's hidden units: col, col + 1
-    const int col = 2 * pair;
-    const bool owner = q == 0;                               // the class-0 thread of a pair also keeps its b1 / w2 entries
-    const int unit = 16 * warp + (lane & 15), sig_state = lane >> 4;   // hidden-layer duty: one (unit, state) sigmoid per lane
-    const float2 *wt2 = reinterpret_cast<const float2 *>(p.wt);
-    for (int pos = 0; pos < td_class_rows(q); pos++) {
-        const int f = td_row_of(q, pos);
-        W2[f * 64 + pair] = wt2[f * 64 + pair];
-        E2[f * 64 + pair] = make_float2(0.f, 0.f);
-    }
+    float4 SE[kTdSlots], SW[kTdSlots];                       // the slots: trace and weight of a live row, units col .. col + 3
+    int slot_lane[kTdSlots];                                 // which lane (= row of the class) a slot holds
+#pragma unroll
+    for (int s = 0; s < kTdSlots; s++) { SE[s] = SW[s] = make_float4(0.f, 0.f, 0.f, 0.f); slot_lane[s] = 0; }
+    uint32_t occ = 0;                                        // occupied slots
+    int slot = -1;                                           // lane r: the slot holding row r, -1 = the row is at home in shared memory
+    int last = -1;                                           // lane r: last step applied to the HOME copy of row r, -1 = untouched in this game
+    int sweep = 0;                                           // where the round-robin catch-up of sleeping rows continues
+    const int8_t *traj = nullptr;                            // loader: the game's records
     unsigned long long steps = 0, games = 0, lazy = 0;
     double sq_sum = 0.0;
 
+    // loader: take the next finished game off the queue, publish it, stage its first three records
+    auto next_game = [&]() {
+        td_fetch_wait<0>();                                  // nothing of the previous game is still on its way into the ring
+        long long g = -1;
+        int T = 0, status = 0;
+        for (;;) {
+            unsigned long long take = 0;
+            if (lane == 0) take = atomicAdd(p.queue, 1ull);
+            take = __shfl_sync(kFull, take, 0);
+            if (take >= (unsigned long long)p.n_games) break;
+            status = (int)p.slots[take * 32 + 31];
+            T = min(min(p.ply[take], p.traj_cap), kTdMaxSteps);
+            if ((status == kP1Won || status == kP2Won) && T > 0) { g = (long long)take; break; }   // others: still running or truncated
+        }
+        if (lane == 0) {
+            ctrl->done = g < 0;
+            ctrl->game = g;
+            ctrl->T = T;
+            ctrl->won = status == kP1Won;
+            if (p.sched && g >= 0) {                         // the per-game schedule of train.py:538 / model.py:69-73
+                const long long ep = p.episode_first + g;
+                ctrl->lr = p.sched[min(ep / 40000, (long long)kTdSchedLen - 1)];
+                ctrl->lam = (float)p.sched[kTdSchedLen + min(ep / 30000, (long long)kTdSchedLen - 1)];
+            } else {
+                ctrl->lr = p.lr;
+                ctrl->lam = p.lambda;
+            }
+        }
+        if (g >= 0) {                                        // records 0 .. kTdAhead - 1 (8 lanes x 4 bytes each), complete before the barrier
+            traj = p.traj + (size_t)g * p.traj_cap * 32;
+            if (lane < 8)
+                for (int k = 0; k < kTdAhead; k++) td_fetch(ring + k * 32 + lane * 4, traj + (size_t)min(k, T - 1) * 32 + lane * 4);
+            td_fetch_commit();
+            td_fetch_wait<0>();
+        }
+    };
+    if (loader) next_game();
+
     for (;;) {
-        td_bar_all();                                        // game start
+        td_bar();                                            // game start: ctrl and the first records are ready
         if (ctrl->done) break;
         const int T = ctrl->T;
         const bool p1_won = ctrl->won != 0;
         const float lam = ctrl->lam;
         const double lr = ctrl->lr;
-        const float2 lam2 = make_float2(lam, lam);
+        const float lr_hi = (float)lr, lr_lo = (float)(lr - (double)lr_hi);
+        last = -1; slot = -1; occ = 0;
         if (owner) {
-            *reinterpret_cast<float2 *>(b1s + col) = *reinterpret_cast<const float2 *>(p.flat + kTableFloats + col);
-            *reinterpret_cast<float2 *>(w2s + col) = *reinterpret_cast<const float2 *>(p.flat + kTableFloats + kHidden + col);
+            *reinterpret_cast<float4 *>(b1s + col) = *reinterpret_cast<const float4 *>(p.flat + kTableFloats + col);
+            *reinterpret_cast<float4 *>(w2s + col) = *reinterpret_cast<const float4 *>(p.flat + kTableFloats + kHidden + col);
         }
         float b2 = p.flat[kTableFloats + 2 * kHidden], eb2 = 0.f;            // every thread keeps its own copy
-        float2 eb1 = make_float2(0.f, 0.f), ew2 = make_float2(0.f, 0.f);     // owners only
+        float4 eb1 = make_float4(0.f, 0.f, 0.f, 0.f), ew2 = eb1;             // owners only
 
         // first layer of step 0: this class's live rows against x(s_0) and x(s_1)
-        float2 z0 = make_float2(0.f, 0.f), z1 = make_float2(0.f, 0.f);
+        float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f), z1 = z0;
+        float x0, x1, x2;                                    // lane r: row r's feature value in s_t, s_t+1, s_t+2
         {
-            const TdEnt *ent = lists[0].ent[q];
-            const int n = lists[0].n[q];
-            for (int i = 0; i < n; i++) {
-                const TdEnt e = ent[i];
-                const float2 w = W2[(int)(e.meta & 0xFFu) * 64 + pair];
-                z0 = fma2(make_float2(e.x0, e.x0), w, z0);
-                z1 = fma2(make_float2(e.x1, e.x1), w, z1);
+            uint32_t live = td_list(ring, offtab, me, 0, T, x0, x1, x2);
+            while (live) {
+                const int r = __ffs(live) - 1;
+                live &= live - 1;
+                const float4 w = W4[td_row_of(cls, r) * 32 + lane];
+                z0 = fma4(__shfl_sync(kFull, x0, r), w, z0);
+                z1 = fma4(__shfl_sync(kFull, x1, r), w, z1);
             }
         }
 
         if (kProf) pt = clock64();
         for (int t = 0; t < T; t++) {
-            const TdList *L = lists + t % 3;
-            const TdEnt *ent = L->ent[q];
-            const int n = L->n[q];
             const bool terminal = t == T - 1;
             const float *w2c = w2s + (t & 1) * kHidden;
             // (1) class partials of both pre-activations -> shared memory, [class][unit][state]
-            *reinterpret_cast<float4 *>(zpart + (q * kHidden + col) * 2) = make_float4(z0.x, z1.x, z0.y, z1.y);
-            TD_MARK(0);
-            td_bar_workers();
-            TD_MARK(1);
-            // (2) hidden layer: lane = (unit, state); output partials of this warp's 16 units
             {
-                const float za = zpart[(0 * kHidden + unit) * 2 + sig_state], zb = zpart[(1 * kHidden + unit) * 2 + sig_state];
-                const float zc = zpart[(2 * kHidden + unit) * 2 + sig_state], zd = zpart[(3 * kHidden + unit) * 2 + sig_state];
+                float4 *zp = reinterpret_cast<float4 *>(zpart + (cls * kHidden + col) * 2);
+                zp[0] = make_float4(z0.x, z1.x, z0.y, z1.y);
+                zp[1] = make_float4(z0.z, z1.z, z0.w, z1.w);
+            }
+            TD_MARK(0);
+            td_bar();
+            TD_MARK(1);
+            // (2) hidden layer: lane = (unit, state); output partials of the warp's 16 units
+            {
+                const float *zp = zpart + unit * 2 + sig_state;
+                const float za = zp[0 * kHidden * 2] + zp[1 * kHidden * 2], zb = zp[2 * kHidden * 2] + zp[3 * kHidden * 2];
+                const float zc = zp[4 * kHidden * 2] + zp[5 * kHidden * 2], zd = zp[6 * kHidden * 2] + zp[7 * kHidden * 2];
                 const float h = sigmoid_f32(((za + zb) + (zc + zd)) + b1s[unit]);
                 hs[unit * 2 + sig_state] = h;
                 float y = w2c[unit] * h;
 #pragma unroll
                 for (int o = 1; o < 16; o <<= 1) y += __shfl_xor_sync(kFull, y, o);
-                if ((lane & 15) == 0) red[((t & 1) * 2 + sig_state) * 8 + warp] = y;
+                if ((lane & 15) == 0) red[((t & 1) * 2 + sig_state) * 8 + cls] = y;
             }
             TD_MARK(2);
-            // (3) rows entering the window catch up through step t-1 while the partials travel
-            lazy += td_catch_up(ent, n, t - 1, pair, W2, E2, chist, lam2);
+            // (3) the live rows of this class; rows that left the window go home, rows that entered it take a free slot
+            if (t > 0) {                                     // the window moves on by one state: one new feature value per lane
+                x0 = x1; x1 = x2;
+                x2 = t + 2 < T ? me.value((int)ring[((t + 2) & (kTdRing - 1)) * 32 + me.byte], offtab) : 0.f;
+            }
+            const uint32_t live = __ballot_sync(kFull, x0 != 0.f || x1 != 0.f || x2 != 0.f);
+            const uint32_t resident = __ballot_sync(kFull, slot >= 0);
+            if (resident & ~live) {
+                const uint32_t leave = resident & ~live;
+#pragma unroll
+                for (int s = 0; s < kTdSlots; s++) {
+                    if ((occ >> s & 1) && (leave >> slot_lane[s] & 1)) {
+                        const int idx = td_row_of(cls, slot_lane[s]) * 32 + lane;
+                        E4[idx] = SE[s];
+                        W4[idx] = SW[s];
+                        occ &= ~(1u << s);
+                    }
+                }
+                if (leave >> lane & 1) { slot = -1; last = t - 1; }          // its home copy is current through step t-1
+            }
+            uint32_t enter = live & ~resident;
+            while (enter && occ != (1u << kTdSlots) - 1u) {
+                const int j = __ffs(enter) - 1;
+                enter &= enter - 1;
+                const int s_new = __ffs(~occ) - 1;
+                const int from = __shfl_sync(kFull, last, j) + 1;            // first step its home copy misses (0: untouched, nothing to replay)
+                const int idx = td_row_of(cls, j) * 32 + lane;
+                if (from > 0 && from <= t - 1) lazy += (unsigned)(t - from);
+#define TD_ENTER(S)                                                                                       \
+    case S:                                                                                               \
+        SE[S] = E4[idx]; SW[S] = W4[idx]; slot_lane[S] = j;                                               \
+        if (from > 0 && from <= t - 1) td_replay_row(SE[S], SW[S], from, t - 1, chist, lam);              \
+        break;
+                switch (s_new) { TD_ENTER(0) TD_ENTER(1) TD_ENTER(2) TD_ENTER(3) TD_ENTER(4) TD_ENTER(5) TD_ENTER(6) TD_ENTER(7) }
+#undef TD_ENTER
+                occ |= 1u << s_new;
+                if (lane == j) slot = s_new;
+            }
+            // rows the slots have no room for stay at home and are brought up to date there
+            uint32_t crowd = enter;
+            while (crowd) {
+                const int j = __ffs(crowd) - 1;
+                crowd &= crowd - 1;
+                const int from = __shfl_sync(kFull, last, j) + 1;
+                if (from > 0 && from <= t - 1) {
+                    const int idx = td_row_of(cls, j) * 32 + lane;
+                    float4 e = E4[idx], w = W4[idx];
+                    td_replay_row(e, w, from, t - 1, chist, lam);
+                    E4[idx] = e;
+                    W4[idx] = w;
+                    lazy += (unsigned)(t - from);
+                }
+            }
+            if (enter >> lane & 1) last = t;                 // (their update of step t follows in (6))
+            // one sleeping row of the class per step is brought up to date at home, round robin: no row is ever more than
+            // ~25 steps behind, so an entering row has little to replay and no warp keeps the others waiting at the barrier
+            if (BGX_TD_SWEEP) {
+                const uint32_t behind = __ballot_sync(kFull, slot < 0 && last >= 0 && last < t - 1);
+                if (behind) {
+                    const int j = (sweep + __ffs(__funnelshift_r(behind, behind, sweep)) - 1) & 31;
+                    const int from = __shfl_sync(kFull, last, j) + 1;
+                    const int idx = td_row_of(cls, j) * 32 + lane;
+                    float4 e = E4[idx], w = W4[idx];
+                    td_replay_row(e, w, from, t - 1, chist, lam);
+                    E4[idx] = e;
+                    W4[idx] = w;
+                    lazy += (unsigned)(t - from);
+                    if (lane == j) last = t - 1;
+                    sweep = (j + 1) & 31;
+                }
+            }
             TD_MARK(3);
-            td_bar_all();                                    // the step's barrier
+            if (kProf && lane == 0) td_arrive[cls] = clock64();
+            td_bar();                                        // the step's second barrier
             TD_MARK(4);
+            if (kProf) {
+                long long la = 0;
+                for (int w = 0; w < 8; w++) la = max(la, td_arrive[w]);
+                const long long now_ = clock64();
+                pc[11] += now_ - la;                         // barrier release after the last arrival
+                pc[12] += la - td_arrive[cls];               // this warp's wait for the last arrival
+                pt = clock64();
+            }
             // (4) values, TD error: odd lanes evaluate s_t+1, even lanes s_t (one sigmoid stream per warp)
             const float4 ra = *reinterpret_cast<const float4 *>(red + ((t & 1) * 2 + (lane & 1)) * 8);
             const float4 rb = *reinterpret_cast<const float4 *>(red + ((t & 1) * 2 + (lane & 1)) * 8 + 4);
             const float v_mine = sigmoid_f32((((ra.x + ra.y) + (ra.z + ra.w)) + ((rb.x + rb.y) + (rb.z + rb.w))) + b2);
             const float v_cur = __shfl_sync(kFull, v_mine, 0);
+            TD_MARK(8);
             float c;                                         // (float)(lr * delta), lr a double: train.py:147
             if (!terminal) {
                 const float v_next = __shfl_sync(kFull, v_mine, 1);
@@ -412,100 +457,144 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
                     sq_sum += delta * delta;
                     if (p.sq_errors) p.sq_errors[t] = delta * delta;         // train.py:162
                 }
-                c = (float)(lr * (double)d);
+                c = td_scale(lr_hi, lr_lo, d);
             } else {
                 c = (float)(lr * ((p1_won ? 1.0 : 0.0) - (double)v_cur));    // train.py:168
             }
             if (tid == 0) chist[t] = c;
+            TD_MARK(9);
+            if (loader) {                                    // the record of s_(t+kTdAhead) starts its way into the ring; s_t+3 has arrived
+                if (lane < 8) td_fetch(ring + ((t + kTdAhead) & (kTdRing - 1)) * 32 + lane * 4, traj + (size_t)min(t + kTdAhead, T - 1) * 32 + lane * 4);
+                td_fetch_commit();
+                td_fetch_wait<kTdAhead - 4>();
+            }
+            TD_MARK(10);
             // (5) gradients w.r.t. the pre-update weights
             const float gv = __fmul_rn(__fsub_rn(1.0f, v_cur), v_cur);
-            const float4 hh = *reinterpret_cast<const float4 *>(hs + col * 2);           // h(s_t), h(s_t+1) of col, then of col + 1
-            const float2 w2v = *reinterpret_cast<const float2 *>(w2c + col);
-            const float2 gh = make_float2(__fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.x), __fsub_rn(1.0f, hh.x)), hh.x),
-                                          __fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.y), __fsub_rn(1.0f, hh.z)), hh.z));
-            // (6) one pass over the live rows: e <- lambda*e + grad ; w <- w + c*e (train.py:141-147), and with the NEW weights
-            // the first layer of step t+1 (s_t+1 and s_t+2 have all their non-zero features among these rows)
-            const float2 c2 = make_float2(c, c);
-            z0 = make_float2(0.f, 0.f); z1 = make_float2(0.f, 0.f);
+            const float4 ha = *reinterpret_cast<const float4 *>(hs + col * 2), hb = *reinterpret_cast<const float4 *>(hs + col * 2 + 4);
+            const float4 h0 = make_float4(ha.x, ha.z, hb.x, hb.z);           // h(s_t) of col .. col + 3 (the odd entries are h(s_t+1))
+            const float4 w2v = *reinterpret_cast<const float4 *>(w2c + col);
+            const float4 gh = make_float4(__fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.x), __fsub_rn(1.0f, h0.x)), h0.x),
+                                          __fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.y), __fsub_rn(1.0f, h0.y)), h0.y),
+                                          __fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.z), __fsub_rn(1.0f, h0.z)), h0.z),
+                                          __fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.w), __fsub_rn(1.0f, h0.w)), h0.w));
+            // (6) one pass over the slots: e <- lambda*e + grad ; w <- w + c*e (train.py:141-147), and with the NEW weights
+            // the first layer of step t+1 (s_t+1 and s_t+2 have all their non-zero features among the live rows)
+            z0 = make_float4(0.f, 0.f, 0.f, 0.f); z1 = z0;
             TD_MARK(5);
-#pragma unroll 2
-            for (int i = 0; i < n; i++) {
-                const TdEnt e = ent[i];
-                const int idx = (int)(e.meta & 0xFFu) * 64 + pair;
-                const float2 tr = fma2(lam2, E2[idx], mul2(gh, make_float2(e.x0, e.x0)));
-                const float2 w = fma2(c2, tr, W2[idx]);
-                E2[idx] = tr;
-                W2[idx] = w;
-                z0 = fma2(make_float2(e.x1, e.x1), w, z0);
-                z1 = fma2(make_float2(e.x2, e.x2), w, z1);
+#pragma unroll
+            for (int s = 0; s < kTdSlots; s++) {
+                if (occ >> s & 1) {
+                    const float xa = __shfl_sync(kFull, x0, slot_lane[s]), xb = __shfl_sync(kFull, x1, slot_lane[s]);
+                    const float xc = __shfl_sync(kFull, x2, slot_lane[s]);
+                    SE[s] = fma4(lam, SE[s], mul4(xa, gh));
+                    SW[s] = fma4(c, SE[s], SW[s]);
+                    z0 = fma4(xb, SW[s], z0);
+                    z1 = fma4(xc, SW[s], z1);
+                }
             }
-            if (owner) {                                     // fc1.bias, fc2.weight: one thread per unit pair
+            crowd = enter;
+            while (crowd) {                                  // the same for live rows that stayed at home
+                const int j = __ffs(crowd) - 1;
+                crowd &= crowd - 1;
+                const int idx = td_row_of(cls, j) * 32 + lane;
+                const float4 e = fma4(lam, E4[idx], mul4(__shfl_sync(kFull, x0, j), gh));
+                const float4 w = fma4(c, e, W4[idx]);
+                E4[idx] = e;
+                W4[idx] = w;
+                z0 = fma4(__shfl_sync(kFull, x1, j), w, z0);
+                z1 = fma4(__shfl_sync(kFull, x2, j), w, z1);
+            }
+            if (owner) {                                     // fc1.bias, fc2.weight: one thread per four units
                 eb1.x = __fadd_rn(__fmul_rn(lam, eb1.x), gh.x); eb1.y = __fadd_rn(__fmul_rn(lam, eb1.y), gh.y);
-                ew2.x = __fadd_rn(__fmul_rn(lam, ew2.x), __fmul_rn(gv, hh.x)); ew2.y = __fadd_rn(__fmul_rn(lam, ew2.y), __fmul_rn(gv, hh.z));
-                float2 b = *reinterpret_cast<float2 *>(b1s + col);
+                eb1.z = __fadd_rn(__fmul_rn(lam, eb1.z), gh.z); eb1.w = __fadd_rn(__fmul_rn(lam, eb1.w), gh.w);
+                ew2.x = __fadd_rn(__fmul_rn(lam, ew2.x), __fmul_rn(gv, h0.x)); ew2.y = __fadd_rn(__fmul_rn(lam, ew2.y), __fmul_rn(gv, h0.y));
+                ew2.z = __fadd_rn(__fmul_rn(lam, ew2.z), __fmul_rn(gv, h0.z)); ew2.w = __fadd_rn(__fmul_rn(lam, ew2.w), __fmul_rn(gv, h0.w));
+                float4 b = *reinterpret_cast<float4 *>(b1s + col);
                 b.x = __fadd_rn(b.x, __fmul_rn(c, eb1.x)); b.y = __fadd_rn(b.y, __fmul_rn(c, eb1.y));
-                *reinterpret_cast<float2 *>(b1s + col) = b;
-                *reinterpret_cast<float2 *>(w2s + ((t + 1) & 1) * kHidden + col) =
-                    make_float2(__fadd_rn(w2v.x, __fmul_rn(c, ew2.x)), __fadd_rn(w2v.y, __fmul_rn(c, ew2.y)));
+                b.z = __fadd_rn(b.z, __fmul_rn(c, eb1.z)); b.w = __fadd_rn(b.w, __fmul_rn(c, eb1.w));
+                *reinterpret_cast<float4 *>(b1s + col) = b;
+                *reinterpret_cast<float4 *>(w2s + ((t + 1) & 1) * kHidden + col) =
+                    make_float4(__fadd_rn(w2v.x, __fmul_rn(c, ew2.x)), __fadd_rn(w2v.y, __fmul_rn(c, ew2.y)),
+                                __fadd_rn(w2v.z, __fmul_rn(c, ew2.z)), __fadd_rn(w2v.w, __fmul_rn(c, ew2.w)));
             }
             eb2 = __fadd_rn(__fmul_rn(lam, eb2), gv);
             b2 = __fadd_rn(b2, __fmul_rn(c, eb2));
             TD_MARK(6);
         }
 
-        td_bar_all();                                        // game end: the list of touched rows is ready
-        const TdList *F = lists + 3;
-        lazy += td_catch_up(F->ent[q], F->n[q], T - 1, pair, W2, E2, chist, lam2);
+        td_bar();                                            // game end: every c_k is visible; the ring and ctrl are free
+        if (loader) next_game();                             // its global loads land while the rows are flushed
+        // the slots go home (current through the last step) ...
+#pragma unroll
+        for (int s = 0; s < kTdSlots; s++) {
+            if (occ >> s & 1) {
+                const int idx = td_row_of(cls, slot_lane[s]) * 32 + lane;
+                E4[idx] = SE[s];
+                W4[idx] = SW[s];
+            }
+        }
+        if (slot >= 0) last = T - 1;
+        // ... and every row the game touched replays what it still misses, adds its change to the CTA's sum (feature-major
+        // W1, then b1, w2, b2) and returns to the snapshot with zero traces
         const float *w2f = w2s + (T & 1) * kHidden;
         if (p.final_weights) {                               // single-game calls: the weights after the replay, state_dict order
-            for (int pos = 0; pos < td_class_rows(q); pos++) {
-                const int f = td_row_of(q, pos);
-                const float2 w = W2[f * 64 + pair];
-                p.final_weights[col * kFeatures + f] = w.x;
-                p.final_weights[(col + 1) * kFeatures + f] = w.y;
-            }
-            if (owner) {
-                p.final_weights[kTableFloats + col] = b1s[col]; p.final_weights[kTableFloats + col + 1] = b1s[col + 1];
-                p.final_weights[kTableFloats + kHidden + col] = w2f[col]; p.final_weights[kTableFloats + kHidden + col + 1] = w2f[col + 1];
-            }
+            if (owner)
+                for (int k = 0; k < 4; k++) {
+                    p.final_weights[kTableFloats + col + k] = b1s[col + k];
+                    p.final_weights[kTableFloats + kHidden + col + k] = w2f[col + k];
+                }
             if (tid == 0) p.final_weights[kTableFloats + 2 * kHidden] = b2;
         }
-        // this game's weight change, accumulated per CTA (feature-major W1, then b1, w2, b2); touched rows go back to the snapshot
         {
-            float2 *acc = reinterpret_cast<float2 *>(mine);
-            const int nF = F->n[q];
-            for (int i = 0; i < nF; i++) {
-                const int f = (int)(F->ent[q][i].meta & 0xFFu);
-                const float2 w = W2[f * 64 + pair], o = wt2[f * 64 + pair];
-                float2 a = acc[f * 64 + pair];
-                a.x += w.x - o.x; a.y += w.y - o.y;
-                acc[f * 64 + pair] = a;
-                W2[f * 64 + pair] = o;
-                E2[f * 64 + pair] = make_float2(0.f, 0.f);
+            float4 *acc = reinterpret_cast<float4 *>(mine);
+            uint32_t touched = __ballot_sync(kFull, last >= 0);
+            if (p.final_weights) touched = cls < 6 ? 0x1FFFFFFu : 0xFFFFFFu;
+            while (touched) {
+                const int j = __ffs(touched) - 1;
+                touched &= touched - 1;
+                const int f = td_row_of(cls, j), idx = f * 32 + lane;
+                const int from = __shfl_sync(kFull, last, j) + 1;
+                float4 w = W4[idx];
+                if (from > 0 && from <= T - 1) {
+                    float4 e = E4[idx];
+                    td_replay_row(e, w, from, T - 1, chist, lam);
+                    lazy += (unsigned)(T - from);
+                }
+                const float4 o = wt4[idx];
+                if (p.final_weights) {
+                    p.final_weights[(col + 0) * kFeatures + f] = w.x; p.final_weights[(col + 1) * kFeatures + f] = w.y;
+                    p.final_weights[(col + 2) * kFeatures + f] = w.z; p.final_weights[(col + 3) * kFeatures + f] = w.w;
+                }
+                float4 a = acc[idx];
+                a.x += w.x - o.x; a.y += w.y - o.y; a.z += w.z - o.z; a.w += w.w - o.w;
+                acc[idx] = a;
+                W4[idx] = o;
+                E4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (owner) {
-                mine[kTableFloats + col] += b1s[col] - p.flat[kTableFloats + col];
-                mine[kTableFloats + col + 1] += b1s[col + 1] - p.flat[kTableFloats + col + 1];
-                mine[kTableFloats + kHidden + col] += w2f[col] - p.flat[kTableFloats + kHidden + col];
-                mine[kTableFloats + kHidden + col + 1] += w2f[col + 1] - p.flat[kTableFloats + kHidden + col + 1];
-            }
+            if (owner)
+                for (int k = 0; k < 4; k++) {
+                    mine[kTableFloats + col + k] += b1s[col + k] - p.flat[kTableFloats + col + k];
+                    mine[kTableFloats + kHidden + col + k] += w2f[col + k] - p.flat[kTableFloats + kHidden + col + k];
+                }
             if (tid == 0) mine[kTableFloats + 2 * kHidden] += b2 - p.flat[kTableFloats + 2 * kHidden];
         }
         steps += (unsigned long long)T;
         games++;
         TD_MARK(7);
     }
-    if (kProf && blockIdx.x == 0 && tid == 0) {
-        for (int i = 0; i < 8; i++) p.prof[i] = (unsigned long long)pc[i];
-        p.prof[10] = steps;
-    }
-#undef TD_MARK
-    if (lane == 0 && (warp >> 2) == 0) atomicAdd(p.stats + 7, lazy);          // row-steps replayed lazily, all four classes
+    if (lane == 0) atomicAdd(p.stats + 7, lazy);                              // row-steps replayed lazily, all eight classes
     if (tid == 0) {
         atomicAdd(p.stats + 3, games);
         atomicAdd(p.stats + 6, steps);
         atomicAdd(p.dstats, sq_sum);
     }
+    if (kProf && blockIdx.x == 0 && lane == 0) {
+        for (int i = 0; i < 14; i++) p.prof[cls * 16 + i] = (unsigned long long)pc[i];
+        p.prof[cls * 16 + 15] = steps;
+    }
+    (void)my_row;
+#undef TD_MARK
 }
 
 // delta[state_dict order] = sum over CTAs of their feature-major partials

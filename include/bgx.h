@@ -287,10 +287,10 @@ int bgx_launch_count(bgx_engine *e, int64_t *n);
 /* CUDA-event duration (ms) of the last self-play / select / enumerate kernel launch */
 int bgx_last_kernel_ms(bgx_engine *e, float *ms);
 int bgx_device_props(bgx_engine *e, int *sm_count, int *clock_khz, int64_t *global_mem);
-/* on != 0: later TD replays run the instrumented variant of k_td_replay.  cycles[16] (may be NULL) receives what the last
- * instrumented launch recorded on CTA 0: [0..7] SM cycles one worker thread spent in each phase of the step (first-layer
- * store, worker barrier, hidden layer, lazy catch-up, step barrier, values + gradients, row pass, end of game), [8] [9] the
- * lister's list building and barrier wait, [10] the TD steps of that CTA. */
+/* on != 0: later TD replays run the instrumented variant of k_td_replay.  cycles[8][16] (may be NULL) receives what the last
+ * instrumented launch recorded on CTA 0, per warp (= row class): [0..7] SM cycles lane 0 spent in each phase of the step
+ * (first-layer store, barrier, hidden layer, window bookkeeping + lazy replay, barrier, values + gradients, row pass, end of
+ * game; a barrier's wait shows up in the phase that follows it), [15] the TD steps of that CTA. */
 int bgx_td_profile(bgx_engine *e, int on, uint64_t *cycles);
 /* warps per CTA of the fused ply kernels as configured (defaults or BGX_*_WARPS) */
 int bgx_kernel_config(bgx_engine *e, int *selfplay_warps, int *select_warps);

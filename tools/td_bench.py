@@ -38,6 +38,8 @@ if os.environ.get("BGX_TD_PROFILE"):
     eng.td_profile(True)
     eng.td_replay(0.1, 0.9, delta)
     pc = eng.td_profile(False).astype(float)
-    n = max(pc[10], 1.0)
-    names = ["z store", "worker barrier", "hidden layer", "catch-up", "step barrier", "values+grad", "row pass", "end of game", "lister build", "lister wait"]
-    print("cycles per step on CTA 0 (%d steps): " % n + ", ".join(f"{nm} {pc[i] / n:.0f}" for i, nm in enumerate(names)) + f"; sum of worker phases {pc[:8].sum() / n:.0f}")
+    names = ["z store", "(bar A)", "hidden", "window", "(bar B)", "grad", "row pass", "end of game", "values", "c", "ring", "release-after-last", "wait-for-last"]
+    print("cycles per step on CTA 0, per warp: " + " | ".join(names))
+    for w in range(8):
+        n = max(pc[w, 15], 1.0)
+        print(f"  warp {w}: " + " ".join(f"{pc[w, i] / n:7.0f}" for i in range(13)) + f"   sum {pc[w, :11].sum() / n:.0f}")
