@@ -116,6 +116,10 @@ class BatchEngine:
             t = total.value
             return offsets, mv[:t], ln[:t], st[:t]
 
+    def enumerate_count(self, queries, n_seq, offsets):
+        """device tensors: int8[n,32] -> int32[n] list sizes, int64[n+1] exclusive prefix sum (offsets[n] = total rows)"""
+        L.check(self._lib.bgx_enumerate_count(self._h, L.ptr(queries), queries.shape[0], L.ptr(n_seq), L.ptr(offsets)))
+
     def enumerate(self, queries, offsets, moves, lens, states):
         L.check(self._lib.bgx_enumerate(self._h, L.ptr(queries), queries.shape[0], L.ptr(offsets), L.ptr(moves),
                                         L.ptr(lens), L.ptr(states)))
@@ -177,6 +181,19 @@ class BatchEngine:
         L.check(self._lib.bgx_play_ply_host_async(self._h, int(lane), q.ctypes.data, L.ptr(next_ply), L.ptr(game_id), n,
                                                   float(epsilon), int(explore_seed), int(dice_seed),
                                                   L.ptr(next_records), L.ptr(winner), L.ptr(value), L.ptr(n_seq)))
+
+    def play_ply_restart_host_async(self, lane, records, ply, game_id, id_stride, next_records, winner=None, value=None, n_seq=None,
+                                    first_mover=L.FIRST_PARITY, epsilon=0.0, explore_seed=0, dice_seed=0x5EED2026):
+        """play_ply_host_async with the bookkeeping on the device: ply / game_id (int32 / int64 numpy, updated in place when the
+        lane completes) describe `records` on entry and `next_records` on return; finished games restart in place."""
+        q = _records(records)
+        n = q.shape[0]
+        assert next_records.dtype == np.int8 and next_records.shape == (n, 32) and next_records.flags["C_CONTIGUOUS"]
+        assert ply.dtype == np.int32 and ply.shape == (n,) and ply.flags["C_CONTIGUOUS"]
+        assert game_id.dtype == np.int64 and game_id.shape == (n,) and game_id.flags["C_CONTIGUOUS"]
+        L.check(self._lib.bgx_play_ply_restart_host_async(self._h, int(lane), q.ctypes.data, L.ptr(ply), L.ptr(game_id), int(id_stride),
+                                                          int(first_mover), n, float(epsilon), int(explore_seed), int(dice_seed),
+                                                          L.ptr(next_records), L.ptr(winner), L.ptr(value), L.ptr(n_seq)))
 
     def wait(self, lane):
         L.check(self._lib.bgx_lane_wait(self._h, int(lane)))
@@ -247,6 +264,13 @@ class BatchEngine:
         """delta: device fp32[25604] (torch tensor or raw pointer), overwritten with the summed weight change"""
         st = L.Stats()
         L.check(self._lib.bgx_td_replay(self._h, float(lr), float(lam), L.ptr(delta), C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    def td_replay_scheduled(self, games_done, delta, want_stats=True):
+        """td_replay with the reference's per-game lr / lambda schedule (train.py:538, model.py:69-73): the game in global
+        slot k of the round is episode games_done + k + 1"""
+        st = L.Stats()
+        L.check(self._lib.bgx_td_replay_scheduled(self._h, int(games_done), L.ptr(delta), C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
 
     def apply_delta(self, delta, scale=1.0):

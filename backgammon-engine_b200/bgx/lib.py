@@ -54,6 +54,7 @@ _SIGNATURES = {
     "bgx_enumerate_summary": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "bgx_enumerate_summary_host": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "bgx_enumerate": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "bgx_enumerate_count": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "bgx_enumerate_host": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i64)]),
     "bgx_encode": (C.c_int, [_vp, _vp, _i64, _vp]),
     "bgx_encode_host": (C.c_int, [_vp, _vp, _i64, _vp]),
@@ -63,6 +64,7 @@ _SIGNATURES = {
     "bgx_select_moves_host": (C.c_int, [_vp, _vp, _i64, C.c_float, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bgx_select_moves_host_async": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_float, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bgx_play_ply_host_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _i64, C.c_float, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
+    "bgx_play_ply_restart_host_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _i64, C.c_int, _i64, C.c_float, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
     "bgx_lane_wait": (C.c_int, [_vp, C.c_int]),
     "bgx_advance": (C.c_int, [_vp, _vp, _vp, _i64, C.c_uint64, C.c_int32, _vp, _vp]),
     "bgx_advance_host": (C.c_int, [_vp, _vp, _i64, C.c_uint64, _vp, _vp, _vp]),
@@ -77,10 +79,11 @@ _SIGNATURES = {
     "bgx_selfplay_sample": (C.c_int, [_vp, C.c_int32, C.c_uint64, _vp]),
     "bgx_selfplay_sample_host": (C.c_int, [_vp, C.c_int32, C.c_uint64, _vp]),
     # section 5
-    "bgx_td_replay": (C.c_int, [_vp, C.c_float, C.c_float, _vp, C.POINTER(Stats)]),
+    "bgx_td_replay": (C.c_int, [_vp, C.c_double, C.c_double, _vp, C.POINTER(Stats)]),
+    "bgx_td_replay_scheduled": (C.c_int, [_vp, _i64, _vp, C.POINTER(Stats)]),
     "bgx_apply_delta": (C.c_int, [_vp, _vp, C.c_float]),
-    "bgx_td_round_host": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, _vp, C.POINTER(Stats)]),
-    "bgx_td_replay_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp]),
+    "bgx_td_round_host": (C.c_int, [_vp, C.c_double, C.c_double, C.c_float, _vp, C.POINTER(Stats)]),
+    "bgx_td_replay_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     # section 6
     "bgx_launch_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "bgx_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),

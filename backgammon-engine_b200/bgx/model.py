@@ -59,6 +59,8 @@ class TDLGammonModel(nn.Module):
         self.initialize_traces()
         self.lambda_decay = 0.7
         self._engine = None
+        self._uploaded = None
+        self._ahead = None                                   # a GpuTrainer whose weights are newer than this module's
 
     # ------------------------------------------------------------------ reference contract
     def initialize_traces(self):
@@ -142,20 +144,34 @@ class TDLGammonModel(nn.Module):
         sd = self.state_dict()
         return tuple(sd[k].detach().cpu().numpy() for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"))
 
+    def _weights_version(self):
+        """Changes whenever a parameter is written (in place or replaced): what tells engine() to upload again."""
+        return tuple((p.data_ptr(), p._version) for p in (self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias))
+
     def engine(self, device=0):
-        """BatchEngine on `device` loaded with the current weights (created on first use; raises without a GPU)."""
+        """BatchEngine on `device` holding this module's weights (created on first use; raises without a GPU).  The weights
+        are uploaded when the engine is created and again only after the module's parameters have changed."""
         from .engine import BatchEngine
         if self._engine is None:
             self._engine = BatchEngine(device)
-        self._engine.set_weights(*self.weights_np())
+            self._uploaded = None
+        version = self._weights_version()
+        if version != self._uploaded:
+            self._engine.set_weights(*self.weights_np())
+            self._uploaded = version
         return self._engine
 
-    def load_engine_weights(self):
-        """Copy the engine's weights (e.g. after GPU TD rounds) back into this module."""
-        W1, b1, w2, b2 = self._engine.get_weights()
+    def load_weights_from(self, engine):
+        """Copy an engine's weights (e.g. a GpuTrainer's after its rounds) into this module."""
+        W1, b1, w2, b2 = engine.get_weights()
         with torch.no_grad():
             self.fc1.weight.copy_(torch.from_numpy(W1)); self.fc1.bias.copy_(torch.from_numpy(b1))
             self.fc2.weight.copy_(torch.from_numpy(w2)); self.fc2.bias.copy_(torch.from_numpy(b2))
+
+    def load_engine_weights(self):
+        """Copy this module's own engine weights back into the module."""
+        self.load_weights_from(self._engine)
+        self._uploaded = self._weights_version()
 
     def make_moves_batch(self, games, epsilon=0.0, seed=0, device=0):
         """make_move for a list of compat Game objects in ONE kernel launch; applies the chosen

@@ -41,20 +41,41 @@ class GpuTrainer:
     """Round-structured self-play TD(lambda) on one GPU per process (rank = torch.distributed rank).
 
     games_per_rank concurrent games; game ids are global (rank * games_per_rank + slot, stride
-    world * games_per_rank) so a run is invariant to how the population is sharded."""
+    world * games_per_rank) so a run is invariant to how the population is sharded.
+
+    The trainer owns a PRIVATE engine: the live weights are the engine's, the torch module is a snapshot that
+    `sync_model()` refreshes (save_checkpoint does it by itself), and nothing the module's own engine() does - batched
+    make_move, play_games_batch - can disturb the trainer's population or weights.
+
+    lr / lambda follow the reference PER GAME (train.py:538: update_learning_params(games_done + k + 1) before the
+    k-th game of the round): the replay kernel looks the schedule of model.py:69-73 up for every game.  What a parallel
+    round cannot reproduce is the reference applying the games' updates one after the other; a round applies
+    delta_scale x their sum (default: the mean).  One round is ONE step of that size, so the population is a batch
+    size: a few hundred games per round train fastest per game played; a 262,144-game round is the
+    throughput configuration of BASELINE.json configs[3], not a training recipe - a warning says so."""
 
     def __init__(self, model, games_per_rank, device=0, seed=0x5EED2026, traj_cap=2048,
-                 first_mover=L.FIRST_ROLLOFF, delta_scale=None):
+                 first_mover=L.FIRST_ROLLOFF, delta_scale=None, schedule="per_game"):
+        import warnings
         import torch.distributed as dist
+        from .engine import BatchEngine
+        if schedule not in ("per_game", "per_round"):
+            raise ValueError("schedule is 'per_game' (train.py:538) or 'per_round'")
         self.dist = dist if dist.is_available() and dist.is_initialized() else None
         self.rank = self.dist.get_rank() if self.dist else 0
         self.world = self.dist.get_world_size() if self.dist else 1
         self.model = model
+        self.schedule = schedule
         self.games_per_rank = int(games_per_rank)
         self.global_games = self.games_per_rank * self.world
+        if self.global_games > 8192:
+            warnings.warn(f"GpuTrainer: {self.global_games:,} games per round means one weight update per {self.global_games:,} games, and the "
+                          "reference's lr / lambda schedule (periods 40,000 / 30,000 games) advances by whole periods per update; "
+                          "use a few hundred games per round for training and keep rounds this large for throughput runs", stacklevel=2)
         # default: the MEAN of the per-game updates (mini-batch TD); the reference applies them in sequence
         self.delta_scale = (1.0 / self.global_games) if delta_scale is None else float(delta_scale)
-        self.eng = model.engine(device)
+        self.eng = BatchEngine(device)
+        self.eng.set_weights(*model.weights_np())
         self.eng.set_stream(torch.cuda.current_stream().cuda_stream)
         first_id, n_slots, stride = shard(self.global_games, self.rank, self.world)
         self.eng.selfplay_init(n_slots, first_id=first_id, id_stride=stride, seed=seed, first_mover=first_mover, traj_cap=traj_cap)
@@ -66,18 +87,29 @@ class GpuTrainer:
         """Play, replay, reduce, apply.  Returns the round's statistics (this rank's counts)."""
         if self.rounds:
             self.eng.selfplay_next_round()
-        self.model.update_learning_params(self.games_done + 1)               # schedule of model.py:69-73
         play = self.eng.selfplay_round(epsilon)
-        td = self.eng.td_replay(self.model.learning_rate, self.model.lambda_decay, self.delta)
+        if self.schedule == "per_game":
+            td = self.eng.td_replay_scheduled(self.games_done, self.delta)
+            self.model.update_learning_params(self.games_done + self.global_games)    # what the reference's model holds after the round
+        else:
+            self.model.update_learning_params(self.games_done + 1)
+            td = self.eng.td_replay(self.model.learning_rate, self.model.lambda_decay, self.delta)
         allreduce_delta(self.delta, self.dist)                               # the only cross-GPU traffic: 102,416 B
         self.eng.apply_delta(self.delta, self.delta_scale)
         self.games_done += self.global_games
         self.rounds += 1
+        self.model._ahead = self
         return {**play, "td_steps": td["td_steps"], "td_sq_error": td["td_sq_error"], "games": self.global_games}
 
     def sync_model(self):
-        self.model.load_engine_weights()
+        """The engine's weights -> the torch module (state_dict, checkpoints, CPU evaluation)."""
+        self.model.load_weights_from(self.eng)
+        self.model._ahead = None
         return self.model
+
+    def close(self):
+        self.sync_model()
+        self.eng.close()
 
 
 # ------------------------------------------------------------------ checkpoints (train.py:361-381, 513-515)
@@ -108,5 +140,8 @@ def latest_compatible_model(models_dir):
 
 
 def save_checkpoint(model, path):
-    """The reference's checkpoint format: the 4-tensor state_dict (train.py:513-515)."""
+    """The reference's checkpoint format: the 4-tensor state_dict (train.py:513-515).  If a GpuTrainer holds newer weights
+    than the module, they are pulled into the module first."""
+    if getattr(model, "_ahead", None) is not None:
+        model._ahead.sync_model()
     torch.save(model.state_dict(), path)

@@ -381,7 +381,7 @@ class BatchEngine {
         return py::make_tuple(p, c);
     }
     // exact online TD(lambda) replay of every finished game from the current weights, summed; weights += scale * delta
-    py::tuple td_round(float lr, float lambda, float scale)
+    py::tuple td_round(double lr, double lambda, float scale)
     {
         bgx_stats s;
         py::array_t<float> delta(BGX_NPARAMS);

@@ -5,8 +5,9 @@
 #include "bgx_internal.h"
 #include "bgx_kernels.cuh"
 #include "bgx_td.cuh"
-#include "bgx_td_dense.cuh"
 
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -62,6 +63,8 @@ struct bgx_engine {
     // TD
     float *td_partial = nullptr;             // [td_grid][25604] per-CTA delta accumulators
     float *td_delta = nullptr;               // [25604] summed delta of bgx_td_round_host
+    float *td_home = nullptr;                // [td_grid][2][198][128] per-CTA home copies of W1 and its traces (k_td_replay)
+    double *td_sched = nullptr;              // [2][64] lr / lambda by schedule index (bgx_td_replay_scheduled)
     unsigned long long *td_prof = nullptr;   // [16] phase cycles of the profiling variant of k_td_replay
     bool td_profile = false;
     int td_grid = 0;
@@ -198,7 +201,6 @@ static_assert(ply_smem<16, 110>() <= 232448 && ply_smem<20, 87>() <= 232448 && p
 #undef BGX_SMEM_ATTR
     CU(cudaFuncSetAttribute(k_td_replay<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
     CU(cudaFuncSetAttribute(k_td_replay<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
-    CU(cudaFuncSetAttribute(k_td_replay_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdDSmem));
     *out = e;
     return BGX_OK;
 }
@@ -211,7 +213,7 @@ int bgx_destroy(bgx_engine *e)
     for (int i = 0; i < bgx_engine::kScratch; i++) cudaFree(e->dbuf[i]);
     cudaFree(e->flat); cudaFree(e->wt); cudaFree(e->fixed); cudaFree(e->aux); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats); cudaFree(e->steal);
     cudaFree(e->uniq_tables); cudaFree(e->uniq_gens); cudaFree(e->slots); cudaFree(e->traj_pre); cudaFree(e->traj_chosen);
-    cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial); cudaFree(e->td_delta); cudaFree(e->td_prof);
+    cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial); cudaFree(e->td_delta); cudaFree(e->td_prof); cudaFree(e->td_home); cudaFree(e->td_sched);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_sync);
     for (bgx_lane &l : e->lanes) {
         if (l.stream) cudaStreamDestroy(l.stream);
@@ -347,6 +349,29 @@ int bgx_enumerate(bgx_engine *e, const int8_t *queries, int64_t n, const int64_t
     return BGX_OK;
 }
 
+// sizes of every query's sequence list and their exclusive prefix sum, on the device: the allocation pass of the
+// materialised enumeration (a count-only walk, no dedup table, no digest) + a three-launch scan
+int bgx_enumerate_count(bgx_engine *e, const int8_t *queries, int64_t n, int32_t *n_seq, int64_t *offsets)
+{
+    USE(e);
+    NEED(queries && n_seq && offsets && n >= 0, "bad argument");
+    if (n == 0) { CU(cudaMemsetAsync(offsets, 0, 8, e->stream)); return BGX_OK; }
+    const int n_tiles = (int)((n + kScanTile - 1) / kScanTile);
+    void *sums;
+    int rc;
+    if ((rc = scratch(e, 9, (size_t)(n_tiles + 1) * 8, &sums))) return rc;
+    CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
+    tick(e);
+    k_enumerate_count<<<e->sm_count * 2, kGameThreads, 0, e->stream>>>(queries, n, n_seq, e->counter);
+    tock(e);
+    k_scan_tiles<<<n_tiles, kScanThreads, 0, e->stream>>>(n_seq, n, (long long *)offsets, (long long *)sums);
+    k_scan_sums<<<1, 1024, 0, e->stream>>>((long long *)sums, n_tiles);
+    k_scan_add<<<(unsigned)((n + kScanThreads - 1) / kScanThreads), kScanThreads, 0, e->stream>>>((long long *)offsets, n, (const long long *)sums, n_tiles);
+    e->launches += 4;
+    CU(cudaGetLastError());
+    return BGX_OK;
+}
+
 int bgx_enumerate_host(bgx_engine *e, const int8_t *queries, int64_t n, int64_t cap, int64_t *offsets,
                        int8_t *seq_moves, int8_t *seq_len, int8_t *states, int64_t *total)
 {
@@ -354,32 +379,27 @@ int bgx_enumerate_host(bgx_engine *e, const int8_t *queries, int64_t n, int64_t 
     NEED(queries && total && n >= 0 && cap >= 0, "bad argument");
     *total = 0;
     if (n == 0) { if (offsets) offsets[0] = 0; return BGX_OK; }
-    void *dq, *dn, *du, *dd, *doff;
+    void *dq, *dn, *doff;
     int rc;
     if ((rc = scratch(e, 0, (size_t)n * 32, &dq))) return rc;
     if ((rc = scratch(e, 1, (size_t)n * 4, &dn))) return rc;
-    if ((rc = scratch(e, 2, (size_t)n * 4, &du))) return rc;
-    if ((rc = scratch(e, 3, (size_t)n * 8, &dd))) return rc;
     if ((rc = scratch(e, 4, (size_t)(n + 1) * 8, &doff))) return rc;
     CU(cudaMemcpyAsync(dq, queries, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
-    if ((rc = bgx_enumerate_summary(e, (const int8_t *)dq, n, (int32_t *)dn, (int32_t *)du, (uint64_t *)dd))) return rc;
-    std::vector<int32_t> cnt((size_t)n);
-    CU(cudaMemcpyAsync(cnt.data(), dn, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if ((rc = bgx_enumerate_count(e, (const int8_t *)dq, n, (int32_t *)dn, (int64_t *)doff))) return rc;
+    // the one number the host needs before it can size anything: 8 bytes
+    int64_t rows_needed = 0;
+    CU(cudaMemcpyAsync(&rows_needed, (const int64_t *)doff + n, 8, cudaMemcpyDeviceToHost, e->stream));
+    if (offsets) CU(cudaMemcpyAsync(offsets, doff, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    std::vector<int64_t> off((size_t)n + 1);
-    off[0] = 0;
-    for (int64_t i = 0; i < n; i++) off[i + 1] = off[i] + cnt[i];
-    *total = off[n];
-    if (offsets) std::memcpy(offsets, off.data(), (size_t)(n + 1) * 8);
-    if (off[n] > cap) { set_error("bgx_enumerate_host: %lld rows needed, cap %lld", (long long)off[n], (long long)cap); return BGX_E_CAPACITY; }
+    *total = rows_needed;
+    if (rows_needed > cap) { set_error("bgx_enumerate_host: %lld rows needed, cap %lld", (long long)rows_needed, (long long)cap); return BGX_E_CAPACITY; }
     NEED(seq_moves && seq_len && states, "null output buffer");
-    const size_t rows = (size_t)off[n];
+    const size_t rows = (size_t)rows_needed;
     if (rows == 0) return BGX_OK;
     void *dm, *dl, *ds;
     if ((rc = scratch(e, 5, rows * 8, &dm))) return rc;
     if ((rc = scratch(e, 6, rows, &dl))) return rc;
     if ((rc = scratch(e, 7, rows * 32, &ds))) return rc;
-    CU(cudaMemcpyAsync(doff, off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     if ((rc = bgx_enumerate(e, (const int8_t *)dq, n, (const int64_t *)doff, (int8_t *)dm, (int8_t *)dl, (int8_t *)ds))) return rc;
     CU(cudaMemcpyAsync(seq_moves, dm, rows * 8, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaMemcpyAsync(seq_len, dl, rows, cudaMemcpyDeviceToHost, e->stream));
@@ -616,18 +636,15 @@ int bgx_select_moves_host_async(bgx_engine *e, int lane, const int8_t *queries, 
     return BGX_OK;
 }
 
-// One iteration of play_game's loop (train.py:103-121) for n games through host buffers, asynchronous:
-// make_move, is_game_over, setTurn, roll_dice.  = bgx_select_moves_host_async + bgx_advance_host in one queued call.
-int bgx_play_ply_host_async(bgx_engine *e, int lane, const int8_t *records, const int32_t *next_ply, const int64_t *game_id,
-                            int64_t n, float epsilon, uint64_t explore_seed, uint64_t dice_seed,
-                            int8_t *next_records, int8_t *winner, float *value, int32_t *n_seq)
+static int play_ply(bgx_engine *e, int lane, const int8_t *records, int32_t *ply, int64_t *game_id, int64_t id_stride, int first_mover,
+                    int64_t n, float epsilon, uint64_t explore_seed, uint64_t dice_seed,
+                    int8_t *next_records, int8_t *winner, float *value, int32_t *n_seq, const char *who)
 {
-    USE(e);
     NEED(lane >= 0 && lane < kLanes, "lane out of range");
     NEED(records && next_records && n >= 0, "bad argument");
-    if (!e->have_weights) { set_error("bgx_play_ply_host_async: weights not set"); return BGX_E_STATE; }
+    if (!e->have_weights) { set_error("%s: weights not set", who); return BGX_E_STATE; }
     bgx_lane &l = e->lanes[lane];
-    if (l.busy) { set_error("bgx_play_ply_host_async: lane %d has a batch in flight (bgx_lane_wait first)", lane); return BGX_E_STATE; }
+    if (l.busy) { set_error("%s: lane %d has a batch in flight (bgx_lane_wait first)", who, lane); return BGX_E_STATE; }
     if (!l.stream) {
         CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
@@ -642,7 +659,7 @@ int bgx_play_ply_host_async(bgx_engine *e, int lane, const int8_t *records, cons
     if ((rc = lane_scratch(l, 3, (size_t)n, &dw))) return rc;
     if ((rc = lane_scratch(l, 4, (size_t)n * 4, &dv))) return rc;
     if ((rc = lane_scratch(l, 5, (size_t)n * 4, &dn))) return rc;
-    if (next_ply && (rc = lane_scratch(l, 8, (size_t)n * 4, &dp))) return rc;
+    if (ply && (rc = lane_scratch(l, 8, (size_t)n * 4, &dp))) return rc;
     if (game_id && (rc = lane_scratch(l, 9, (size_t)n * 8, &dg))) return rc;
     OrderPlan plan;
     if (n <= e->select_order_max) {
@@ -659,20 +676,48 @@ int bgx_play_ply_host_async(bgx_engine *e, int lane, const int8_t *records, cons
     CU(cudaEventRecord(e->ev_sync, e->stream));
     CU(cudaStreamWaitEvent(l.stream, e->ev_sync, 0));
     CU(cudaMemcpyAsync(dq, records, (size_t)n * 32, cudaMemcpyHostToDevice, l.stream));
-    if (dp) CU(cudaMemcpyAsync(dp, next_ply, (size_t)n * 4, cudaMemcpyHostToDevice, l.stream));
+    if (dp) CU(cudaMemcpyAsync(dp, ply, (size_t)n * 4, cudaMemcpyHostToDevice, l.stream));
     if (dg) CU(cudaMemcpyAsync(dg, game_id, (size_t)n * 8, cudaMemcpyHostToDevice, l.stream));
     const SelectOut out = {nullptr, nullptr, nullptr, value ? (float *)dv : nullptr, n_seq ? (int32_t *)dn : nullptr, nullptr};
     AdvanceOut adv = {(int8_t *)dc, winner ? (int8_t *)dw : nullptr, (const int32_t *)dp, (const long long *)dg,
-                      (uint32_t)dice_seed, (uint32_t)(dice_seed >> 32), nullptr, nullptr};
+                      (uint32_t)dice_seed, (uint32_t)(dice_seed >> 32), nullptr, nullptr,
+                      (long long)id_stride, first_mover, id_stride > 0 ? (int32_t *)dp : nullptr, id_stride > 0 ? (long long *)dg : nullptr};
     if ((rc = launch_select(e, l.stream, l.counter, l.steal, (const int8_t *)dq, n, epsilon, explore_seed, out, plan, e->lane_grid, adv))) return rc;
     if (plan.produce) { l.order_slot = 1 - plan.slot; l.order_n = n; }
     CU(cudaMemcpyAsync(next_records, dc, (size_t)n * 32, cudaMemcpyDeviceToHost, l.stream));
     if (winner) CU(cudaMemcpyAsync(winner, dw, (size_t)n, cudaMemcpyDeviceToHost, l.stream));
     if (value) CU(cudaMemcpyAsync(value, dv, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
     if (n_seq) CU(cudaMemcpyAsync(n_seq, dn, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
+    if (id_stride > 0) {
+        CU(cudaMemcpyAsync(ply, dp, (size_t)n * 4, cudaMemcpyDeviceToHost, l.stream));
+        CU(cudaMemcpyAsync(game_id, dg, (size_t)n * 8, cudaMemcpyDeviceToHost, l.stream));
+    }
     CU(cudaEventRecord(l.done, l.stream));
     l.busy = true;
     return BGX_OK;
+}
+
+// One iteration of play_game's loop (train.py:103-121) for n games through host buffers, asynchronous:
+// make_move, is_game_over, setTurn, roll_dice.  = bgx_select_moves_host_async + bgx_advance_host in one queued call.
+int bgx_play_ply_host_async(bgx_engine *e, int lane, const int8_t *records, const int32_t *next_ply, const int64_t *game_id,
+                            int64_t n, float epsilon, uint64_t explore_seed, uint64_t dice_seed,
+                            int8_t *next_records, int8_t *winner, float *value, int32_t *n_seq)
+{
+    USE(e);
+    return play_ply(e, lane, records, const_cast<int32_t *>(next_ply), const_cast<int64_t *>(game_id), 0, 0, n, epsilon, explore_seed, dice_seed,
+                    next_records, winner, value, n_seq, "bgx_play_ply_host_async");
+}
+
+// The same with the population's bookkeeping on the device: finished games restart in place, ply and game id travel with the records.
+int bgx_play_ply_restart_host_async(bgx_engine *e, int lane, const int8_t *records, int32_t *ply, int64_t *game_id, int64_t id_stride,
+                                    int first_mover, int64_t n, float epsilon, uint64_t explore_seed, uint64_t dice_seed,
+                                    int8_t *next_records, int8_t *winner, float *value, int32_t *n_seq)
+{
+    USE(e);
+    NEED(ply && game_id && id_stride > 0, "restart mode needs ply, game_id and a positive id_stride");
+    NEED(first_mover == BGX_FIRST_ROLLOFF || first_mover == BGX_FIRST_PARITY, "unknown first-mover rule");
+    return play_ply(e, lane, records, ply, game_id, id_stride, first_mover, n, epsilon, explore_seed, dice_seed,
+                    next_records, winner, value, n_seq, "bgx_play_ply_restart_host_async");
 }
 
 int bgx_lane_wait(bgx_engine *e, int lane)
@@ -861,15 +906,17 @@ int bgx_selfplay_sample_host(bgx_engine *e, int32_t per_game, uint64_t seed, int
 static int ensure_td(bgx_engine *e)
 {
     if (e->td_partial) return BGX_OK;
-    e->td_grid = e->sm_count;
+    e->td_grid = e->sm_count * kTdCtasPerSm;
     CU(cudaMalloc(&e->td_partial, (size_t)e->td_grid * BGX_NPARAMS_PADDED * sizeof(float)));
+    CU(cudaMalloc(&e->td_home, (size_t)e->td_grid * 2 * kTableBytes));
     CU(cudaMalloc(&e->td_delta, (size_t)BGX_NPARAMS_PADDED * sizeof(float)));
     CU(cudaMalloc(&e->td_prof, 128 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&e->td_sched, 2 * kTdSchedLen * sizeof(double)));
     return BGX_OK;
 }
 
 static int launch_td(bgx_engine *e, const int8_t *traj, const int8_t *slots, const int32_t *ply, long long n_games, int traj_cap,
-                     float lr, float lambda, float *delta_dev, float *final_weights, double *sq_errors, bgx_stats *out)
+                     double lr, double lambda, long long episode_first, float *delta_dev, float *final_weights, double *sq_errors, bgx_stats *out)
 {
     int rc = ensure_td(e);
     if (rc) return rc;
@@ -878,19 +925,30 @@ static int launch_td(bgx_engine *e, const int8_t *traj, const int8_t *slots, con
     if (grid > n_games) grid = (int)n_games;
     TdParams p;
     p.traj = traj; p.slots = slots; p.ply = ply; p.n_games = n_games; p.traj_cap = traj_cap;
-    p.lr = (double)lr; p.lambda = lambda;
+    p.lr = lr; p.lambda = (float)lambda;
     p.flat = e->flat; p.wt = e->wt; p.partial = e->td_partial;
     p.final_weights = final_weights; p.sq_errors = sq_errors;
     p.stats = e->stats; p.dstats = e->dstats;
-    p.sched = nullptr; p.episode_first = 0; p.queue = e->counter;
+    p.sched = nullptr; p.episode_first = 0;
+    if (episode_first >= 0) {                        // the reference's schedule (model.py:69-73), tabulated with the host's libm pow
+        double sched[2 * kTdSchedLen];
+        for (int k = 0; k < kTdSchedLen; k++) {
+            sched[k] = std::max(0.01, 0.1 * std::pow(0.96, (double)k));
+            sched[kTdSchedLen + k] = std::max(0.7, 0.9 * std::pow(0.96, (double)k));
+        }
+        CU(cudaMemcpyAsync(e->td_sched, sched, sizeof sched, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));        // `sched` is on this stack frame
+        p.sched = e->td_sched;
+        p.episode_first = episode_first;
+    }
     p.prof = e->td_prof;
+    p.home = e->td_home;
     if (e->td_profile) CU(cudaMemsetAsync(e->td_prof, 0, 128 * sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->dstats, 0, 2 * sizeof(double), e->stream));
     tick(e);
-    if (getenv("BGX_TD_DENSE")) k_td_replay_dense<<<grid, kTdDThreads, kTdDSmem, e->stream>>>(p);
-    else if (e->td_profile) k_td_replay<true><<<grid, kTdThreads, kTdSmem, e->stream>>>(p);
+    if (e->td_profile) k_td_replay<true><<<grid, kTdThreads, kTdSmem, e->stream>>>(p);
     else k_td_replay<false><<<grid, kTdThreads, kTdSmem, e->stream>>>(p);
     e->launches++;
     CU(cudaGetLastError());
@@ -916,13 +974,25 @@ static int launch_td(bgx_engine *e, const int8_t *traj, const int8_t *slots, con
     return BGX_OK;
 }
 
-int bgx_td_replay(bgx_engine *e, float lr, float lambda, float *delta_dev, bgx_stats *out)
+static int td_replay_population(bgx_engine *e, double lr, double lambda, long long episode_first, float *delta_dev, bgx_stats *out)
+{
+    NEED(delta_dev, "null delta buffer");
+    if (e->n_slots == 0 || !e->traj_pre) { set_error("TD replay: needs a population created with traj_cap > 0"); return BGX_E_STATE; }
+    if (!e->have_weights) { set_error("TD replay: weights not set"); return BGX_E_STATE; }
+    return launch_td(e, e->traj_pre, e->slots, e->ply, e->n_slots, e->traj_cap, lr, lambda, episode_first, delta_dev, nullptr, nullptr, out);
+}
+
+int bgx_td_replay(bgx_engine *e, double lr, double lambda, float *delta_dev, bgx_stats *out)
 {
     USE(e);
-    NEED(delta_dev, "null delta buffer");
-    if (e->n_slots == 0 || !e->traj_pre) { set_error("bgx_td_replay: needs a population created with traj_cap > 0"); return BGX_E_STATE; }
-    if (!e->have_weights) { set_error("bgx_td_replay: weights not set"); return BGX_E_STATE; }
-    return launch_td(e, e->traj_pre, e->slots, e->ply, e->n_slots, e->traj_cap, lr, lambda, delta_dev, nullptr, nullptr, out);
+    return td_replay_population(e, lr, lambda, -1, delta_dev, out);
+}
+
+int bgx_td_replay_scheduled(bgx_engine *e, int64_t games_done, float *delta_dev, bgx_stats *out)
+{
+    USE(e);
+    NEED(games_done >= 0, "games_done must not be negative");
+    return td_replay_population(e, 0.0, 0.0, (long long)games_done + e->first_id + 1, delta_dev, out);
 }
 
 int bgx_apply_delta(bgx_engine *e, const float *delta_dev, float scale)
@@ -936,7 +1006,7 @@ int bgx_apply_delta(bgx_engine *e, const float *delta_dev, float scale)
 }
 
 // bgx_td_replay + bgx_apply_delta for a single-GPU caller without device buffers of its own (the pybind11 module)
-int bgx_td_round_host(bgx_engine *e, float lr, float lambda, float scale, float *delta_host, bgx_stats *out)
+int bgx_td_round_host(bgx_engine *e, double lr, double lambda, float scale, float *delta_host, bgx_stats *out)
 {
     USE(e);
     int rc = ensure_td(e);
@@ -950,11 +1020,11 @@ int bgx_td_round_host(bgx_engine *e, float lr, float lambda, float scale, float 
     return scale != 0.f ? bgx_apply_delta(e, dd, scale) : BGX_OK;
 }
 
-int bgx_td_replay_host(bgx_engine *e, const int8_t *records, int32_t T, int player1_won, float lr, float lambda,
+int bgx_td_replay_host(bgx_engine *e, const int8_t *records, int32_t T, int player1_won, double lr, double lambda,
                        float *new_W1, float *new_b1, float *new_w2, float *new_b2, double *sq_errors)
 {
     USE(e);
-    NEED(records && T > 0 && new_W1 && new_b1 && new_w2 && new_b2, "bad argument");
+    NEED(records && T > 0 && T <= kTdMaxSteps && new_W1 && new_b1 && new_w2 && new_b2, "bad argument (1 <= T <= BGX_TD_MAX_STEPS)");
     if (!e->have_weights) { set_error("bgx_td_replay_host: weights not set"); return BGX_E_STATE; }
     void *dtraj, *dslot, *dply, *dfinal, *dsq;
     int rc;
@@ -969,7 +1039,7 @@ int bgx_td_replay_host(bgx_engine *e, const int8_t *records, int32_t T, int play
     CU(cudaMemcpyAsync(dslot, slot, 32, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(dply, &T, 4, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemsetAsync(dsq, 0, (size_t)T * 8, e->stream));
-    if ((rc = launch_td(e, (const int8_t *)dtraj, (const int8_t *)dslot, (const int32_t *)dply, 1, T, lr, lambda,
+    if ((rc = launch_td(e, (const int8_t *)dtraj, (const int8_t *)dslot, (const int32_t *)dply, 1, T, lr, lambda, -1,
                         nullptr, (float *)dfinal, (double *)dsq, nullptr)))
         return rc;
     std::vector<float> flat(BGX_NPARAMS_PADDED);

@@ -194,6 +194,98 @@ k_enumerate_summary(const int8_t *__restrict__ queries, long long n, int32_t *__
     if (lane == 0) gens[gwarp] = gen;
 }
 
+// ---- batched legalTurnSequences, count only (game.cpp:134-191): the size of every query's list ----
+__global__ void __launch_bounds__(kGameThreads, 1)
+k_enumerate_count(const int8_t *__restrict__ queries, long long n, int32_t *__restrict__ n_seq, unsigned long long *counter)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        const long long q = claim(counter, lane);
+        if (q >= n) break;
+        const int b = load_record_byte(queries + q * 32, lane);
+        const int root = lane < 28 ? b : 0;
+        const int player = __shfl_sync(kFull, b, 28), d1 = __shfl_sync(kFull, b, 29), d2 = __shfl_sync(kFull, b, 30);
+        CountLeaf leaf;
+        walk_turn(root, lane, player, d1, d2, leaf);
+        if (lane == 0) n_seq[q] = leaf.n;
+    }
+}
+
+// ---- exclusive prefix sum of the counts (int32 -> int64 offsets[n + 1]) in three small launches ----
+constexpr int kScanThreads = 256, kScanPerThread = 8, kScanTile = kScanThreads * kScanPerThread;
+
+__device__ __forceinline__ long long block_exclusive_scan(long long x, long long *warp_sums, long long &block_total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    long long inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const long long s = lane < n_warps ? warp_sums[lane] : 0;
+        long long si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(kFull, si, o);
+            if (lane >= o) si += y;
+        }
+        if (lane < n_warps) warp_sums[lane] = si - s;
+        if (lane == 31) warp_sums[32] = si;
+    }
+    __syncthreads();
+    block_total = warp_sums[32];
+    const long long base = warp_sums[warp];
+    __syncthreads();
+    return base + inc - x;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const int32_t *__restrict__ cnt, long long n, long long *__restrict__ offsets,
+                                                           long long *__restrict__ tile_sums)
+{
+    __shared__ long long warp_sums[33];
+    const long long first = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanPerThread;
+    long long v[kScanPerThread], mine = 0;
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; i++) {
+        v[i] = first + i < n ? (long long)cnt[first + i] : 0;
+        mine += v[i];
+    }
+    long long total;
+    long long run = block_exclusive_scan(mine, warp_sums, total);
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; i++) {
+        if (first + i < n) offsets[first + i] = run;
+        run += v[i];
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(long long *__restrict__ tile_sums, int n_tiles)
+{
+    __shared__ long long warp_sums[33];
+    long long carry = 0;
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const long long x = i < n_tiles ? tile_sums[i] : 0;
+        long long total;
+        const long long ex = block_exclusive_scan(x, warp_sums, total);
+        if (i < n_tiles) tile_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) tile_sums[n_tiles] = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_add(long long *__restrict__ offsets, long long n, const long long *__restrict__ tile_sums, int n_tiles)
+{
+    const long long i = (long long)blockIdx.x * kScanThreads + threadIdx.x;
+    if (i < n) offsets[i] += tile_sums[i / kScanTile];
+    if (i == 0) offsets[n] = tile_sums[n_tiles];
+}
+
 // ---- batched evaluateTurnSequences, materialised (game.cpp:193-222, bindings:27-39) ----
 struct WriteLeaf {
     int8_t *moves, *lens, *states;   // already offset to this query's first row
@@ -456,26 +548,48 @@ __global__ void __launch_bounds__(256) k_select_order(const int8_t *__restrict__
 struct AdvanceOut {
     int8_t *next;                 // [n][32] advanced records (nullptr: plain select)
     int8_t *winner;               // [n] or nullptr
-    const int32_t *ply_of;        // [n] ply whose dice each game gets, or nullptr (0)
+    const int32_t *ply_of;        // [n] ply whose dice each game gets (restart mode: the ply just played), or nullptr (0)
     const long long *game_id;     // [n] or nullptr (the query index)
     uint32_t seed_lo, seed_hi;    // dice key
     int32_t *next_region;         // [16][n] or nullptr
     uint32_t *next_totals;        // [16], zeroed by the caller
+    // restart mode (id_stride > 0): a finished game is replaced in place by the opening record of game id + id_stride,
+    // and the ply / game id of what `next` now holds are written back (the buffers may be ply_of / game_id themselves)
+    long long id_stride;
+    int first_mover;
+    int32_t *ply_out;
+    long long *gid_out;
 };
 
 __device__ __forceinline__ void store_advanced(const AdvanceOut &a, long long q, long long n, int v, int lane, int player)
 {
     const int off1 = __shfl_sync(kFull, v, 26), off2 = __shfl_sync(kFull, v, 27);
     const int win = off1 == 15 ? 0 : (off2 == 15 ? 1 : -1);                  // game.cpp:388-407
-    const unsigned long long g = a.game_id ? (unsigned long long)a.game_id[q] : (unsigned long long)q;
-    const Philox r = philox4x32_10(a.seed_lo, a.seed_hi, (uint32_t)(a.ply_of ? a.ply_of[q] : 0), (uint32_t)g, (uint32_t)(g >> 32), 0u);
-    const int mover = win < 0 ? player ^ 1 : player, d1 = die_of(r.x[0]), d2 = die_of(r.x[1]);
-    const int tail = lane == 28 ? mover : lane == 29 ? d1 : lane == 30 ? d2 : win + 1;
+    unsigned long long g = a.game_id ? (unsigned long long)a.game_id[q] : (unsigned long long)q;
+    int ply = a.ply_of ? a.ply_of[q] : 0;
+    int mover = win < 0 ? player ^ 1 : player, status = win + 1;
+    if (a.id_stride > 0) {
+        ply++;
+        if (win >= 0) {                                                      // train.py:64-97 for the slot's next game
+            g += (unsigned long long)a.id_stride;
+            ply = 0;
+            v = start_value(lane);
+            mover = first_mover_of(a.seed_lo, a.seed_hi, g, a.first_mover);
+            status = kRunning;
+        }
+    }
+    const Philox r = philox4x32_10(a.seed_lo, a.seed_hi, (uint32_t)ply, (uint32_t)g, (uint32_t)(g >> 32), 0u);
+    const int d1 = die_of(r.x[0]), d2 = die_of(r.x[1]);
+    const int tail = lane == 28 ? mover : lane == 29 ? d1 : lane == 30 ? d2 : status;
     a.next[q * 32 + lane] = (int8_t)(lane < 28 ? v : tail);
-    if (a.winner && lane == 0) a.winner[q] = (int8_t)win;
+    if (lane == 0) {
+        if (a.winner) a.winner[q] = (int8_t)win;
+        if (a.ply_out) a.ply_out[q] = ply;
+        if (a.gid_out) a.gid_out[q] = (long long)g;
+    }
     if (a.next_region) {
-        // a finished game is restarted by the caller: an opening position, mid-sized
-        const int b = win < 0 ? order_bucket(lane < 28 ? v : 0, lane, mover, d1, d2) : 6;
+        // a finished game that the CALLER restarts will be an opening position: mid-sized
+        const int b = status == kRunning ? order_bucket(lane < 28 ? v : 0, lane, mover, d1, d2) : 6;
         if (lane == 0) a.next_region[(size_t)b * n + atomicAdd(&a.next_totals[b], 1u)] = (int32_t)q;
     }
 }

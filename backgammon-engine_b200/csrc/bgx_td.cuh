@@ -11,20 +11,20 @@
 //     order as the dense update, so the result is bit-identical to updating all 198 rows every step (which is what
 //     torch does), not an algebraic shortcut.  Per row and missed step: 2 packed instructions (FMUL2, FFMA2).
 //
-// Layout (256 threads, 8 warps): the 198 feature rows are 8-coloured (td_class: the eight features of a point land in
-// eight different classes, rotated by the point, so a position's ~35 live rows spread evenly); warp = class, lane = four
-// hidden units.  A thread owns element (row, 4 units) of every row of its class for the whole kernel, so update, lazy
-// replay and the next forward need no synchronisation.
-//   * Weights and traces of all 198 rows have their home in SHARED MEMORY (2 x 101,376 B of the 227 KB a CTA may own), but
-//     the LIVE rows of a class sit in REGISTERS: 8 slots x (float4 trace + float4 weight) per thread.  A row is loaded into
-//     a free slot when it enters the window (replaying what it slept through on the way) and written back when it leaves;
-//     while it stays - a checker configuration lasts many plies - its per-step update touches no memory at all.  (With
-//     the live rows updated in shared memory the window update moves ~80 KB per step through a 128 B/cycle port: measured
-//     887 of 2,800 cycles per step; with static per-class registers for ALL rows the 25 is-it-live tests per warp and
-//     step cost as much.)  More than 8 live rows in one class - rare - are updated in place in shared memory.
-//   * Every warp lists the live rows of its own class itself, lane r = row r of the class, from the three records of the
-//     window kept in a shared-memory ring: one ballot gives the live set, the feature values travel by shuffle.
-//   * ONE pass over the slots per step updates trace and weight AND accumulates, with the new weights, the first-layer
+// Layout (256 threads, 8 warps, two CTAs = two games per SM): the 198 feature rows are 8-coloured (td_class: the eight
+// features of a point land in eight different classes, rotated by the point, so a position's ~35 live rows spread evenly);
+// warp = class, lane = four hidden units.  A thread owns element (row, 4 units) of every row of its class for the whole
+// kernel - nobody else reads or writes it - so update, lazy replay and the next forward need no synchronisation.
+//   * Weights and traces of a game (2 x 101,376 B) live in a per-CTA scratch in GLOBAL memory that never leaves L2, and the
+//     ~35 live rows of the moment (35 KB) are L1 hits (96.8 % measured): L1 is the cache of the window, by itself.  Keeping
+//     both tables in shared memory instead allows one game per SM (the step is a chain of dependent phases; one game leaves
+//     60 % of the issue slots empty) and pushes ~80 KB per step through the same 128 B/cycle port; explicit register slots
+//     for the live rows cost more instructions (slot tests, slot moves) than the loads they save (measured: 8 slots 95,
+//     4 slots 116, 3 slots 125, none 118 M TD steps/s) - see profiles/r2_td_replay.md for every variant tried.
+//   * Every warp lists the live rows of its own class itself, lane r = row r of the class, from the records of the window
+//     kept in a shared-memory ring that a cp.async stream fills 8 states ahead: one ballot gives the live set, the feature
+//     values travel by shuffle; per step one new feature value per lane (the window moves on by one state).
+//   * ONE pass over the live rows per step updates trace and weight AND accumulates, with the new weights, the first-layer
 //     partial sums of the next step's two forwards (s_t+1 and s_t+2 have all their non-zero features inside the window).
 // Two block barriers per step: class partials -> hidden layer (one sigmoid per lane), output partials -> values.
 //
@@ -52,10 +52,10 @@ struct TdParams {
     const float *flat;         // snapshot, state_dict order (b1, w2, b2 are read from here)
     const float *wt;           // snapshot W1 transposed [198][128]
     float *partial;            // [gridDim.x][25604] per-CTA sum of (w_final - w_snapshot), feature-major W1
+    float *home;               // [gridDim.x][2][198][128] per-CTA home copies of W1 (transposed) and of its traces; L2-resident
     float *final_weights;      // optional [25604] state_dict order (single-game calls)
     double *sq_errors;         // optional [T-1] (single-game calls)
-    unsigned long long *queue; // work queue: next game index (zeroed by the host)
-    unsigned long long *stats; // [3] games replayed, [6] TD steps, [7] row-steps caught up lazily
+    unsigned long long *stats; // [3] games replayed, [5] truncated games skipped, [6] TD steps, [7] row-steps replayed lazily
     double *dstats;            // [0] sum of squared TD errors
     unsigned long long *prof;  // k_td_replay<true>: [8 warps][16] cycles per phase, CTA 0 (bgx_td_profile)
 };
@@ -84,10 +84,10 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b)
 }
 
 constexpr int kTdWarps = 8;
+constexpr int kTdCtasPerSm = 2;                             // two games per SM: one hides the other's dependent-issue latency
 constexpr int kTdThreads = kTdWarps * 32;
 constexpr int kTdClasses = 8;                               // = warps: warp c owns class c
 constexpr int kTdClassRows = 25;                            // classes 0..5 have 25 rows, 6 and 7 have 24
-constexpr int kTdSlots = 8;                                 // live rows of a class held in registers (the switch in k_td_replay lists them)
 
 // the fixed 8-colouring of the feature rows: the eight features of a point (4 per side) go to eight different classes,
 // rotated by the point so that "at least one checker" rows do not pile up in one class
@@ -103,9 +103,7 @@ struct __align__(16) TdCtrl {
 };
 
 // shared memory map (bytes)
-constexpr int kTdOffW = 0;                                           // W1 transposed [198][128]
-constexpr int kTdOffE = kTdOffW + kTableBytes;                       // its eligibility traces
-constexpr int kTdOffC = kTdOffE + kTableBytes;                       // c_k of every step so far
+constexpr int kTdOffC = 0;                                           // c_k of every step so far
 constexpr int kTdOffZ = kTdOffC + kTdMaxSteps * 4;                   // class partial pre-activations [8][128 units][2 states]
 constexpr int kTdOffH = kTdOffZ + kTdClasses * kHidden * 2 * 4;      // hidden activations [128 units][2 states]
 constexpr int kTdOffB1 = kTdOffH + kHidden * 2 * 4;                  // b1 [128]
@@ -214,18 +212,14 @@ __device__ __forceinline__ float td_scale(float lr_hi, float lr_lo, float d)
     return __fadd_rn(prod, __fmaf_rn(lr_lo, d, err));
 }
 
-#ifndef BGX_TD_SWEEP
-#define BGX_TD_SWEEP 0
-#endif
-
 template <bool kProf>
-__global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
+__global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams p)
 {
     extern __shared__ __align__(16) unsigned char td_smem[];
     long long pc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;
     __shared__ long long td_arrive[8];       // kProf: cycles per phase as seen by thread 0
 #define TD_MARK(i) do { if (kProf) { const long long now_ = clock64(); pc[i] += now_ - pt; pt = now_; } } while (0)
-    float4 *W4 = reinterpret_cast<float4 *>(td_smem + kTdOffW), *E4 = reinterpret_cast<float4 *>(td_smem + kTdOffE);
+    float4 *W4 = reinterpret_cast<float4 *>(p.home + (size_t)blockIdx.x * 2 * kTableFloats), *E4 = W4 + kTableFloats / 4;
     float *chist = reinterpret_cast<float *>(td_smem + kTdOffC);
     float *zpart = reinterpret_cast<float *>(td_smem + kTdOffZ);
     float *hs = reinterpret_cast<float *>(td_smem + kTdOffH);
@@ -242,7 +236,6 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
     const bool loader = cls == kTdWarps - 1;                 // this warp pops the queue and feeds the record ring
     TdLaneRow me;
     me.init(cls, lane);
-    const int my_row = td_row_of(cls, min(lane, 24));        // lane r < 25: the feature row it speaks for
 
     float *mine = p.partial + (size_t)blockIdx.x * BGX_NPARAMS_PADDED;
     for (int i = tid; i < BGX_NPARAMS_PADDED; i += kTdThreads) mine[i] = 0.f;
@@ -253,15 +246,9 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
         W4[td_row_of(cls, r) * 32 + lane] = wt4[td_row_of(cls, r) * 32 + lane];
         E4[td_row_of(cls, r) * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float4 SE[kTdSlots], SW[kTdSlots];                       // the slots: trace and weight of a live row, units col .. col + 3
-    int slot_lane[kTdSlots];                                 // which lane (= row of the class) a slot holds
-#pragma unroll
-    for (int s = 0; s < kTdSlots; s++) { SE[s] = SW[s] = make_float4(0.f, 0.f, 0.f, 0.f); slot_lane[s] = 0; }
-    uint32_t occ = 0;                                        // occupied slots
-    int slot = -1;                                           // lane r: the slot holding row r, -1 = the row is at home in shared memory
     int last = -1;                                           // lane r: last step applied to the HOME copy of row r, -1 = untouched in this game
-    int sweep = 0;                                           // where the round-robin catch-up of sleeping rows continues
     const int8_t *traj = nullptr;                            // loader: the game's records
+    long long cursor = blockIdx.x;                           // loader: the next game of this CTA
     unsigned long long steps = 0, games = 0, lazy = 0;
     double sq_sum = 0.0;
 
@@ -270,14 +257,14 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
         td_fetch_wait<0>();                                  // nothing of the previous game is still on its way into the ring
         long long g = -1;
         int T = 0, status = 0;
-        for (;;) {
-            unsigned long long take = 0;
-            if (lane == 0) take = atomicAdd(p.queue, 1ull);
-            take = __shfl_sync(kFull, take, 0);
-            if (take >= (unsigned long long)p.n_games) break;
+        for (;;) {                                           // CTA b replays games b, b + grid, ...: a fixed order, so the CTA's
+            const long long take = cursor;                   // fp32 sum of weight changes is the same in every run
+            cursor += gridDim.x;
+            if (take >= p.n_games) break;
             status = (int)p.slots[take * 32 + 31];
             T = min(min(p.ply[take], p.traj_cap), kTdMaxSteps);
             if ((status == kP1Won || status == kP2Won) && T > 0) { g = (long long)take; break; }   // others: still running or truncated
+            if (status == kTruncated && lane == 0) atomicAdd(p.stats + 5, 1ull);
         }
         if (lane == 0) {
             ctrl->done = g < 0;
@@ -311,7 +298,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
         const float lam = ctrl->lam;
         const double lr = ctrl->lr;
         const float lr_hi = (float)lr, lr_lo = (float)(lr - (double)lr_hi);
-        last = -1; slot = -1; occ = 0;
+        last = -1;
         if (owner) {
             *reinterpret_cast<float4 *>(b1s + col) = *reinterpret_cast<const float4 *>(p.flat + kTableFloats + col);
             *reinterpret_cast<float4 *>(w2s + col) = *reinterpret_cast<const float4 *>(p.flat + kTableFloats + kHidden + col);
@@ -359,77 +346,26 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
                 if ((lane & 15) == 0) red[((t & 1) * 2 + sig_state) * 8 + cls] = y;
             }
             TD_MARK(2);
-            // (3) the live rows of this class; rows that left the window go home, rows that entered it take a free slot
+            // (3) the live rows of this class
             if (t > 0) {                                     // the window moves on by one state: one new feature value per lane
                 x0 = x1; x1 = x2;
                 x2 = t + 2 < T ? me.value((int)ring[((t + 2) & (kTdRing - 1)) * 32 + me.byte], offtab) : 0.f;
             }
             const uint32_t live = __ballot_sync(kFull, x0 != 0.f || x1 != 0.f || x2 != 0.f);
-            const uint32_t resident = __ballot_sync(kFull, slot >= 0);
-            if (resident & ~live) {
-                const uint32_t leave = resident & ~live;
-#pragma unroll
-                for (int s = 0; s < kTdSlots; s++) {
-                    if ((occ >> s & 1) && (leave >> slot_lane[s] & 1)) {
-                        const int idx = td_row_of(cls, slot_lane[s]) * 32 + lane;
-                        E4[idx] = SE[s];
-                        W4[idx] = SW[s];
-                        occ &= ~(1u << s);
-                    }
-                }
-                if (leave >> lane & 1) { slot = -1; last = t - 1; }          // its home copy is current through step t-1
-            }
-            uint32_t enter = live & ~resident;
-            while (enter && occ != (1u << kTdSlots) - 1u) {
-                const int j = __ffs(enter) - 1;
-                enter &= enter - 1;
-                const int s_new = __ffs(~occ) - 1;
-                const int from = __shfl_sync(kFull, last, j) + 1;            // first step its home copy misses (0: untouched, nothing to replay)
-                const int idx = td_row_of(cls, j) * 32 + lane;
-                if (from > 0 && from <= t - 1) lazy += (unsigned)(t - from);
-#define TD_ENTER(S)                                                                                       \
-    case S:                                                                                               \
-        SE[S] = E4[idx]; SW[S] = W4[idx]; slot_lane[S] = j;                                               \
-        if (from > 0 && from <= t - 1) td_replay_row(SE[S], SW[S], from, t - 1, chist, lam);              \
-        break;
-                switch (s_new) { TD_ENTER(0) TD_ENTER(1) TD_ENTER(2) TD_ENTER(3) TD_ENTER(4) TD_ENTER(5) TD_ENTER(6) TD_ENTER(7) }
-#undef TD_ENTER
-                occ |= 1u << s_new;
-                if (lane == j) slot = s_new;
-            }
-            // rows the slots have no room for stay at home and are brought up to date there
-            uint32_t crowd = enter;
-            while (crowd) {
-                const int j = __ffs(crowd) - 1;
-                crowd &= crowd - 1;
+            // rows that enter the window after a sleep replay what they missed (through step t-1) in their home copies
+            uint32_t late = __ballot_sync(kFull, (live >> lane & 1) && last >= 0 && last < t - 1);
+            while (late) {
+                const int j = __ffs(late) - 1;
+                late &= late - 1;
                 const int from = __shfl_sync(kFull, last, j) + 1;
-                if (from > 0 && from <= t - 1) {
-                    const int idx = td_row_of(cls, j) * 32 + lane;
-                    float4 e = E4[idx], w = W4[idx];
-                    td_replay_row(e, w, from, t - 1, chist, lam);
-                    E4[idx] = e;
-                    W4[idx] = w;
-                    lazy += (unsigned)(t - from);
-                }
+                const int idx = td_row_of(cls, j) * 32 + lane;
+                float4 e = E4[idx], w = W4[idx];
+                td_replay_row(e, w, from, t - 1, chist, lam);
+                E4[idx] = e;
+                W4[idx] = w;
+                lazy += (unsigned)(t - from);
             }
-            if (enter >> lane & 1) last = t;                 // (their update of step t follows in (6))
-            // one sleeping row of the class per step is brought up to date at home, round robin: no row is ever more than
-            // ~25 steps behind, so an entering row has little to replay and no warp keeps the others waiting at the barrier
-            if (BGX_TD_SWEEP) {
-                const uint32_t behind = __ballot_sync(kFull, slot < 0 && last >= 0 && last < t - 1);
-                if (behind) {
-                    const int j = (sweep + __ffs(__funnelshift_r(behind, behind, sweep)) - 1) & 31;
-                    const int from = __shfl_sync(kFull, last, j) + 1;
-                    const int idx = td_row_of(cls, j) * 32 + lane;
-                    float4 e = E4[idx], w = W4[idx];
-                    td_replay_row(e, w, from, t - 1, chist, lam);
-                    E4[idx] = e;
-                    W4[idx] = w;
-                    lazy += (unsigned)(t - from);
-                    if (lane == j) last = t - 1;
-                    sweep = (j + 1) & 31;
-                }
-            }
+            if (live >> lane & 1) last = t;                  // (their update of step t follows in (6))
             TD_MARK(3);
             if (kProf && lane == 0) td_arrive[cls] = clock64();
             td_bar();                                        // the step's second barrier
@@ -478,32 +414,32 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
                                           __fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.y), __fsub_rn(1.0f, h0.y)), h0.y),
                                           __fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.z), __fsub_rn(1.0f, h0.z)), h0.z),
                                           __fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.w), __fsub_rn(1.0f, h0.w)), h0.w));
-            // (6) one pass over the slots: e <- lambda*e + grad ; w <- w + c*e (train.py:141-147), and with the NEW weights
+            // (6) one pass over the live rows: e <- lambda*e + grad ; w <- w + c*e (train.py:141-147), and with the NEW weights
             // the first layer of step t+1 (s_t+1 and s_t+2 have all their non-zero features among the live rows)
             z0 = make_float4(0.f, 0.f, 0.f, 0.f); z1 = z0;
             TD_MARK(5);
-#pragma unroll
-            for (int s = 0; s < kTdSlots; s++) {
-                if (occ >> s & 1) {
-                    const float xa = __shfl_sync(kFull, x0, slot_lane[s]), xb = __shfl_sync(kFull, x1, slot_lane[s]);
-                    const float xc = __shfl_sync(kFull, x2, slot_lane[s]);
-                    SE[s] = fma4(lam, SE[s], mul4(xa, gh));
-                    SW[s] = fma4(c, SE[s], SW[s]);
-                    z0 = fma4(xb, SW[s], z0);
-                    z1 = fma4(xc, SW[s], z1);
+            for (uint32_t rows = live; rows;) {              // two live rows per trip: their loads travel together
+                const int ja = __ffs(rows) - 1;
+                rows &= rows - 1;
+                const bool two = rows != 0;
+                const int jb = two ? __ffs(rows) - 1 : ja;
+                rows &= rows - 1;
+                const int ia = td_row_of(cls, ja) * 32 + lane, ib = td_row_of(cls, jb) * 32 + lane;
+                float4 ea = E4[ia], wa = W4[ia], eb = E4[ib], wb = W4[ib];
+                ea = fma4(lam, ea, mul4(__shfl_sync(kFull, x0, ja), gh));
+                wa = fma4(c, ea, wa);
+                E4[ia] = ea;
+                W4[ia] = wa;
+                z0 = fma4(__shfl_sync(kFull, x1, ja), wa, z0);
+                z1 = fma4(__shfl_sync(kFull, x2, ja), wa, z1);
+                if (two) {
+                    eb = fma4(lam, eb, mul4(__shfl_sync(kFull, x0, jb), gh));
+                    wb = fma4(c, eb, wb);
+                    E4[ib] = eb;
+                    W4[ib] = wb;
+                    z0 = fma4(__shfl_sync(kFull, x1, jb), wb, z0);
+                    z1 = fma4(__shfl_sync(kFull, x2, jb), wb, z1);
                 }
-            }
-            crowd = enter;
-            while (crowd) {                                  // the same for live rows that stayed at home
-                const int j = __ffs(crowd) - 1;
-                crowd &= crowd - 1;
-                const int idx = td_row_of(cls, j) * 32 + lane;
-                const float4 e = fma4(lam, E4[idx], mul4(__shfl_sync(kFull, x0, j), gh));
-                const float4 w = fma4(c, e, W4[idx]);
-                E4[idx] = e;
-                W4[idx] = w;
-                z0 = fma4(__shfl_sync(kFull, x1, j), w, z0);
-                z1 = fma4(__shfl_sync(kFull, x2, j), w, z1);
             }
             if (owner) {                                     // fc1.bias, fc2.weight: one thread per four units
                 eb1.x = __fadd_rn(__fmul_rn(lam, eb1.x), gh.x); eb1.y = __fadd_rn(__fmul_rn(lam, eb1.y), gh.y);
@@ -525,17 +461,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
 
         td_bar();                                            // game end: every c_k is visible; the ring and ctrl are free
         if (loader) next_game();                             // its global loads land while the rows are flushed
-        // the slots go home (current through the last step) ...
-#pragma unroll
-        for (int s = 0; s < kTdSlots; s++) {
-            if (occ >> s & 1) {
-                const int idx = td_row_of(cls, slot_lane[s]) * 32 + lane;
-                E4[idx] = SE[s];
-                W4[idx] = SW[s];
-            }
-        }
-        if (slot >= 0) last = T - 1;
-        // ... and every row the game touched replays what it still misses, adds its change to the CTA's sum (feature-major
+        // every row the game touched replays what it still misses, adds its change to the CTA's sum (feature-major
         // W1, then b1, w2, b2) and returns to the snapshot with zero traces
         const float *w2f = w2s + (T & 1) * kHidden;
         if (p.final_weights) {                               // single-game calls: the weights after the replay, state_dict order
@@ -550,27 +476,38 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
             float4 *acc = reinterpret_cast<float4 *>(mine);
             uint32_t touched = __ballot_sync(kFull, last >= 0);
             if (p.final_weights) touched = cls < 6 ? 0x1FFFFFFu : 0xFFFFFFu;
-            while (touched) {
-                const int j = __ffs(touched) - 1;
-                touched &= touched - 1;
-                const int f = td_row_of(cls, j), idx = f * 32 + lane;
-                const int from = __shfl_sync(kFull, last, j) + 1;
-                float4 w = W4[idx];
-                if (from > 0 && from <= T - 1) {
-                    float4 e = E4[idx];
-                    td_replay_row(e, w, from, T - 1, chist, lam);
-                    lazy += (unsigned)(T - from);
+            while (touched) {                                // four rows per trip: their global loads travel together
+                int idx[4], from[4], f[4];
+                bool ok[4];
+                float4 e[4], w[4], o[4], a[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    ok[i] = touched != 0;
+                    const int j = ok[i] ? __ffs(touched) - 1 : 0;
+                    touched &= touched - 1;
+                    f[i] = td_row_of(cls, j);
+                    idx[i] = f[i] * 32 + lane;
+                    from[i] = __shfl_sync(kFull, last, j) + 1;
                 }
-                const float4 o = wt4[idx];
-                if (p.final_weights) {
-                    p.final_weights[(col + 0) * kFeatures + f] = w.x; p.final_weights[(col + 1) * kFeatures + f] = w.y;
-                    p.final_weights[(col + 2) * kFeatures + f] = w.z; p.final_weights[(col + 3) * kFeatures + f] = w.w;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (ok[i]) { e[i] = E4[idx[i]]; w[i] = W4[idx[i]]; o[i] = wt4[idx[i]]; a[i] = acc[idx[i]]; }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (!ok[i]) continue;
+                    if (from[i] > 0 && from[i] <= T - 1) {
+                        td_replay_row(e[i], w[i], from[i], T - 1, chist, lam);
+                        lazy += (unsigned)(T - from[i]);
+                    }
+                    if (p.final_weights) {
+                        p.final_weights[(col + 0) * kFeatures + f[i]] = w[i].x; p.final_weights[(col + 1) * kFeatures + f[i]] = w[i].y;
+                        p.final_weights[(col + 2) * kFeatures + f[i]] = w[i].z; p.final_weights[(col + 3) * kFeatures + f[i]] = w[i].w;
+                    }
+                    a[i].x += w[i].x - o[i].x; a[i].y += w[i].y - o[i].y; a[i].z += w[i].z - o[i].z; a[i].w += w[i].w - o[i].w;
+                    acc[idx[i]] = a[i];
+                    W4[idx[i]] = o[i];
+                    E4[idx[i]] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                float4 a = acc[idx];
-                a.x += w.x - o.x; a.y += w.y - o.y; a.z += w.z - o.z; a.w += w.w - o.w;
-                acc[idx] = a;
-                W4[idx] = o;
-                E4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (owner)
                 for (int k = 0; k < 4; k++) {
@@ -593,7 +530,6 @@ __global__ void __launch_bounds__(kTdThreads, 1) k_td_replay(TdParams p)
         for (int i = 0; i < 14; i++) p.prof[cls * 16 + i] = (unsigned long long)pc[i];
         p.prof[cls * 16 + 15] = steps;
     }
-    (void)my_row;
 #undef TD_MARK
 }
 

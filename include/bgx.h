@@ -133,7 +133,11 @@ int bgx_enumerate_summary_host(bgx_engine *e, const int8_t *queries, int64_t n_q
  * states[row][32] (RECORD, byte 28 = mover). */
 int bgx_enumerate(bgx_engine *e, const int8_t *queries, int64_t n_queries, const int64_t *offsets,
                   int8_t *seq_moves, int8_t *seq_len, int8_t *states);
-/* host convenience: runs summary + scan + enumerate; *total = sum N.  Output buffers hold
+/* The allocation pass of the materialised form, on DEVICE buffers: n_seq[n] (int32) = size of every query's list
+ * (a count-only walk: no distinct-afterstate table, no digest), offsets[n + 1] (int64) = their exclusive prefix sum,
+ * offsets[n] = total rows.  What bgx_enumerate takes as `offsets`. */
+int bgx_enumerate_count(bgx_engine *e, const int8_t *queries, int64_t n_queries, int32_t *n_seq, int64_t *offsets);
+/* host convenience: count + device scan + enumerate; *total = sum N.  Output buffers hold
  * `cap` rows; BGX_E_CAPACITY (with *total set) when more are needed. offsets may be NULL. */
 int bgx_enumerate_host(bgx_engine *e, const int8_t *queries, int64_t n_queries, int64_t cap,
                        int64_t *offsets, int8_t *seq_moves, int8_t *seq_len, int8_t *states,
@@ -192,6 +196,15 @@ int bgx_lane_wait(bgx_engine *e, int lane);
 int bgx_play_ply_host_async(bgx_engine *e, int lane, const int8_t *records, const int32_t *next_ply, const int64_t *game_id,
                             int64_t n, float epsilon, uint64_t explore_seed, uint64_t dice_seed,
                             int8_t *next_records, int8_t *winner, float *value, int32_t *n_seq);
+
+/* The same loop iteration with the population's bookkeeping done on the device (train.py:199-220 / 527-547 run game after
+ * game in every slot): ply[i] holds the ply number of records[i] and game_id[i] its game; on return they describe
+ * next_records[i].  A game that ended is replaced IN PLACE by its slot's next game: id + id_stride, the opening position
+ * (game.cpp:251), first mover by `first_mover` (BGX_FIRST_*), the dice of its ply 0; winner[i] still reports 0 / 1 for the
+ * game that ended (-1 otherwise).  The caller's loop is submit / wait / swap buffers, nothing per game. */
+int bgx_play_ply_restart_host_async(bgx_engine *e, int lane, const int8_t *records, int32_t *ply, int64_t *game_id, int64_t id_stride,
+                                    int first_mover, int64_t n, float epsilon, uint64_t explore_seed, uint64_t dice_seed,
+                                    int8_t *next_records, int8_t *winner, float *value, int32_t *n_seq);
 
 /* The rest of a host-driven ply (train.py:113-121, benchmark.py:88-101) for n games at once, on
  * DEVICE buffers: next[i] = chosen[i] (an afterstate RECORD as bgx_select_moves writes it) with
@@ -266,17 +279,28 @@ int bgx_selfplay_sample_host(bgx_engine *e, int32_t per_game, uint64_t seed, int
 /* Exact online TD(lambda) replay of every finished slot trajectory, each from the engine's
  * current weights (the round snapshot) with zeroed traces; the per-game weight changes are
  * SUMMED into delta[BGX_NPARAMS_PADDED] (device fp32, WEIGHTS order flattened: W1,b1,w2,b2;
- * overwritten, not accumulated).  Weights are not modified. */
-int bgx_td_replay(bgx_engine *e, float lr, float lambda, float *delta_dev, bgx_stats *out);
+ * overwritten, not accumulated).  Weights are not modified.  lr and lambda are doubles, as
+ * model.learning_rate / model.lambda_decay are Python floats: lr * td_error is formed in
+ * float64 and rounded to fp32 (train.py:147), lambda is rounded to fp32 when it meets the
+ * trace tensor.  Trajectories of up to BGX_TD_MAX_STEPS recorded plies (traj_cap above that
+ * is refused); out->truncated counts the slots skipped because their game hit traj_cap. */
+#define BGX_TD_MAX_STEPS 2048
+int bgx_td_replay(bgx_engine *e, double lr, double lambda, float *delta_dev, bgx_stats *out);
+/* The same with the reference's PER-GAME schedule (train.py:538 calls update_learning_params(games_done + k + 1)
+ * before replaying the k-th game of a round; model.py:69-73: lr = max(0.01, 0.1 * 0.96^(episode // 40000)),
+ * lambda = max(0.7, 0.9 * 0.96^(episode // 30000))): the game in slot s of this engine is episode
+ * games_done + first_id + s + 1, where first_id is the population's first global slot (bgx_selfplay_init) -
+ * the k-th game of the round in global slot order. */
+int bgx_td_replay_scheduled(bgx_engine *e, int64_t games_done, float *delta_dev, bgx_stats *out);
 /* weights += scale * delta   (after the caller's allreduce over ranks) */
 int bgx_apply_delta(bgx_engine *e, const float *delta_dev, float scale);
 /* both in one call for a single-GPU caller: delta_host[BGX_NPARAMS] (may be NULL) receives the summed weight
  * change, then weights += scale * delta (scale 0: weights untouched).  One round of train.py:527-547. */
-int bgx_td_round_host(bgx_engine *e, float lr, float lambda, float scale, float *delta_host, bgx_stats *out);
+int bgx_td_round_host(bgx_engine *e, double lr, double lambda, float scale, float *delta_host, bgx_stats *out);
 /* one external trajectory (host buffers): records[T][32] with byte 28 = the turn flag of each
  * pre-move state; new_* receive the weights after the replay; sq_errors[T-1] may be NULL */
 int bgx_td_replay_host(bgx_engine *e, const int8_t *records, int32_t T, int player1_won,
-                       float lr, float lambda,
+                       double lr, double lambda,
                        float *new_W1, float *new_b1, float *new_w2, float *new_b2, double *sq_errors);
 
 /* ------------------------------------------------------------------------------------

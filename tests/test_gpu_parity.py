@@ -559,25 +559,28 @@ def test_selfplay_step_restarts_and_rank_invariance(eng, golden):
 
 # ------------------------------------------------------------------ TD(lambda)
 
-def td_tol(dref, wref):
-    return 1e-5 * np.max(np.abs(dref)) + np.spacing(np.float32(np.max(np.abs(wref))))
+def td_game_bound(tag, k):
+    """What a SINGLE game's max|dw - dw_ref| / max|dw_ref| may be: the worst of the 1,024 fixture games + 20 % (GPU_VS_TORCH below,
+    all coordinates).  1e-5 holds for the median game, not for every game - for no fp32 implementation (RESTATEMENT_VS_TORCH)."""
+    return 1.2 * GPU_VS_TORCH[tag]["all"][k][2]
 
 
 def test_td_replay_host_golden(eng, golden):
-    """apply_td_updates (train.py:124-172) on the reference's own trajectories."""
+    """apply_td_updates (train.py:124-172) on the reference's own trajectories (five reference-played games)."""
     g = golden("games.npz")
     gm = golden("model.npz")
     for name in g["names"]:
         name = str(name)
-        w0 = golden_weights(gm, "rand" if name.startswith("rand") else "trained")
+        tag = "rand" if name.startswith("rand") else "trained"
+        w0 = golden_weights(gm, tag)
         eng.set_weights(*w0)
         rec = records_from(g[f"{name}.pre"], g[f"{name}.player"])
         new, sq = eng.td_replay_host(rec, int(g[f"{name}.winner"]) == 0, float(g[f"{name}.lr"]), float(g[f"{name}.lam"]))
         for a, b, k in zip(new, w0, ("W1", "b1", "w2", "b2")):
             ref_new = g[f"{name}.new_{k}"].reshape(-1)
-            dref = ref_new - np.asarray(b).reshape(-1)
-            dgot = np.asarray(a).reshape(-1) - np.asarray(b).reshape(-1)
-            assert np.max(np.abs(dgot - dref)) <= td_tol(dref, ref_new), (name, k)
+            dref = ref_new.astype(np.float64) - np.asarray(b).reshape(-1)
+            dgot = np.asarray(a).reshape(-1).astype(np.float64) - np.asarray(b).reshape(-1)
+            assert np.max(np.abs(dgot - dref)) <= td_game_bound(tag, k) * np.max(np.abs(dref)), (name, k)
         assert np.max(np.abs(np.sqrt(sq) - np.sqrt(g[f"{name}.losses"]))) <= 1e-5, name
 
 
@@ -619,59 +622,132 @@ def test_td_round_delta_is_sum_of_per_game_replays(eng, orc, golden, tag):
     assert np.allclose(after, flat0 + 0.5 * got[:25601], rtol=0, atol=1e-7 * np.max(np.abs(flat0)) + 1e-9)
 
 
+# max|dw - dw_ref| / max|dw_ref| per game of bgx_td_replay_host against the reference's own apply_td_updates (torch) on the
+# 1,024 fixture trajectories per weight set, (p50, p99, max) as measured on a B200 (tools/td_parity_probe.py,
+# profiles/r2_td_parity.json).  "fixture": over the 320 coordinates per game the committed fixture holds; "all": over all
+# 25,601 coordinates against the live torch replay (tests/ref_td.py, which reproduces the fixture bit for bit on the box).
+# The asserted bounds are these + 20 %.  For scale, the same distances for the fp32 C restatement of the reference are
+# RESTATEMENT_VS_TORCH in tests/test_oracle_golden.py: no fp32 implementation sits within 1e-5 of torch on every game.
+GPU_VS_TORCH = {
+    "rand": {"fixture": {"W1": (3.57e-6, 1.09e-5, 1.45e-5), "b1": (3.15e-6, 1.27e-5, 1.71e-5), "w2": (1.11e-6, 3.79e-6, 5.19e-6), "b2": (8.10e-7, 3.49e-6, 5.09e-6)},
+             "all": {"W1": (7.92e-6, 1.90e-5, 2.19e-5), "b1": (3.32e-6, 1.29e-5, 1.71e-5), "w2": (1.11e-6, 3.79e-6, 5.19e-6), "b2": (8.10e-7, 3.49e-6, 5.09e-6)}},
+    "trained": {"fixture": {"W1": (9.26e-6, 4.26e-5, 8.39e-5), "b1": (4.97e-6, 3.80e-5, 9.73e-5), "w2": (3.12e-6, 1.35e-5, 2.54e-5), "b2": (4.63e-7, 1.17e-5, 2.25e-4)},
+                "all": {"W1": (1.25e-5, 4.26e-5, 8.39e-5), "b1": (8.27e-6, 3.80e-5, 9.73e-5), "w2": (3.36e-6, 1.36e-5, 2.54e-5), "b2": (4.63e-7, 1.17e-5, 2.25e-4)}},
+}
+
+
 @pytest.mark.parametrize("tag", ["rand", "trained"])
-def test_td_per_game_parity_thousand_trajectories(eng, orc, golden, tag):
-    """per-game weight change on >= 1,000 exported self-play trajectories, replayed one by one by
-    bgx_td_replay_host and by the oracle's apply_td_updates restatement (train.py:124-172) from the same snapshot.
-
-    A TD error is the difference of two fp32 values that agree in their first 2-4 digits, so ANY two fp32
-    implementations scatter by ~1e-5 of max|dw| per game (torch itself sits 1e-5 from the exact result on the golden
-    games, test_td_replay_f64_yardstick).  Two statements are therefore checked: (i) against the fp32 oracle the
-    error stays at that noise level - median within the documented tolerance, bounded tails; (ii) against the exact
-    float64 replay the GPU kernel is no farther away than the fp32 oracle is, quantile by quantile."""
-    import os
-    from concurrent.futures import ThreadPoolExecutor
+def test_td_per_game_parity_vs_the_reference_update(eng, orc, golden, tag):
+    """the per-game weight change of k_td_replay on 1,024 GPU-exported self-play trajectories per weight
+    set against the REFERENCE'S OWN apply_td_updates (train.py:124-172, torch autograd) from the same snapshot:
+      (i)   against the committed results of the unmodified reference (tests/golden/td_parity.npz) on every game;
+      (ii)  against a live torch replay of all games over all 25,601 coordinates, after checking that this replay reproduces
+            the fixture bit for bit (so (ii) is a statement about the reference, not about a restatement);
+      (iii) against the exact float64 replay the kernel is as close as torch itself is;
+      (iv)  the per-step TD errors agree at the value tolerance."""
     from oracle.oracle import td_replay_f64
-    w0 = golden_weights(golden("model.npz"), tag)
-    eng.set_weights(*w0)
-    n = 1024
-    eng.selfplay_init(n, first_id=5000, id_stride=n, seed=SEED, traj_cap=2048)
-    eng.selfplay_round()
-    rec, ply, gid = eng.selfplay_read()
-    assert np.all((rec[:, 31] == 1) | (rec[:, 31] == 2))
-    trajs = [eng.export_trajectory(s)[0].copy() for s in range(n)]
-    won = [bool(rec[s, 31] == 1) for s in range(n)]
-    assert sum(len(t) for t in trajs) == int(ply.sum())
+    from ref_td import replay_many
+    from td_fixture import BOUNDS, TENSORS, TdFixture, engine_errors, quantiles
+    fx = TdFixture(golden, tag)
+    err, worst_sq, news = engine_errors(eng, fx)
+    assert worst_sq <= 1e-5                                                  # (iv)
+    got = quantiles(err)
+    for name in TENSORS:                                                     # (i)
+        for g_, w_, what in zip(got[name], GPU_VS_TORCH[tag]["fixture"][name], ("p50", "p99", "max")):
+            assert g_ <= 1.2 * w_, (tag, name, what, g_, w_)
 
-    def cpu(s):
-        pre = trajs[s]
-        X = np.concatenate([orc.encode(pre[t:t + 1, :28].astype(np.int32), int(pre[t, 28])) for t in range(len(pre))])
-        return orc.td_replay(w0, X, won[s], 0.1, 0.9), td_replay_f64(w0, X, won[s], 0.1, 0.9)
-    with ThreadPoolExecutor(os.cpu_count() or 4) as ex:
-        refs = list(ex.map(cpu, range(n)))
-
-    tolr = np.zeros((n, 4)); e_gpu = np.zeros((n, 4)); e_orc = np.zeros((n, 4)); sq_err = 0.0
-    for s in range(n):
-        new, sq = eng.td_replay_host(trajs[s], won[s], 0.1, 0.9)
-        (new32, sq32), new64 = refs[s]
-        if len(sq):
-            sq_err = max(sq_err, float(np.max(np.abs(np.sqrt(sq) - np.sqrt(sq32)))))
+    def enc(r):
+        return np.concatenate([orc.encode(r[t:t + 1, :28].astype(np.int32), int(r[t, 28])) for t in range(len(r))])
+    X = [enc(fx.trajectory(g)) for g in range(fx.n)]
+    live = replay_many([(fx.w0, X[g], int(fx.p1_won[g]), fx.lr, fx.lam) for g in range(fx.n)])
+    full = np.zeros((fx.n, 4))
+    for g, (new, sq) in enumerate(live):                                     # (ii)
+        assert np.array_equal(new[fx.coords(g)], fx.new_at[g]), ("the live torch replay is not the fixture's", tag, g)
+        d_ref = new.astype(np.float64) - fx.w0_flat
+        d = np.abs(news[g].astype(np.float64) - new.astype(np.float64))
         for k in range(4):
-            b = np.asarray(w0[k], np.float32).reshape(-1)
-            dgot = np.asarray(new[k]).reshape(-1).astype(np.float64) - b
-            d32 = np.asarray(new32[k]).reshape(-1).astype(np.float64) - b
-            d64 = np.asarray(new64[k]).reshape(-1) - b.astype(np.float64)
-            tolr[s, k] = np.max(np.abs(dgot - d32)) / (1e-5 * np.max(np.abs(d32)) + np.spacing(np.float32(np.max(np.abs(b)))))
-            e_gpu[s, k] = np.max(np.abs(dgot - d64)) / np.max(np.abs(d64))
-            e_orc[s, k] = np.max(np.abs(d32 - d64)) / np.max(np.abs(d64))
-    assert sq_err <= 1e-5                                        # per-step TD errors at the value tolerance
-    for k, name in enumerate(("W1", "b1", "w2", "b2")):
-        # (i) fp32 against fp32: measured medians 0.06-0.71 of the tolerance, p99 <= 1.8, worst single game 6.9 (b2, one number)
-        assert np.median(tolr[:, k]) <= 1.0, (tag, name, np.median(tolr[:, k]))
-        assert np.quantile(tolr[:, k], 0.99) <= 3.0 and np.max(tolr[:, k]) <= 12.0, (tag, name, np.max(tolr[:, k]))
-        # (ii) against exact arithmetic the kernel is as good as the fp32 restatement of the reference
-        for q, slack in ((0.5, 1.15), (0.9, 1.2), (0.99, 1.35), (1.0, 1.5)):
-            assert np.quantile(e_gpu[:, k], q) <= slack * np.quantile(e_orc[:, k], q), (tag, name, q)
+            full[g, k] = d[BOUNDS[k]:BOUNDS[k + 1]].max() / np.abs(d_ref[BOUNDS[k]:BOUNDS[k + 1]]).max()
+    got = quantiles(full)
+    for name in TENSORS:
+        for g_, w_, what in zip(got[name], GPU_VS_TORCH[tag]["all"][name], ("p50", "p99", "max")):
+            assert g_ <= 1.2 * w_, (tag, name, "all coordinates", what, g_, w_)
+    games = range(0, fx.n, 4)                                                # (iii) 256 games, all coordinates
+    e_gpu, e_ref = np.zeros((len(games), 4)), np.zeros((len(games), 4))
+    for i, g in enumerate(games):
+        new64 = np.concatenate([np.asarray(a).reshape(-1) for a in td_replay_f64(fx.w0, X[g], fx.p1_won[g], fx.lr, fx.lam)])
+        d64 = new64 - fx.w0_flat
+        for k in range(4):
+            sl = slice(BOUNDS[k], BOUNDS[k + 1])
+            e_gpu[i, k] = np.abs(news[g][sl] - new64[sl]).max() / np.abs(d64[sl]).max()
+            e_ref[i, k] = np.abs(live[g][0][sl] - new64[sl]).max() / np.abs(d64[sl]).max()
+    for k, name in enumerate(TENSORS):
+        # measured kernel / torch: W1 0.98 / 0.98 / 1.11 (p50 / p99 / max), the small tensors 0.7 .. 1.23 (b2 is one number)
+        for q, slack in ((0.5, 1.3), (0.99, 1.3), (1.0, 1.4)):
+            assert np.quantile(e_gpu[:, k], q) <= slack * np.quantile(e_ref[:, k], q), (tag, name, q)
+
+
+def test_td_replay_scheduled_follows_the_reference_schedule_per_game(eng, golden):
+    """train.py:538 calls update_learning_params(games_done + k + 1) before the k-th game of a round (model.py:69-73).
+    bgx_td_replay_scheduled looks that schedule up per game: across the 30,000-game boundary of lambda and the 40,000-game
+    boundary of lr the summed weight change equals the sum of fixed-(lr, lambda) replays of the games on either side."""
+    import torch
+    from bgx.model import TDLGammonModel
+    w0 = golden_weights(golden("model.npz"), "trained")
+    eng.set_weights(*w0)
+    n = 64
+    eng.selfplay_init(n, first_id=0, id_stride=n, seed=SEED, traj_cap=2048)
+    eng.selfplay_round()
+    m = TDLGammonModel()
+    delta = torch.zeros(25604, device="cuda", dtype=torch.float32)
+    for boundary in (30000, 40000, 120000):
+        games_done = boundary - 40                                          # slots 0..38 are episodes <= boundary - 1, the rest beyond
+        eng.td_replay_scheduled(games_done, delta)
+        got = delta.cpu().numpy().astype(np.float64)
+        want = np.zeros(25604)
+        trajs = [eng.export_trajectory(s)[0] for s in range(n)]
+        rec, _, _ = eng.selfplay_read()
+        flat0 = np.concatenate([np.asarray(a, np.float32).reshape(-1) for a in w0])
+        params = set()
+        for s in range(n):
+            m.update_learning_params(games_done + s + 1)
+            params.add((m.learning_rate, m.lambda_decay))
+            new, _ = eng.td_replay_host(trajs[s], rec[s, 31] == 1, m.learning_rate, m.lambda_decay)
+            want[:25601] += np.concatenate([np.asarray(a, np.float32).reshape(-1) for a in new]).astype(np.float64) - flat0
+        assert len(params) == 2, (boundary, params)                          # the round really straddles a schedule step
+        assert np.max(np.abs(got - want)) <= 2e-6 * np.max(np.abs(want)) + n * np.spacing(np.float32(np.max(np.abs(flat0))))
+    eng.set_weights(*w0)
+
+
+def test_gpu_trainer_owns_its_engine_and_checkpoints_see_its_weights(golden, tmp_path):
+    """A GpuTrainer keeps the live weights in a private engine: batched calls through the module's own engine neither
+    overwrite them nor free its population, and save_checkpoint writes the trained weights."""
+    import torch
+    from bgx.model import TDLGammonModel
+    from bgx.train import GpuTrainer, play_games_batch, save_checkpoint
+    torch.manual_seed(3)
+    m = TDLGammonModel()
+    before = np.concatenate([a.reshape(-1) for a in m.weights_np()])
+    tr = GpuTrainer(m, 64, delta_scale=1.0 / 64)
+    try:
+        tr.round()
+        trained = np.concatenate([np.asarray(a).reshape(-1) for a in tr.eng.get_weights()])
+        assert not np.array_equal(trained, before)
+        games = play_games_batch(m, 4, seed=SEED)                            # the module's own engine: stale weights, own population
+        assert len(games) == 4
+        assert np.array_equal(np.concatenate([np.asarray(a).reshape(-1) for a in tr.eng.get_weights()]), trained)
+        st = tr.round()                                                      # the trainer's population is intact
+        assert st["games_finished"] == 64 and st["td_steps"] > 0
+        trained = np.concatenate([np.asarray(a).reshape(-1) for a in tr.eng.get_weights()])
+        path = str(tmp_path / "ckpt.pth")
+        save_checkpoint(m, path)                                             # pulls the trainer's weights first
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+        saved = np.concatenate([sd[k].numpy().reshape(-1) for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")])
+        assert np.array_equal(saved, trained)
+        # the module's engine is refreshed only when the module's parameters changed
+        e = m.engine(0)
+        assert np.array_equal(np.concatenate([np.asarray(a).reshape(-1) for a in e.get_weights()]), trained)
+    finally:
+        tr.eng.close()
 
 
 # ------------------------------------------------------------------ batched head-to-head (train.py:262-302, benchmark.py:64-130)
@@ -762,7 +838,8 @@ def test_play_games_batch_feeds_the_reference_td_update(eng, golden):
     for a, name in zip(new, ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")):
         ref = m.state_dict()[name].numpy().reshape(-1)
         d_ref = ref - sd[name].numpy().reshape(-1)
-        assert np.max(np.abs(np.asarray(a).reshape(-1) - ref)) <= td_tol(d_ref, ref), name
+        k = {"fc1.weight": "W1", "fc1.bias": "b1", "fc2.weight": "w2", "fc2.bias": "b2"}[name]
+        assert np.max(np.abs(np.asarray(a).reshape(-1) - ref)) <= td_game_bound("trained", k) * np.max(np.abs(d_ref)), name
 
 
 # ------------------------------------------------------------------ the pybind11 module's batched entry points
