@@ -77,6 +77,10 @@ class BatchEngine:
         L.check(self._lib.bgx_kernel_config(self._h, C.byref(a), C.byref(b)))
         return {"k_selfplay": a.value, "k_select": b.value}
 
+    def set_option(self, key, value):
+        """Tuning knobs of the fused ply kernels (bgx_set_option): selfplay_warps, select_warps, select_lane_grid, ..."""
+        L.check(self._lib.bgx_set_option(self._h, key.encode(), int(value)))
+
     def device_props(self):
         sm, khz, mem = C.c_int(), C.c_int(), C.c_int64()
         L.check(self._lib.bgx_device_props(self._h, C.byref(sm), C.byref(khz), C.byref(mem)))

@@ -25,7 +25,8 @@ class BgxError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("plies", C.c_int64), ("sequences", C.c_int64), ("scored", C.c_int64),
                 ("games_finished", C.c_int64), ("p1_wins", C.c_int64), ("truncated", C.c_int64),
-                ("td_steps", C.c_int64), ("td_sq_error", C.c_double), ("tree_edges", C.c_int64)]
+                ("td_steps", C.c_int64), ("td_sq_error", C.c_double), ("tree_edges", C.c_int64),
+                ("td_live_rows", C.c_int64), ("td_lazy_row_steps", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -67,6 +68,7 @@ _SIGNATURES = {
     "bgx_play_ply_restart_host_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _i64, C.c_int, _i64, C.c_float, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
     "bgx_lane_wait": (C.c_int, [_vp, C.c_int]),
     "bgx_advance": (C.c_int, [_vp, _vp, _vp, _i64, C.c_uint64, C.c_int32, _vp, _vp]),
+    "bgx_set_host_threads": (C.c_int, [C.c_int]),
     "bgx_advance_host": (C.c_int, [_vp, _vp, _i64, C.c_uint64, _vp, _vp, _vp]),
     # section 4
     "bgx_selfplay_init": (C.c_int, [_vp, _i64, _i64, _i64, C.c_uint64, C.c_int, C.c_int32]),
@@ -84,10 +86,16 @@ _SIGNATURES = {
     "bgx_apply_delta": (C.c_int, [_vp, _vp, C.c_float]),
     "bgx_td_round_host": (C.c_int, [_vp, C.c_double, C.c_double, C.c_float, _vp, C.POINTER(Stats)]),
     "bgx_td_replay_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "bgx_allreduce_delta": (C.c_int, [_vp, _vp, _vp]),
+    "bgx_nccl_load": (C.c_int, [C.c_char_p]),
+    "bgx_nccl_unique_id": (C.c_int, [_vp]),
+    "bgx_nccl_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
+    "bgx_nccl_comm_destroy": (C.c_int, [_vp]),
     # section 6
     "bgx_launch_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "bgx_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "bgx_kernel_config": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bgx_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "bgx_td_profile": (C.c_int, [_vp, C.c_int, _vp]),
     "bgx_device_props": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64)]),
 }

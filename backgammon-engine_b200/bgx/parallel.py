@@ -30,6 +30,51 @@ def allreduce_delta(delta, dist=None):
     return delta
 
 
+def torch_nccl_path():
+    """The libnccl that torch itself loaded (the wheel bundles its own); None if it cannot be found."""
+    import glob
+    import os
+    import sys
+    for base in sys.path:
+        hits = glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so*"))
+        if hits:
+            return sorted(hits)[0]
+    return None
+
+
+class NcclComm:
+    """One NCCL communicator made through libbgx's C-ABI (bgx_nccl_*), for bgx_allreduce_delta.  torch.distributed is used
+    only to hand rank 0's 128-byte unique id to the other ranks - any transport would do."""
+
+    def __init__(self, engine, dist):
+        import ctypes as C
+        from . import lib as L
+        self._lib, self._eng, self._h = L.load(), engine, C.c_void_p()
+        path = torch_nccl_path()
+        L.check(self._lib.bgx_nccl_load(path.encode() if path else None))
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            L.check(self._lib.bgx_nccl_unique_id(ident.numpy().ctypes.data))
+        ident = ident.cuda() if dist.get_backend() == "nccl" else ident
+        dist.broadcast(ident, 0)
+        ident = ident.cpu().contiguous()
+        L.check(self._lib.bgx_nccl_comm_init(engine._h, world, rank, ident.numpy().ctypes.data, C.byref(self._h)))
+
+    def allreduce_delta(self, delta):
+        """Sum fp32[25604] over the ranks in place on the engine's stream (bgx_allreduce_delta)."""
+        from . import lib as L
+        if delta.numel() != NPARAMS_PADDED or delta.dtype != torch.float32 or not delta.is_cuda:
+            raise ValueError("delta must be a CUDA fp32[25604] tensor")
+        L.check(self._lib.bgx_allreduce_delta(self._eng._h, self._h, L.ptr(delta)))
+        return delta
+
+    def close(self):
+        if self._h:
+            self._lib.bgx_nccl_comm_destroy(self._h)
+            self._h = None
+
+
 def split_weights(flat):
     """flat fp32[>=25601] in state_dict order -> (W1[128,198], b1[128], w2[1,128], b2[1])"""
     flat = flat[:NPARAMS]

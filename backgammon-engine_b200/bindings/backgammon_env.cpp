@@ -339,7 +339,7 @@ class BatchEngine {
         py::dict d;
         d["plies"] = s.plies; d["sequences"] = s.sequences; d["scored"] = s.scored; d["games_finished"] = s.games_finished;
         d["p1_wins"] = s.p1_wins; d["truncated"] = s.truncated; d["td_steps"] = s.td_steps; d["td_sq_error"] = s.td_sq_error;
-        d["tree_edges"] = s.tree_edges;
+        d["tree_edges"] = s.tree_edges; d["td_live_rows"] = s.td_live_rows; d["td_lazy_row_steps"] = s.td_lazy_row_steps;
         return d;
     }
     void selfplay_init(int64_t n_slots, int64_t first_id, int64_t id_stride, uint64_t seed, int first_mover, int traj_cap, bool record_chosen)

@@ -6,10 +6,13 @@
 #include "bgx_kernels.cuh"
 #include "bgx_td.cuh"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 using namespace bgx;
@@ -69,10 +72,10 @@ struct bgx_engine {
     bool td_profile = false;
     int td_grid = 0;
     int lane_grid = -1;                      // CTAs of a k_select launch on an asynchronous lane: half the SMs, so that two lanes'
-                                             // batches are resident at once (0: one per SM; BGX_SELECT_LANE_GRID)
-    long long select_order_max = 1 << 21;    // launches up to this many queries get a sorted queue (BGX_SELECT_ORDER_MAX; 64 B of scratch per query)
-    int select_urgent_min = 7, select_giant_min = kGiantMinChildren, select_urgent_from_pct = 0;   // k_select help policy (BGX_SELECT_*)
-    int selfplay_warps = 24, select_warps = 24;   // warps per CTA of k_selfplay / k_select (measured best; BGX_*_WARPS override)
+                                             // batches are resident at once (0: one per SM); this and the next: bgx_set_option
+    long long select_order_max = 1 << 21;    // launches up to this many queries get a sorted queue (64 B of scratch per query)
+    int select_urgent_min = 7, select_giant_min = kGiantMinChildren, select_urgent_from_pct = 0;   // k_select help policy
+    int selfplay_warps = 24, select_warps = 24;   // warps per CTA of k_selfplay / k_select (measured best)
     // bookkeeping
     long long launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
@@ -120,8 +123,10 @@ static int scratch(bgx_engine *e, int i, size_t bytes, void **out)
     return BGX_OK;
 }
 
-static void tick(bgx_engine *e) { cudaEventRecord(e->ev0, e->stream); }
-static void tock(bgx_engine *e) { cudaEventRecord(e->ev1, e->stream); e->timed = true; }
+static int tick_(bgx_engine *e) { CU(cudaEventRecord(e->ev0, e->stream)); return BGX_OK; }
+static int tock_(bgx_engine *e) { CU(cudaEventRecord(e->ev1, e->stream)); e->timed = true; return BGX_OK; }
+#define tick(e) do { const int rc__ = tick_(e); if (rc__ != BGX_OK) return rc__; } while (0)
+#define tock(e) do { const int rc__ = tock_(e); if (rc__ != BGX_OK) return rc__; } while (0)
 
 static int game_grid(bgx_engine *e) { return e->sm_count; }   // persistent: one 16-warp CTA per SM
 
@@ -134,6 +139,46 @@ int bgx_device_count(int *n)
     cudaError_t err = cudaGetDeviceCount(&c);
     if (err != cudaSuccess) { *n = 0; set_error("cudaGetDeviceCount: %s", cudaGetErrorString(err)); return BGX_E_NO_DEVICE; }
     *n = c;
+    return BGX_OK;
+}
+
+// everything bgx_create allocates hangs off *e, so a failure half-way is undone by bgx_destroy
+static int create_into(bgx_engine *e, int device, const cudaDeviceProp &prop)
+{
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    e->global_mem = prop.totalGlobalMem;
+    CU(cudaDeviceGetAttribute(&e->clock_khz, cudaDevAttrClockRate, device));
+    CU(cudaMalloc(&e->flat, BGX_NPARAMS_PADDED * sizeof(float)));
+    CU(cudaMemset(e->flat, 0, BGX_NPARAMS_PADDED * sizeof(float)));
+    CU(cudaMalloc(&e->wt, kTableBytes));
+    CU(cudaMalloc(&e->fixed, kFixedBytes));
+    CU(cudaMalloc(&e->aux, 4 * sizeof(float)));
+    CU(cudaMemset(e->aux, 0, 4 * sizeof(float)));
+    CU(cudaMalloc(&e->counter, kCounterBytes));
+    CU(cudaMalloc(&e->stats, 16 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&e->dstats, 2 * sizeof(double)));
+    CU(cudaMalloc(&e->steal, (size_t)e->sm_count * 32 * kStealMaxResults * sizeof(StealResult)));
+    CU(cudaEventCreate(&e->ev0));
+    CU(cudaEventCreate(&e->ev1));
+    CU(cudaEventCreateWithFlags(&e->ev_sync, cudaEventDisableTiming));
+    CU(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, kEvalSmem));
+    CU(cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmem));
+    e->lane_grid = e->sm_count / 2;
+    static_assert(ply_smem<16, 110>() <= 232448 && ply_smem<20, 87>() <= 232448 && ply_smem<24, 73>() <= 232448 && ply_smem<32, 54>() <= 232448,
+                  "fused ply kernels: shared memory per CTA");
+#define BGX_SMEM_ATTR(W, S)                                                                                                    \
+    CU(cudaFuncSetAttribute(k_select<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));            \
+    CU(cudaFuncSetAttribute(k_select<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));             \
+    CU(cudaFuncSetAttribute(k_selfplay<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));          \
+    CU(cudaFuncSetAttribute(k_selfplay<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));
+    BGX_SMEM_ATTR(16, 110)
+    BGX_SMEM_ATTR(20, 87)
+    BGX_SMEM_ATTR(24, 73)
+    BGX_SMEM_ATTR(32, 54)
+#undef BGX_SMEM_ATTR
+    CU(cudaFuncSetAttribute(k_td_replay<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
+    CU(cudaFuncSetAttribute(k_td_replay<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
     return BGX_OK;
 }
 
@@ -153,55 +198,35 @@ int bgx_create(int device, bgx_engine **out)
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { set_error("bgx_create: device %d is sm_%d%d; libbgx is built for sm_100a only", device, prop.major, prop.minor); return BGX_E_NO_DEVICE; }
     bgx_engine *e = new bgx_engine();
-    e->device = device;
-    e->sm_count = prop.multiProcessorCount;
-    e->global_mem = prop.totalGlobalMem;
-    cudaDeviceGetAttribute(&e->clock_khz, cudaDevAttrClockRate, device);
-    CU(cudaMalloc(&e->flat, BGX_NPARAMS_PADDED * sizeof(float)));
-    CU(cudaMemset(e->flat, 0, BGX_NPARAMS_PADDED * sizeof(float)));
-    CU(cudaMalloc(&e->wt, kTableBytes));
-    CU(cudaMalloc(&e->fixed, kFixedBytes));
-    CU(cudaMalloc(&e->aux, 4 * sizeof(float)));
-    CU(cudaMemset(e->aux, 0, 4 * sizeof(float)));
-    CU(cudaMalloc(&e->counter, kCounterBytes));
-    CU(cudaMalloc(&e->stats, 8 * sizeof(unsigned long long)));
-    CU(cudaMalloc(&e->dstats, 2 * sizeof(double)));
-    CU(cudaMalloc(&e->steal, (size_t)e->sm_count * 32 * kStealMaxResults * sizeof(StealResult)));
-    CU(cudaEventCreate(&e->ev0));
-    CU(cudaEventCreate(&e->ev1));
-    CU(cudaEventCreateWithFlags(&e->ev_sync, cudaEventDisableTiming));
-    CU(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, kEvalSmem));
-    CU(cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmem));
-    {
-        // tuning knobs: BGX_PLY_WARPS sets both kernels, BGX_SELFPLAY_WARPS / BGX_SELECT_WARPS one of them (16, 20, 24 or 32)
-        const char *both = getenv("BGX_PLY_WARPS"), *sp = getenv("BGX_SELFPLAY_WARPS"), *se = getenv("BGX_SELECT_WARPS");
-        if (both) e->selfplay_warps = e->select_warps = atoi(both);
-        if (sp) e->selfplay_warps = atoi(sp);
-        if (se) e->select_warps = atoi(se);
-        if (const char *v = getenv("BGX_SELECT_URGENT_MIN")) e->select_urgent_min = atoi(v);
-        if (const char *v = getenv("BGX_SELECT_ORDER_MAX")) e->select_order_max = atoll(v);
-        if (const char *v = getenv("BGX_SELECT_LANE_GRID")) e->lane_grid = atoi(v);
-        if (e->lane_grid < 0) e->lane_grid = e->sm_count / 2;
-        if (const char *v = getenv("BGX_SELECT_GIANT_MIN")) e->select_giant_min = atoi(v);
-        if (const char *v = getenv("BGX_SELECT_URGENT_FROM_PCT")) e->select_urgent_from_pct = atoi(v);
-        for (int w : {e->selfplay_warps, e->select_warps})
-            if (w != 16 && w != 20 && w != 24 && w != 32) { set_error("BGX_*_WARPS must be 16, 20, 24 or 32"); delete e; return BGX_E_INVALID; }
+    const int rc = create_into(e, device, prop);
+    if (rc != BGX_OK) {                              // the message of the failing call survives the clean-up
+        bgx_destroy(e);
+        return rc;
     }
-static_assert(ply_smem<16, 110>() <= 232448 && ply_smem<20, 87>() <= 232448 && ply_smem<24, 73>() <= 232448 && ply_smem<32, 54>() <= 232448,
-                  "fused ply kernels: shared memory per CTA");
-#define BGX_SMEM_ATTR(W, S)                                                                                                    \
-    CU(cudaFuncSetAttribute(k_select<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));            \
-    CU(cudaFuncSetAttribute(k_select<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));             \
-    CU(cudaFuncSetAttribute(k_selfplay<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));          \
-    CU(cudaFuncSetAttribute(k_selfplay<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));
-    BGX_SMEM_ATTR(16, 110)
-    BGX_SMEM_ATTR(20, 87)
-    BGX_SMEM_ATTR(24, 73)
-    BGX_SMEM_ATTR(32, 54)
-#undef BGX_SMEM_ATTR
-    CU(cudaFuncSetAttribute(k_td_replay<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
-    CU(cudaFuncSetAttribute(k_td_replay<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
     *out = e;
+    return BGX_OK;
+}
+
+// Tuning knobs of the fused ply kernels, for benchmarks and probes (the defaults are the measured best):
+//   "selfplay_warps" / "select_warps"  warps per CTA of k_selfplay / k_select: 16, 20, 24 or 32
+//   "select_lane_grid"                 CTAs of a launch on an asynchronous lane (0: one per SM; default: half the SMs)
+//   "select_order_max"                 largest batch that gets a sorted queue
+//   "select_urgent_min" / "select_giant_min" / "select_urgent_from_pct"   when a CTA helps a published double
+int bgx_set_option(bgx_engine *e, const char *key, int64_t value)
+{
+    if (!e || !key) { set_error("bgx_set_option: null"); return BGX_E_INVALID; }
+    const std::string k(key);
+    if (k == "selfplay_warps" || k == "select_warps") {
+        if (value != 16 && value != 20 && value != 24 && value != 32) { set_error("bgx_set_option: %s must be 16, 20, 24 or 32", key); return BGX_E_INVALID; }
+        (k == "selfplay_warps" ? e->selfplay_warps : e->select_warps) = (int)value;
+    } else if (k == "select_lane_grid") {
+        if (value < 0 || value > e->sm_count) { set_error("bgx_set_option: select_lane_grid is 0 .. %d", e->sm_count); return BGX_E_INVALID; }
+        e->lane_grid = (int)value;
+    } else if (k == "select_order_max") e->select_order_max = (long long)value;
+    else if (k == "select_urgent_min") e->select_urgent_min = (int)value;
+    else if (k == "select_giant_min") e->select_giant_min = (int)value;
+    else if (k == "select_urgent_from_pct") e->select_urgent_from_pct = (int)value;
+    else { set_error("bgx_set_option: unknown option '%s'", key); return BGX_E_INVALID; }
     return BGX_OK;
 }
 
@@ -214,7 +239,9 @@ int bgx_destroy(bgx_engine *e)
     cudaFree(e->flat); cudaFree(e->wt); cudaFree(e->fixed); cudaFree(e->aux); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats); cudaFree(e->steal);
     cudaFree(e->uniq_tables); cudaFree(e->uniq_gens); cudaFree(e->slots); cudaFree(e->traj_pre); cudaFree(e->traj_chosen);
     cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial); cudaFree(e->td_delta); cudaFree(e->td_prof); cudaFree(e->td_home); cudaFree(e->td_sched);
-    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_sync);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_sync) cudaEventDestroy(e->ev_sync);
     for (bgx_lane &l : e->lanes) {
         if (l.stream) cudaStreamDestroy(l.stream);
         if (l.done) cudaEventDestroy(l.done);
@@ -239,6 +266,14 @@ int bgx_synchronize(bgx_engine *e)
     return BGX_OK;
 }
 
+// weights may not change under a batch in flight: a lane's k_select reads the tables on its own stream
+static int lanes_idle(bgx_engine *e, const char *who)
+{
+    for (int i = 0; i < kLanes; i++)
+        if (e->lanes[i].busy) { set_error("%s: lane %d has a batch in flight (bgx_lane_wait first)", who, i); return BGX_E_STATE; }
+    return BGX_OK;
+}
+
 static int rebuild_table(bgx_engine *e)
 {
     k_build_table<<<(kTableFloats + 255) / 256, 256, 0, e->stream>>>(e->flat, e->wt);
@@ -253,6 +288,7 @@ int bgx_set_weights(bgx_engine *e, const float *W1, const float *b1, const float
 {
     USE(e);
     NEED(W1 && b1 && w2 && b2, "null weight pointer");
+    if (int rc = lanes_idle(e, "bgx_set_weights")) return rc;
     std::vector<float> flat(BGX_NPARAMS_PADDED, 0.f);
     std::memcpy(flat.data(), W1, kTableFloats * sizeof(float));
     std::memcpy(flat.data() + kTableFloats, b1, kHidden * sizeof(float));
@@ -748,10 +784,16 @@ int bgx_advance(bgx_engine *e, const int8_t *chosen, int8_t *next, int64_t n, ui
 
 // ------------------------------------------------------------------------ self-play
 
+static int ensure_td(bgx_engine *e);
+
 int bgx_selfplay_init(bgx_engine *e, int64_t n_slots, int64_t first_id, int64_t id_stride, uint64_t seed,
                       int first_mover, int32_t traj_cap)
 {
     USE(e);
+    if (traj_cap > 0) {                              // a population that records trajectories will be replayed: allocate the replay's
+        const int rc = ensure_td(e);                 // scratch now, not inside the first (timed) bgx_td_replay
+        if (rc) return rc;
+    }
     NEED(n_slots > 0 && id_stride > 0 && first_id >= 0 && traj_cap >= 0, "bad argument");
     NEED(first_mover == BGX_FIRST_ROLLOFF || first_mover == BGX_FIRST_PARITY, "unknown first-mover rule");
     CU(cudaStreamSynchronize(e->stream));
@@ -806,7 +848,7 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
     p.n_plies = n_plies; p.round_mode = round_mode; p.epsilon = epsilon;
     p.counter = e->counter; p.stats = e->stats;
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
-    CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
+    CU(cudaMemsetAsync(e->stats, 0, 16 * sizeof(unsigned long long), e->stream));
     tick(e);
 #define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->fixed, e->flat, e->steal)
     const bool ex = epsilon > 0.f;
@@ -945,7 +987,7 @@ static int launch_td(bgx_engine *e, const int8_t *traj, const int8_t *slots, con
     p.home = e->td_home;
     if (e->td_profile) CU(cudaMemsetAsync(e->td_prof, 0, 128 * sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
-    CU(cudaMemsetAsync(e->stats, 0, 8 * sizeof(unsigned long long), e->stream));
+    CU(cudaMemsetAsync(e->stats, 0, 16 * sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->dstats, 0, 2 * sizeof(double), e->stream));
     tick(e);
     if (e->td_profile) k_td_replay<true><<<grid, kTdThreads, kTdSmem, e->stream>>>(p);
@@ -959,7 +1001,7 @@ static int launch_td(bgx_engine *e, const int8_t *traj, const int8_t *slots, con
     }
     tock(e);
     if (out) {
-        unsigned long long h[8];
+        unsigned long long h[16];
         double d[2];
         CU(cudaMemcpyAsync(h, e->stats, sizeof h, cudaMemcpyDeviceToHost, e->stream));
         CU(cudaMemcpyAsync(d, e->dstats, sizeof d, cudaMemcpyDeviceToHost, e->stream));
@@ -969,7 +1011,8 @@ static int launch_td(bgx_engine *e, const int8_t *traj, const int8_t *slots, con
         out->games_finished = (int64_t)h[3];
         out->truncated = (int64_t)h[5];
         out->td_sq_error = d[0];
-        out->tree_edges = (int64_t)h[7];           // row-steps replayed lazily (k_td_replay)
+        out->td_lazy_row_steps = (int64_t)h[7];
+        out->td_live_rows = (int64_t)h[8];
     }
     return BGX_OK;
 }
@@ -999,6 +1042,7 @@ int bgx_apply_delta(bgx_engine *e, const float *delta_dev, float scale)
 {
     USE(e);
     NEED(delta_dev, "null delta buffer");
+    if (int rc = lanes_idle(e, "bgx_apply_delta")) return rc;
     k_axpy<<<(BGX_NPARAMS + 255) / 256, 256, 0, e->stream>>>(e->flat, delta_dev, scale, BGX_NPARAMS);
     e->launches++;
     CU(cudaGetLastError());
@@ -1051,6 +1095,88 @@ int bgx_td_replay_host(bgx_engine *e, const int8_t *records, int32_t T, int play
     std::memcpy(new_w2, flat.data() + kTableFloats + kHidden, kHidden * sizeof(float));
     new_b2[0] = flat[kTableFloats + 2 * kHidden];
     return BGX_OK;
+}
+
+// ------------------------------------------------------------------------ the cross-GPU exchange
+// NCCL is bound at run time (dlopen), so that libbgx has no link-time dependency on it and single-GPU users need none.
+namespace {
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load(const char *path)
+{
+    if (g_nccl.AllReduce) return BGX_OK;
+    void *lib = nullptr;
+    const char *tried[] = {path, "libnccl.so.2", "libnccl.so"};
+    for (const char *name : tried)
+        if (name && *name && (lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!lib) { set_error("NCCL: cannot load libnccl (%s)", dlerror()); return BGX_E_STATE; }
+    g_nccl.GetUniqueId = (int (*)(NcclUniqueId *))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, NcclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(lib, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
+        g_nccl = NcclApi();
+        set_error("NCCL: libnccl lacks an expected symbol");
+        return BGX_E_STATE;
+    }
+    g_nccl.lib = lib;
+    return BGX_OK;
+}
+int nccl_check(int rc, const char *what)
+{
+    if (rc == 0) return BGX_OK;
+    set_error("NCCL: %s failed: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return BGX_E_CUDA;
+}
+} // namespace
+
+int bgx_nccl_load(const char *libnccl_path) { return nccl_load(libnccl_path); }
+
+int bgx_nccl_unique_id(void *id128)
+{
+    NEED(id128, "null id buffer");
+    int rc = nccl_load(nullptr);
+    if (rc) return rc;
+    return nccl_check(g_nccl.GetUniqueId((NcclUniqueId *)id128), "ncclGetUniqueId");
+}
+
+int bgx_nccl_comm_init(bgx_engine *e, int n_ranks, int rank, const void *id128, void **comm)
+{
+    USE(e);
+    NEED(id128 && comm && n_ranks > 0 && rank >= 0 && rank < n_ranks, "bad argument");
+    int rc = nccl_load(nullptr);
+    if (rc) return rc;
+    NcclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    return nccl_check(g_nccl.CommInitRank(comm, n_ranks, id, rank), "ncclCommInitRank");
+}
+
+int bgx_nccl_comm_destroy(void *comm)
+{
+    if (!comm) return BGX_OK;
+    int rc = nccl_load(nullptr);
+    if (rc) return rc;
+    return nccl_check(g_nccl.CommDestroy(comm), "ncclCommDestroy");
+}
+
+// the only cross-GPU traffic of the path: sum of the per-rank weight deltas, fp32[25,604], in place, on the engine's stream
+int bgx_allreduce_delta(bgx_engine *e, void *nccl_comm, float *delta_dev)
+{
+    USE(e);
+    NEED(nccl_comm && delta_dev, "null communicator or buffer");
+    int rc = nccl_load(nullptr);
+    if (rc) return rc;
+    return nccl_check(g_nccl.AllReduce(delta_dev, delta_dev, BGX_NPARAMS_PADDED, /*ncclFloat32*/ 7, /*ncclSum*/ 0, nccl_comm, e->stream), "ncclAllReduce");
 }
 
 // ------------------------------------------------------------------------ introspection

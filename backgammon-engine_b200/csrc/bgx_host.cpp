@@ -181,7 +181,7 @@ using namespace bgx;
 extern "C" {
 
 const char *bgx_last_error(void) { return g_err; }
-int bgx_abi_version(void) { return 1; }
+int bgx_abi_version(void) { return 2; }
 
 int bgx_legal_moves(const int32_t *position, int player, int die, int8_t *out_pairs, int cap, int *n)
 {
@@ -242,23 +242,22 @@ int bgx_turn_sequences(const int32_t *position, int player, int d1, int d2, int6
     return BGX_OK;
 }
 
-// host threads of bgx_advance_host: BGX_HOST_THREADS, else this process's share of the cores when several ranks
-// run on one box (torchrun exports LOCAL_WORLD_SIZE), at most 4 (one thread does 65,536 games in ~0.3 ms)
+// host threads of bgx_advance_host: bgx_set_host_threads, else 1..4 by the cores at hand (one thread does 65,536 games in ~0.3 ms).
+// Several ranks on one box should say how many they are (bgx_set_host_threads(cores / ranks)): the library reads no environment.
+static int g_host_threads = 0;
 static int advance_threads()
 {
-    static int cached = 0;
-    if (cached) return cached;
-    int t;
-    if (const char *e = std::getenv("BGX_HOST_THREADS")) {
-        t = std::atoi(e);
-    } else {
-        const char *l = std::getenv("LOCAL_WORLD_SIZE");
-        const int ranks = l ? std::atoi(l) : 1;
-        t = (int)std::thread::hardware_concurrency() / (ranks > 0 ? ranks : 1);
-        if (t > 4) t = 4;
-    }
-    cached = t < 1 ? 1 : (t > 64 ? 64 : t);
-    return cached;
+    if (g_host_threads > 0) return g_host_threads;
+    int t = (int)std::thread::hardware_concurrency();
+    if (t > 4) t = 4;
+    return t < 1 ? 1 : t;
+}
+
+int bgx_set_host_threads(int n)
+{
+    if (n < 0 || n > 64) { bgx::set_error("bgx_set_host_threads: 0 (automatic) .. 64"); return BGX_E_INVALID; }
+    g_host_threads = n;
+    return BGX_OK;
 }
 
 } // extern "C"

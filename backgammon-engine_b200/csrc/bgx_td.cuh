@@ -55,7 +55,7 @@ struct TdParams {
     float *home;               // [gridDim.x][2][198][128] per-CTA home copies of W1 (transposed) and of its traces; L2-resident
     float *final_weights;      // optional [25604] state_dict order (single-game calls)
     double *sq_errors;         // optional [T-1] (single-game calls)
-    unsigned long long *stats; // [3] games replayed, [5] truncated games skipped, [6] TD steps, [7] row-steps replayed lazily
+    unsigned long long *stats; // [3] games replayed, [5] truncated games skipped, [6] TD steps, [7] row-steps replayed lazily, [8] live rows summed over the steps
     double *dstats;            // [0] sum of squared TD errors
     unsigned long long *prof;  // k_td_replay<true>: [8 warps][16] cycles per phase, CTA 0 (bgx_td_profile)
 };
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams
     int last = -1;                                           // lane r: last step applied to the HOME copy of row r, -1 = untouched in this game
     const int8_t *traj = nullptr;                            // loader: the game's records
     long long cursor = blockIdx.x;                           // loader: the next game of this CTA
-    unsigned long long steps = 0, games = 0, lazy = 0;
+    unsigned long long steps = 0, games = 0, lazy = 0, rows_live = 0;
     double sq_sum = 0.0;
 
     // loader: take the next finished game off the queue, publish it, stage its first three records
@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams
                 x2 = t + 2 < T ? me.value((int)ring[((t + 2) & (kTdRing - 1)) * 32 + me.byte], offtab) : 0.f;
             }
             const uint32_t live = __ballot_sync(kFull, x0 != 0.f || x1 != 0.f || x2 != 0.f);
+            rows_live += (unsigned)__popc(live);
             // rows that enter the window after a sleep replay what they missed (through step t-1) in their home copies
             uint32_t late = __ballot_sync(kFull, (live >> lane & 1) && last >= 0 && last < t - 1);
             while (late) {
@@ -520,6 +521,7 @@ __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams
         games++;
         TD_MARK(7);
     }
+    if (lane == 0) atomicAdd(p.stats + 8, rows_live);                         // row updates of the step passes, all eight classes
     if (lane == 0) atomicAdd(p.stats + 7, lazy);                              // row-steps replayed lazily, all eight classes
     if (tid == 0) {
         atomicAdd(p.stats + 3, games);

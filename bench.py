@@ -13,8 +13,9 @@ game of the population plays PLIES_PER_STEP plies (one k_selfplay launch).
              numbers and game ids go pinned-host -> device, one iteration of play_game's loop runs for all of
              them (make_move, is_game_over, setTurn, roll_dice: bgx_play_ply_host_async), the next records and
              the winners come back, and the host restarts finished games
-  roofline   the self-play kernel against the measured HBM peak, in the units SURVEY.md §8(d)
-             prescribes: 1,696 algorithmic bytes per enumerated afterstate
+  roofline   the self-play kernel against the bound that limits it (warp-instruction issue; the kernel's DRAM traffic
+             and the HBM peak beside it), and SURVEY.md §8(d)'s 1,696 B per enumerated afterstate of the
+             materialised dataflow as `materialised_equivalent`
   cpu_baseline  the reference engine + model.py loop on the host cores (oracle/ref_play.py)
 """
 import argparse
@@ -163,6 +164,45 @@ def port_baseline(w, seconds):
 
 # ----------------------------------------------------------------------------- our arm
 
+def kernel_sass_sha(kernel):
+    """sha256 of the SASS of the first function of libbgx.so whose name contains `kernel` (cuobjdump), or None."""
+    import hashlib
+    import re
+    import shutil
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe, "-sass", os.path.join(PKG, "lib", "libbgx.so")], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    keep, on = [], False
+    for ln in out.splitlines():
+        if "Function :" in ln:
+            if on:
+                break
+            on = kernel in ln
+        if on:
+            keep.append(re.sub(r"/\*[0-9a-f]{4,}\*/", "", ln).strip())     # drop the addresses, keep mnemonics and encodings
+    return hashlib.sha256("\n".join(keep).encode()).hexdigest() if keep else None
+
+
+def capture_facts(name):
+    """Numbers of the committed ncu capture of a kernel (profiles/traffic.json) and whether they describe the kernel that is
+    loaded: the capture records the sha256 of the kernel's SASS, which must equal that of the library in this tree."""
+    try:
+        facts = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[name]
+    except Exception as exc:
+        return {}, {"verified": False, "why": f"no capture ({exc})"}
+    want, got = facts.get("sass_sha256"), kernel_sass_sha(facts.get("sass_function", name))
+    if not want or not got:
+        return facts, {"verified": False, "why": "no SASS hash in the capture" if not want else "cuobjdump not available", "file": facts.get("capture")}
+    if want != got:
+        return facts, {"verified": False, "why": f"SASS hash of the loaded kernel {got[:12]} != capture {want[:12]} (kernel changed since the capture)",
+                       "file": facts.get("capture")}
+    return facts, {"verified": True, "why": "SASS hash matches", "file": facts.get("capture"), "sass_sha256": got[:16]}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -201,8 +241,8 @@ def side_legs(eng, dev, peaks, n_positions):
     enumeration + evaluation + arg-best, the unfused encoder (the one truly HBM-bound kernel) and the evaluator."""
     import numpy as np
     import torch
-    from bgx.synth import make_queries
-    q, _ = make_queries(n_positions, seed=20260101)
+    from bgx.synth import make_sweep_queries
+    q, _ = make_sweep_queries(eng, n_positions)      # configs[1]: half constructive, half sampled from random playouts
     qd = torch.from_numpy(q).to(dev)
     n = qd.shape[0]
     n_seq = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -217,14 +257,29 @@ def side_legs(eng, dev, peaks, n_positions):
             ms.append(eng.last_kernel_ms())
         return min(ms)
 
+    def best_event_ms(fn, reps=3):
+        fn()
+        ms = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return min(ms)
+
     t_enum = best_ms(lambda: eng.enumerate_summary(qd, n_seq, n_uni, dig)) * 1e-3
     seqs, uniq = int(n_seq.sum().item()), int(n_uni.clamp(min=0).sum().item())
     chosen = torch.zeros((n, 32), dtype=torch.int8, device=dev)
     val = torch.zeros(n, dtype=torch.float32, device=dev)
     t_sel = best_ms(lambda: eng.select_moves(qd, chosen=chosen, value=val)) * 1e-3
-    # the materialised list (batched evaluateTurnSequences): every sequence's moves, length and 32-byte state row
+    # the materialised list (batched evaluateTurnSequences): every sequence's moves, length and 32-byte state row.
+    # Allocation pass (count-only walk + device scan) and write pass, no host round trip between them.
     offs = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-    offs[1:] = torch.cumsum(n_seq.to(torch.int64), 0)
+    cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+    t_cnt = best_event_ms(lambda: eng.enumerate_count(qd, cnt, offs)) * 1e-3
+    assert int(offs[-1].item()) == seqs and torch.equal(cnt, n_seq)
     mv = torch.empty((seqs, 8), dtype=torch.int8, device=dev)
     ln = torch.empty(seqs, dtype=torch.int8, device=dev)
     st = torch.empty((seqs, 32), dtype=torch.int8, device=dev)
@@ -240,14 +295,36 @@ def side_legs(eng, dev, peaks, n_positions):
     return {"positions": n, "sequences": seqs, "unique_afterstates": uniq,
             "enumerate": {"kernel": "k_enumerate_summary", "ms": t_enum * 1e3, "positions_per_sec": n / t_enum,
                           "sequences_per_sec": seqs / t_enum, "unique_afterstates_per_sec": uniq / t_enum},
-            "enumerate_materialised": {"kernel": "k_enumerate_write", "ms": t_wr * 1e3, "sequences_per_sec": seqs / t_wr,
-                                       "bytes_written_per_sequence": 41, "write_gbs": seqs * 41 / t_wr / 1e9},
+            "enumerate_materialised": {"kernels": "k_enumerate_count + k_scan_* + k_enumerate_write", "count_and_scan_ms": t_cnt * 1e3,
+                                       "write_ms": t_wr * 1e3, "ms": (t_cnt + t_wr) * 1e3, "sequences_per_sec": seqs / (t_cnt + t_wr),
+                                       "bytes_written_per_sequence": 41, "write_gbs": seqs * 41 / t_wr / 1e9,
+                                       "round1_path_ms": (t_enum + t_wr) * 1e3,
+                                       "note": "batched evaluateTurnSequences on device buffers; round 1 ran k_enumerate_summary (exact U + digest) "
+                                               "as the allocation pass and scanned on the host (round1_path_ms = summary + write, without its D2H/H2D)"},
             "select": {"kernel": "k_select", "ms": t_sel * 1e3, "positions_per_sec": n / t_sel,
                        "afterstates_enumerated_and_evaluated_per_sec": seqs / t_sel},
             "encode": {"kernel": "k_encode", "rows": rows, "ms": t_enc * 1e3, "rows_per_sec": rows / t_enc,
                        "roofline": {"bound": "hbm", "achieved": enc_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": enc_gbs / peaks["hbm_gbs"], "note": "824 B per row: 32 B record read + 792 B fp32[198] written"}},
             "evaluate": {"kernel": "k_evaluate", "ms": t_ev * 1e3, "rows_per_sec": n / t_ev}}
+
+
+def td_parity(eng):
+    """Per-game weight change of k_td_replay against the reference's own apply_td_updates on the 1,024 GPU-exported
+    trajectories per weight set of tests/golden/ (td_traj.npz, td_parity.npz; generator: tests/golden/make_golden.py td_parity):
+    p50 / p99 / max over the games of max|dw - dw_ref| / max|dw_ref| per tensor.  The engine's weights are replaced."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import load_golden
+    from td_fixture import TdFixture, engine_errors, quantiles
+    out = {"metric": "max|dw - dw_ref| / max|dw_ref| per game and tensor, quantiles p50 / p99 / max over 1,024 games",
+           "reference": "unmodified apply_td_updates (train.py:124-172), torch CPU fp32, committed as tests/golden/td_parity.npz",
+           "fp32_restatement_vs_reference_W1": {"rand": [3.31e-6, 1.07e-5, 1.61e-5], "trained": [1.14e-5, 4.72e-5, 8.39e-5]}}
+    for tag in ("rand", "trained"):
+        fx = TdFixture(load_golden, tag)
+        err, worst, _ = engine_errors(eng, fx)
+        out[tag] = {k: list(v) for k, v in quantiles(err).items()}
+        out[tag]["worst_step_td_error_diff"] = worst
+    return out
 
 
 def pin_to_gpu_cpus(index):
@@ -340,7 +417,6 @@ def run_ours(args):
     pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
     bufs = [pin((G, 32), torch.int8), pin((G, 32), torch.int8)]
     win = pin((G,), torch.int8)
-    nxt_ply = pin((G,), torch.int32)
     h_gid_pin = pin((G,), torch.int64)
     rec, h_ply, h_gid = eng.selfplay_read()          # continue the (desynchronised) games of the population from the host
     h_gid_pin[:] = h_gid
@@ -353,25 +429,19 @@ def run_ours(args):
     bufs[0][:, 28] ^= 1
     bufs[0][:, 31] = 0
 
-    def submit(h):
-        lo, hi = parts[h]
-        nxt_ply[lo:hi] = h_ply[lo:hi] + 1
-        eng.play_ply_host_async(h, bufs[cur[h]][lo:hi], nxt_ply[lo:hi], h_gid[lo:hi], bufs[1 - cur[h]][lo:hi], win[lo:hi], dice_seed=SEED)
+    h_ply_pin = pin((G,), torch.int32)
+    h_ply_pin[:] = h_ply
+    h_ply = h_ply_pin
 
-    def advance(h):
+    def submit(h):                                      # one iteration of play_game's loop for a third of the population
+        lo, hi = parts[h]
+        eng.play_ply_restart_host_async(h, bufs[cur[h]][lo:hi], h_ply[lo:hi], h_gid[lo:hi], stride, bufs[1 - cur[h]][lo:hi], win[lo:hi],
+                                        first_mover=FIRST_PARITY, dice_seed=SEED)
+
+    def advance(h):                                     # nothing per game on the host: finished games restart on the device
         lo, hi = parts[h]
         eng.wait(h)
         cur[h] ^= 1
-        h_ply[lo:hi] += 1
-        done = np.flatnonzero(win[lo:hi] >= 0)
-        if done.size:                                   # restart in place with the next game id (first mover: id % 2)
-            idx = done + lo
-            h_gid[idx] += stride
-            h_ply[idx] = 0
-            fresh = np.zeros((idx.size, 32), np.int8)
-            fresh[:, :24] = START_BOARD
-            fresh[:, 28] = (h_gid[idx] & 1) ^ 1         # bgx_advance_host flips it and rolls ply 0
-            bufs[cur[h]][idx] = bgx_host.advance(fresh, fresh, SEED, h_ply[idx], h_gid[idx])
         return hi - lo
 
     for h in range(LANES):
@@ -405,11 +475,16 @@ def run_ours(args):
         args.td_games = 262144 if world == 1 else (1 << 20) // world
     if args.td_games > 0:
         from bgx.lib import FIRST_ROLLOFF
-        from bgx.parallel import allreduce_delta, shard
+        from bgx.parallel import NcclComm, shard
         first, n_slots, stride = shard(args.td_games * world, rank, world)
         eng.selfplay_init(n_slots, first_id=first, id_stride=stride, seed=SEED + 1, first_mover=FIRST_ROLLOFF, traj_cap=2048)
         delta = torch.zeros(25604, dtype=torch.float32, device=dev)
-        allreduce_delta(delta, dist if world > 1 else None)      # untimed: NCCL sets this collective up on first use
+        comm = NcclComm(eng, dist) if world > 1 else None        # the C-ABI's own communicator (bgx_nccl_comm_init)
+
+        def exchange():                                          # bgx_allreduce_delta: ncclAllReduce(sum, fp32[25604]) on the engine's stream
+            if comm:
+                comm.allreduce_delta(delta)
+        exchange()                                               # untimed: NCCL sets the collective up on first use
         barrier()
         td_sampler = ClockSampler(local)                         # every rank watches its own GPU over the round
         td_sampler.start()
@@ -419,24 +494,77 @@ def run_ours(args):
         e1.record(stream)
         tdst = eng.td_replay(0.1, 0.9, delta)
         e2.record(stream)
-        allreduce_delta(delta, dist if world > 1 else None)
+        exchange()
+        reduced = delta.double()
         eng.apply_delta(delta, 1.0 / (args.td_games * world))
         e3.record(stream)
         barrier()
         td_sampler.stop_flag.set()
         td_sampler.join(timeout=3)
+        replay_kernel_ms = eng.last_kernel_ms()
+        # the collective alone: every rank enters together, 100 back-to-back all-reduces of the 102,416-byte delta
+        ar_us = None
+        if comm:
+            scratch_delta = delta.clone()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(100):
+                comm.allreduce_delta(delta)
+            a1.record(stream)
+            torch.cuda.synchronize()
+            ar = torch.tensor([a0.elapsed_time(a1) * 10.0], dtype=torch.float64, device=dev)     # ms / 100 -> us
+            dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+            ar_us = float(ar.item())
+            delta.copy_(scratch_delta)
+        # what every rank must agree on: the reduced delta and the weights after the round (SCALE: the same at N = 2, 4, 8 up to
+        # the order of the fp32 sums)
+        w_after = np.concatenate([np.asarray(a, np.float64).reshape(-1) for a in eng.get_weights()])
+        chk = torch.tensor([float(reduced.sum()), float(reduced.abs().sum()), float(w_after.sum()), float(np.abs(w_after).sum())],
+                           dtype=torch.float64, device=dev)
+        spread = torch.stack([chk, -chk])
+        if world > 1:
+            dist.all_reduce(spread, op=dist.ReduceOp.MAX)
+        spread = (spread[0] + spread[1]).tolist()                # max - min over the ranks: 0 when every rank holds the same bits
         tcl = td_sampler.summary()
         watts = [float(r[2]) for r in td_sampler.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         lo = torch.tensor([-(tcl["sm_mhz"] or 0.0), max(watts) if watts else 0.0, float("sw_power_cap" in tcl["reasons"]),
                            float(bool(set(tcl["reasons"]) - {"sw_power_cap"}))], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(lo, op=dist.ReduceOp.MAX)
-        ms = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), e0.elapsed_time(e3)], dtype=torch.float64, device=dev)
-        cnt = torch.tensor([play["plies"], tdst["td_steps"], play["games_finished"], play["truncated"]], dtype=torch.float64, device=dev)
+        ms = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), e0.elapsed_time(e3), replay_kernel_ms], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([play["plies"], tdst["td_steps"], play["games_finished"], play["truncated"], tdst["td_live_rows"], tdst["td_lazy_row_steps"]],
+                           dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         ms, cnt = ms.tolist(), cnt.tolist()
+        steps_td = max(cnt[1], 1.0)
+        # algorithmic work of a TD step as the sparse replay defines it: per live row and hidden unit one trace FMA (+ the
+        # gradient product), one weight FMA and the two forward FMAs of the next step = 9 FLOP; per lazily replayed (row, step)
+        # a multiply and an FMA = 3 FLOP; ~1,300 FLOP for the hidden / output layer of both states.  Dense, as the reference
+        # executes it: ~255 kFLOP per step.
+        props_td = eng.device_props()
+        fp32_peak_td = props_td["sm_count"] * 128 * 2 * peak_json()[0].get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+        flop_sparse = (cnt[4] * 9 + cnt[5] * 3) * 128 + steps_td * 1300
+        k_s = ms[4] * 1e-3
+        tfacts, tstate = capture_facts("k_td_replay")
+        td_roof = {"bound": "fp32", "kernel": "k_td_replay", "kernel_ms": ms[4], "unit": "TFLOP/s", "peak": fp32_peak_td,
+                   "achieved": flop_sparse / k_s / 1e12, "frac": flop_sparse / k_s / 1e12 / fp32_peak_td,
+                   "flop_per_step": flop_sparse / steps_td, "live_rows_per_step": cnt[4] / steps_td, "lazy_row_steps_per_step": cnt[5] / steps_td,
+                   "dense_equivalent": {"flop_per_step": 255000, "achieved": steps_td * 255000 / k_s / 1e12,
+                                        "ratio": steps_td * 255000 / k_s / 1e12 / fp32_peak_td,
+                                        "note": "the reference's dense per-step work (two dense forwards, dense trace and weight update); "
+                                                "the kernel touches only live rows, so this is a speed-up over the dense arithmetic"},
+                   "capture": tstate,
+                   "note": "the step is a chain of dependent phases (first-layer partials -> barrier -> hidden layer -> barrier -> values -> "
+                           "row pass), two games per SM; neither FP32 nor memory bounds it (see `issue`), the FLOP figure says how far the "
+                           "arithmetic is from mattering"}
+        if tfacts.get("warp_inst_per_step") and tstate["verified"]:
+            ipk = props_td["sm_count"] * 4 * peak_json()[0].get("sm_max_mhz", 1965.0) * 1e6
+            td_roof["issue"] = {"unit": "G warp-inst/s", "peak": ipk / 1e9, "achieved": steps_td * tfacts["warp_inst_per_step"] / k_s / 1e9,
+                                "frac": steps_td * tfacts["warp_inst_per_step"] / k_s / ipk, "warp_inst_per_step": tfacts["warp_inst_per_step"],
+                                "traffic": tfacts.get("dram_bytes_per_launch")}
         td = {"workload": ("TD(lambda) self-play training, 262,144 concurrent games on 1 GPU (BASELINE.json configs[3])" if world == 1 and args.td_games == 262144
                            else f"TD(lambda) self-play training sharded over {world} GPU(s), {args.td_games * world:,} games in total (BASELINE.json configs[4])"
                            if world > 1 and args.td_games * world == 1 << 20 else f"TD(lambda) self-play training, {args.td_games:,} games per GPU"),
@@ -444,28 +572,71 @@ def run_ours(args):
               "truncated": int(cnt[3]), "play_ms": ms[0], "td_replay_ms": ms[1], "allreduce_apply_ms": ms[2], "round_ms": ms[3],
               "plies_per_sec_incl_update": cnt[0] / (ms[3] * 1e-3), "td_steps_per_sec": cnt[1] / (ms[1] * 1e-3),
               "replay_ms_this_rank": e1.elapsed_time(e2),
+              "allreduce_us": ar_us,
+              "allreduce": "bgx_allreduce_delta (C-ABI, ncclAllReduce sum of fp32[25604] = 102,416 B on a communicator from bgx_nccl_comm_init); "
+                           "allreduce_us = mean of 100 back-to-back calls entered together, max over ranks" if comm else None,
+              "checksums": {"delta_sum": float(chk[0]), "delta_abs_sum": float(chk[1]), "weights_sum": float(chk[2]), "weights_abs_sum": float(chk[3]),
+                            "max_minus_min_over_ranks": spread,
+                            "note": "of the all-reduced weight delta and of the weights after the round; identical bits on every rank "
+                                    "(max - min = 0), and equal across N = 2, 4, 8 (the same 2^20 games) up to the order of the fp32 sums"},
+              "roofline": td_roof,
               "clocks": {"sm_mhz_min_over_ranks": -float(lo[0]), "power_w_max_over_ranks": float(lo[1]),
                          "sw_power_cap_on_some_rank": bool(lo[2] > 0), "other_slowdown_on_some_rank": bool(lo[3] > 0),
                          "samples_rank0": tcl["samples"],
                          "note": "each rank samples its own GPU (nvidia-smi, 0.2 s) over the whole round; median SM clock per rank, min over ranks"},
               "note": "one round: every game played to its end from one snapshot (k_selfplay), exact online TD(lambda) replay "
-                      "per game (k_td_replay), NCCL all-reduce of fp32[25604], apply; allreduce_apply_ms includes waiting for the "
+                      "per game (k_td_replay, lr 0.1, lambda 0.9), all-reduce of fp32[25604], apply; allreduce_apply_ms includes waiting for the "
                       "slowest rank's replay (max over ranks)"}
+        if rank == 0 and not args.no_td_parity:
+            td["parity"] = td_parity(eng)
+        if comm:
+            comm.close()
 
     if rank == 0:
         peaks, peak_src = peak_json()
-        try:
-            facts = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_selfplay"]
-        except Exception:
-            facts = {}
+        facts, facts_state = capture_facts("k_selfplay")
         traffic = facts.get("dram_bytes_per_launch")
         inst_per_ply = facts.get("warp_inst_per_ply")
         k_ms = float(np.mean(kernel_ms))
         seq_per_launch = seqs / args.steps
         scored_per_launch = scored / args.steps
-        achieved = seq_per_launch * BYTES_PER_AFTERSTATE / (k_ms * 1e-3) / 1e9
         props = eng.device_props()
-        fp32_peak = props["sm_count"] * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
+        clock_hz = peaks.get("sm_max_mhz", 1965.0) * 1e6
+        issue_peak = props["sm_count"] * 4 * clock_hz
+        # What bounds the fused ply kernel: warp-instruction issue (integer / branch / shuffle work, 4 schedulers per SM).
+        # Instructions per ply come from the committed ncu capture of THIS kernel binary (its SASS hash is checked) and are
+        # rescaled by the tree edges per ply counted in this run, so a change of workload mix does not go unnoticed.
+        edges_now = edges / max(plies, 1)
+        roof = {"bound": "issue", "unit": "G warp-inst/s", "peak": issue_peak / 1e9, "achieved": None, "frac": None,
+                "kernel": "k_selfplay", "kernel_ms": k_ms, "traffic": traffic, "capture": facts_state,
+                "tree_edges_per_ply": edges_now, "scored_per_ply": scored / max(plies, 1), "peak_source": peak_src}
+        if inst_per_ply and facts_state["verified"]:
+            scale = edges_now / facts["tree_edges_per_ply"] if facts.get("tree_edges_per_ply") else 1.0
+            ach = (plies / args.steps) * inst_per_ply * scale / (k_ms * 1e-3)
+            roof.update({"achieved": ach / 1e9, "frac": ach / issue_peak, "warp_inst_per_ply": inst_per_ply * scale,
+                         "warp_inst_per_tree_edge": inst_per_ply / facts["tree_edges_per_ply"] if facts.get("tree_edges_per_ply") else None,
+                         "note": "warp instructions per ply (smsp__inst_executed.sum of the committed capture / plies of that launch, rescaled "
+                                 "by this run's tree edges per ply) x plies/s, against 4 schedulers x SMs x max clock: the share of issue "
+                                 "slots the kernel fills.  It is an occupancy of the bound, not proof of minimal work: the work itself is "
+                                 "warp_inst_per_tree_edge x tree edges per ply"})
+        else:
+            print("bench.py: profiles/traffic.json does not describe the k_selfplay in this libbgx.so "
+                  f"({facts_state['why']}): roofline.frac is withheld; re-capture with tools/capture_traffic.py", file=sys.stderr)
+        if traffic:
+            roof["hbm"] = {"achieved": traffic / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": traffic / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                           "note": "the kernel's own DRAM traffic per launch (ncu dram__bytes_read + write): the population is 2 MB and "
+                                   "nothing else is read or written; HBM is idle by design"}
+        achieved = seq_per_launch * BYTES_PER_AFTERSTATE / (k_ms * 1e-3) / 1e9
+        roof["materialised_equivalent"] = {
+            "bytes_per_afterstate": BYTES_PER_AFTERSTATE, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "ratio": achieved / peaks["hbm_gbs"],
+            "fused_dataflow_bytes_per_afterstate": 32, "fused_dataflow_ratio": seq_per_launch * 32 / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "note": "NOT a utilisation: the bytes SURVEY 8d's materialised dataflow (792 B of features written + 792 B read + "
+                    "112 B state row per enumerated afterstate) would move for the sequences this kernel enumerates, over the "
+                    "HBM peak; > 1 means no implementation that stages encodings through HBM can keep up.  32 B: one packed "
+                    "record per afterstate (fused encode + evaluate); this kernel writes none"}
+        fp32_peak = props["sm_count"] * 128 * 2 * clock_hz / 1e12
         fp32_ach = scored_per_launch * FLOP_PER_AFTERSTATE / (k_ms * 1e-3) / 1e12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -475,37 +646,20 @@ def run_ours(args):
                                                                      # enumerated and evaluated (duplicates and twins scored once, counted all)
                 "sequences_per_ply": seqs_all / plies_all, "scored_per_ply": scored_all / plies_all,
                 "tree_edges_per_ply_rank0": edges / max(plies, 1), "ply_warps_per_cta": eng.kernel_config(),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 44, "d2h_bytes_per_step": G * 33,
-                        "note": "one step = one ply for all 65,536 games through bgx_play_ply_host_async (= make_move + is_game_over + "
-                                "setTurn + roll_dice of train.py:103-121 for a batch): three thirds of the population on three lanes of half "
-                                "the SMs each, pinned host buffers, H2D (records, ply numbers, game ids) + k_select_order + k_select + "
-                                f"k_advance + D2H (next records, winners) per ply; the host counts plies and restarts finished games; {e2e_steps} timed ply-steps"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 44, "d2h_bytes_per_step": G * 45,
+                        "note": "one step = one ply for all 65,536 games through bgx_play_ply_restart_host_async (= make_move + is_game_over + "
+                                "setTurn + roll_dice of train.py:103-121 for a batch, finished games restarted in place as train.py:199-220 "
+                                "does game after game): three thirds of the population on three lanes of half the SMs each, pinned host "
+                                "buffers, H2D (records, ply numbers, game ids) + k_select + D2H (next records, winners, ply numbers, game "
+                                f"ids) per ply; the host loop is wait / swap / submit; {e2e_steps} timed ply-steps"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "kernel": "k_selfplay",
-                             "kernel_ms": k_ms, "peak_source": peak_src,
-                             "fused_dataflow": {"bytes_per_afterstate": 32, "achieved": seq_per_launch * 32 / (k_ms * 1e-3) / 1e9,
-                                                "frac": seq_per_launch * 32 / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                                "note": "SURVEY 8d's second figure: an implementation that fuses encode + evaluate but still "
-                                                        "writes one packed int8 record (32 B) per enumerated afterstate; this kernel writes none"},
-                             "note": "algorithmic bytes = sequences enumerated per launch x 1,696 B: what the materialised dataflow "
-                                     "of the reference and of SURVEY 8d moves per enumerated afterstate (792 B of features written, "
-                                     "792 B read back, 112 B state row).  The fused kernel never materialises them (`traffic` is its "
-                                     "real DRAM traffic per launch), so frac > 1 means it outruns ANY implementation that stages "
-                                     "the encodings through HBM; the bound that actually limits it is `roofline_issue`"},
-                "roofline_fp32": {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                                  "frac": fp32_ach / fp32_peak,
-                                  "note": "afterstates actually scored x 50,944 dense-equivalent FLOP; the kernel skips zero features"},
+                "roofline": roof,
+                "fp32_dense_equivalent": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "ratio": fp32_ach / fp32_peak,
+                                          "note": "afterstates actually scored x 50,944 FLOP of the dense 198-128-1 forward the reference runs; the "
+                                                  "kernel evaluates a scored afterstate with 2-4 integer row adds (delta evaluation), so this is a "
+                                                  "speed-up over the dense arithmetic, not a pipe utilisation"},
                 "wall_s_timed_region": wall}
-        if inst_per_ply:
-            issue_peak = props["sm_count"] * 4 * peaks.get("sm_max_mhz", 1965.0) * 1e6
-            issue_ach = (plies / args.steps) * inst_per_ply / (k_ms * 1e-3)
-            line["roofline_issue"] = {"bound": "warp-instruction issue", "achieved": issue_ach / 1e9, "peak": issue_peak / 1e9,
-                                      "unit": "G warp-inst/s", "frac": issue_ach / issue_peak,
-                                      "note": f"{inst_per_ply:.0f} warp instructions per ply (smsp__inst_executed.sum of the committed ncu "
-                                              "capture / plies of that launch) x live plies/s, against 4 schedulers x SMs x clock; "
-                                              "this integer/branch kernel is bound by issue slots and dependent-issue latency, not by HBM"}
         if legs:
             line["side_kernels"] = legs
         if td:
@@ -544,6 +698,7 @@ def main():
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--side-positions", type=int, default=1000000, help="positions of the enumeration/encode side legs (0 = skip)")
+    ap.add_argument("--no-td-parity", action="store_true", help="skip the TD parity block of the td_round object")
     ap.add_argument("--td-games", type=int, default=-1,
                     help="games per GPU in the TD(lambda) round leg (0 = skip; default: 262,144 on one GPU, 2^20 / N on N)")
     args = ap.parse_args()

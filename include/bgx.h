@@ -108,6 +108,8 @@ int bgx_synchronize(bgx_engine *e);
 /* replaces model.load_state_dict / state_dict()               model.py:36-37, train.py:513-515
  * host pointers, WEIGHTS layout. */
 int bgx_set_weights(bgx_engine *e, const float *W1, const float *b1, const float *w2, const float *b2);
+/* (bgx_set_weights and bgx_apply_delta return BGX_E_STATE while an asynchronous lane holds a batch: its kernel reads the
+ * weight tables on its own stream; bgx_lane_wait every busy lane first) */
 int bgx_get_weights(bgx_engine *e, float *W1, float *b1, float *w2, float *b2);
 
 /* ------------------------------------------------------------------------------------
@@ -178,8 +180,8 @@ int bgx_select_moves_host(bgx_engine *e, const int8_t *queries, int64_t n, float
  * With two or three lanes a host loop (model.py make_move callers: train.py:107, benchmark.py:86)
  * advances one part of its games while the GPU plays the others.  A lane's launch occupies half
  * the SMs, so the batches of two lanes are resident at once (a one-ply batch cannot be shorter
- * than its biggest turn tree; BGX_SELECT_LANE_GRID overrides the CTA count, 0 = every SM).
- * Batches of up to 2^21 queries (BGX_SELECT_ORDER_MAX) are walked heaviest first: the order
+ * than its biggest turn tree; bgx_set_option "select_lane_grid" overrides the CTA count, 0 = every SM).
+ * Batches of up to 2^21 queries ("select_order_max") are walked heaviest first: the order
  * never changes a result, only when it is computed. */
 #define BGX_ASYNC_LANES 4
 int bgx_select_moves_host_async(bgx_engine *e, int lane, const int8_t *queries, int64_t n, float epsilon, uint64_t seed,
@@ -219,6 +221,8 @@ int bgx_advance(bgx_engine *e, const int8_t *chosen, int8_t *next, int64_t n, ui
  * lockstep: ply[i] is the ply whose dice game i gets (the caller counts; NULL: 0), no engine needed. */
 int bgx_advance_host(const int8_t *chosen, int8_t *next, int64_t n, uint64_t seed, const int32_t *ply,
                      const int64_t *game_id, int8_t *winner);
+/* threads bgx_advance_host may use (0 = automatic: up to 4); several ranks sharing a box pass cores / ranks */
+int bgx_set_host_threads(int n);
 
 /* ------------------------------------------------------------------------------------
  * 4. Self-play population (replaces play_game, train.py:64-121, for many games at once)
@@ -233,6 +237,8 @@ typedef struct bgx_stats {
     int64_t td_steps;         /* TD(lambda) steps replayed (bgx_td_replay) */
     double td_sq_error;       /* sum of td_error^2 over the non-terminal steps (train.py:162) */
     int64_t tree_edges;       /* moves applied while walking the turn trees (work actually done; <= what the reference walks) */
+    int64_t td_live_rows;     /* TD replay: first-layer rows updated in the step passes (non-zero features of s_t, s_t+1, s_t+2), summed over the steps */
+    int64_t td_lazy_row_steps;/* TD replay: (row, step) pairs replayed late, when a sleeping row re-entered the window or at the end of its game */
 } bgx_stats;
 
 /* first-mover rule */
@@ -303,6 +309,19 @@ int bgx_td_replay_host(bgx_engine *e, const int8_t *records, int32_t T, int play
                        double lr, double lambda,
                        float *new_W1, float *new_b1, float *new_w2, float *new_b2, double *sq_errors);
 
+/* The cross-GPU exchange of a training round (replaces the pickling of trajectories back to the main process and its
+ * sequential replay, train.py:330-348, 527-547): ONE all-reduce(sum) of the fp32[BGX_NPARAMS_PADDED] weight delta per round,
+ * in place, on the engine's stream, through an NCCL communicator the caller owns (ncclComm_t; NCCL is bound with dlopen at
+ * first use, libbgx does not link it).  Afterwards every rank calls bgx_apply_delta with the same buffer. */
+int bgx_allreduce_delta(bgx_engine *e, void *nccl_comm, float *delta_dev);
+/* For callers without an NCCL binding of their own: the three calls that make a communicator.  id128 is the 128-byte
+ * ncclUniqueId that rank 0 creates and hands to the other ranks by any means (a file, MPI, torch.distributed, a socket).
+ * bgx_nccl_load names the library explicitly (NULL / not called: "libnccl.so.2" by the loader's search path). */
+int bgx_nccl_load(const char *libnccl_path);
+int bgx_nccl_unique_id(void *id128);
+int bgx_nccl_comm_init(bgx_engine *e, int n_ranks, int rank, const void *id128, void **nccl_comm);
+int bgx_nccl_comm_destroy(void *nccl_comm);
+
 /* ------------------------------------------------------------------------------------
  * 6. Introspection for benchmarks
  * ---------------------------------------------------------------------------------- */
@@ -316,8 +335,12 @@ int bgx_device_props(bgx_engine *e, int *sm_count, int *clock_khz, int64_t *glob
  * (first-layer store, barrier, hidden layer, window bookkeeping + lazy replay, barrier, values + gradients, row pass, end of
  * game; a barrier's wait shows up in the phase that follows it), [15] the TD steps of that CTA. */
 int bgx_td_profile(bgx_engine *e, int on, uint64_t *cycles);
-/* warps per CTA of the fused ply kernels as configured (defaults or BGX_*_WARPS) */
+/* warps per CTA of the fused ply kernels as configured */
 int bgx_kernel_config(bgx_engine *e, int *selfplay_warps, int *select_warps);
+/* tuning knobs of the fused ply kernels for benchmarks and probes; the defaults are the measured best.  Keys:
+ * "selfplay_warps", "select_warps" (16, 20, 24, 32), "select_lane_grid", "select_order_max", "select_urgent_min",
+ * "select_giant_min", "select_urgent_from_pct".  The library reads no environment variables. */
+int bgx_set_option(bgx_engine *e, const char *key, int64_t value);
 
 #ifdef __cplusplus
 }

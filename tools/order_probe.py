@@ -62,8 +62,9 @@ eng.close()
 policies = [(8, 10, 0), (7, 10, 0), (6, 10, 0), (5, 10, 0), (7, 8, 0)]
 for n in (G, G // 2):
     for (umin, gmin, pct) in policies:
-        os.environ.update(BGX_SELECT_URGENT_MIN=str(umin), BGX_SELECT_GIANT_MIN=str(gmin), BGX_SELECT_URGENT_FROM_PCT=str(pct))
         e = BatchEngine(0); e.set_weights(*w)
+        for key, val in (("select_urgent_min", umin), ("select_giant_min", gmin), ("select_urgent_from_pct", pct)):
+            e.set_option(key, val)
         row = []
         for name, order in orders.items():
             o = order[order < n] if n < G else order
