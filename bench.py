@@ -80,6 +80,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, args.cpu_procs or cores))
     w = init_weights()
+    debug_build = None
     # every step is a bounded sample of the workload; the whole run stays within ~3 minutes whatever K is
     args.cpu_seconds = max(1.0, min(args.cpu_seconds, 150.0 / max(args.steps, 1)))
     if ref_play.available():
@@ -90,8 +91,13 @@ def run_reference(args):
         for _ in range(args.steps):
             r = ref_play.run(w, args.cpu_seconds, procs)
             tot_p += r["plies"]; tot_s += r["sequences"]; tot_t += r["seconds"]
-        sample = (f"reference backgammon_env (oracle/_ref, g++ -O2) + model.py make_move loop (numpy encode, torch CPU "
-                  f"1 thread/process), {procs} processes x {args.cpu_seconds:g} s per step, greedy self-play from the opening")
+        sample = (f"reference backgammon_env (oracle/_ref, g++ -O2) + {r['model']} make_move loop (numpy encode, torch CPU "
+                  f"1 thread/process), {procs} processes x {args.cpu_seconds:g} s per step, greedy self-play from the opening, "
+                  "Philox dice of the GPU arm through Game.setDice")
+        if ref_play.available(debug=True):           # the build the reference's own makefile ships (makefile:15: Debug), once
+            rd = ref_play.run(w, min(3.0, args.cpu_seconds), procs, debug=True)
+            debug_build = {"value": rd["plies"] / rd["seconds"], "unit": UNIT, "build": "g++ -O0 -g (CMAKE_BUILD_TYPE=Debug, makefile:15)",
+                           "sample": f"{procs} processes x {min(3.0, args.cpu_seconds):g} s"}
     else:
         # the reference did not compile here (no /root/reference at build time): time the oracle port
         kind = "port"
@@ -105,7 +111,8 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus),
             "sequences_per_sec": tot_s / tot_t,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample, "enumeration_only": direct},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample, "enumeration_only": direct,
+                             "reference_debug_build": debug_build},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)

@@ -331,3 +331,20 @@ def _reference_encoder():
     from oracle.oracle import Oracle
     o = Oracle()
     return lambda r: np.concatenate([o.encode(r[t:t + 1, :28].astype(np.int32), int(r[t, 28])) for t in range(len(r))])
+
+
+def test_cpu_baseline_driver_restatement_plays_the_reference_models_moves(golden):
+    """oracle/ref_play.py times the reference's own model.py where /root/reference is visible and a restatement of it on the
+    GPU box: on the same Philox dice both choose the same sequence at every ply of whole games (reference engine underneath)."""
+    from oracle import ref_play
+    if not (ref_play.available() and ref_play.reference_model_available()):
+        pytest.skip("needs oracle/_ref and /root/reference")
+    import torch
+    torch.set_num_threads(1)
+    bg = ref_play._import_reference_module()
+    for tag in ("rand", "trained"):
+        w = golden_weights(golden("model.npz"), tag)
+        a, b = [], []
+        ref_play.play(bg, w, [11, 12], 120.0, ref_play.PhiloxDice(), True, record=a)
+        ref_play.play(bg, w, [11, 12], 120.0, ref_play.PhiloxDice(), False, record=b)
+        assert len(a) > 60 and a == b, tag
