@@ -299,7 +299,30 @@ def side_legs(eng, dev, peaks, n_positions):
     enc_gbs = rows * (32 + 792) / t_enc / 1e9
     V = torch.zeros(n, dtype=torch.float32, device=dev)
     t_ev = best_ms(lambda: eng.evaluate(qd, V)) * 1e-3
-    return {"positions": n, "sequences": seqs, "unique_afterstates": uniq,
+    arena_leg = None
+    try:                                             # batched head-to-head evaluation (train.py:262-302, benchmark.py:64-130)
+        from bgx.evaluate import Arena, RANDOM
+        with np.load(os.path.join(ROOT, "tests", "golden", "model.npz")) as z:
+            trained = tuple(z[f"trained_{k}"] for k in ("W1", "b1", "w2", "b2"))
+        arena = Arena(dev.index or 0)
+        games = 4096
+        i = np.arange(games)
+        arena.play(trained, RANDOM, np.zeros(256, np.int8), np.arange(256) % 2)          # warm-up
+        arena_leg = {"games": games}
+        for name, opp in (("model_vs_random", RANDOM), ("model_vs_model", init_weights())):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = arena.play(trained, opp, (i % 2).astype(np.int8), i % 2)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            arena_leg[name] = {"seconds": dt, "games_per_sec": games / dt, "plies_per_sec": float(res["plies"].sum()) / dt,
+                               "a_win_rate": float(np.mean(res["winner"] == (i % 2)))}
+        arena_leg["note"] = ("Arena.play: 4,096 head-to-head games in lockstep, one k_select launch per policy and ply + k_advance; wall clock "
+                             "including the host loop.  The reference plays its 2 x 100 evaluation games per checkpoint at ~300 plies/s per core")
+        arena.close()
+    except Exception as exc:                         # a side figure: never fails the bench
+        arena_leg = {"error": str(exc)}
+    return {"positions": n, "sequences": seqs, "unique_afterstates": uniq, "arena": arena_leg,
             "enumerate": {"kernel": "k_enumerate_summary", "ms": t_enum * 1e3, "positions_per_sec": n / t_enum,
                           "sequences_per_sec": seqs / t_enum, "unique_afterstates_per_sec": uniq / t_enum},
             "enumerate_materialised": {"kernels": "k_enumerate_count + k_scan_* + k_enumerate_write", "count_and_scan_ms": t_cnt * 1e3,
@@ -552,7 +575,7 @@ def run_ours(args):
         # a multiply and an FMA = 3 FLOP; ~1,300 FLOP for the hidden / output layer of both states.  Dense, as the reference
         # executes it: ~255 kFLOP per step.
         props_td = eng.device_props()
-        fp32_peak_td = props_td["sm_count"] * 128 * 2 * peak_json()[0].get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+        fp32_peak_td = world * props_td["sm_count"] * 128 * 2 * peak_json()[0].get("sm_max_mhz", 1965.0) * 1e6 / 1e12   # all ranks
         flop_sparse = (cnt[4] * 9 + cnt[5] * 3) * 128 + steps_td * 1300
         k_s = ms[4] * 1e-3
         tfacts, tstate = capture_facts("k_td_replay")
@@ -568,7 +591,7 @@ def run_ours(args):
                            "row pass), two games per SM; neither FP32 nor memory bounds it (see `issue`), the FLOP figure says how far the "
                            "arithmetic is from mattering"}
         if tfacts.get("warp_inst_per_step") and tstate["verified"]:
-            ipk = props_td["sm_count"] * 4 * peak_json()[0].get("sm_max_mhz", 1965.0) * 1e6
+            ipk = world * props_td["sm_count"] * 4 * peak_json()[0].get("sm_max_mhz", 1965.0) * 1e6
             td_roof["issue"] = {"unit": "G warp-inst/s", "peak": ipk / 1e9, "achieved": steps_td * tfacts["warp_inst_per_step"] / k_s / 1e9,
                                 "frac": steps_td * tfacts["warp_inst_per_step"] / k_s / ipk, "warp_inst_per_step": tfacts["warp_inst_per_step"],
                                 "traffic": tfacts.get("dram_bytes_per_launch")}

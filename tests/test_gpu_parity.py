@@ -373,6 +373,43 @@ def test_play_ply_is_select_plus_advance(eng, golden):
     assert np.array_equal(got2, want2)
 
 
+def test_play_ply_restart_is_the_resident_population(eng, golden):
+    """bgx_play_ply_restart_host_async driven from the host for a few hundred plies = the device-resident population of
+    bgx_selfplay_step after the same number of plies: records, ply numbers and game ids of every slot, bit for bit
+    (restarts in place with id + stride, first mover id % 2, Philox dice of ply 0), and the winners it reported are the
+    games the resident population finished."""
+    from bgx import host as H
+    from bgx.lib import FIRST_PARITY
+    from bgx.synth import START_BOARD
+    eng.set_weights(*golden_weights(golden("model.npz"), "trained"))
+    n, stride, plies = 3000, 3000, 150                     # trained weights: ~77 plies per game, so most slots restart once or twice
+    eng.selfplay_init(n, first_id=0, id_stride=stride, seed=SEED, first_mover=FIRST_PARITY, traj_cap=0)
+    st = eng.selfplay_step(plies)
+    want_rec, want_ply, want_gid = eng.selfplay_read()
+    # the same games from the host: opening records with the dice of ply 0
+    gid = np.arange(n, dtype=np.int64)
+    ply = np.zeros(n, np.int32)
+    fresh = np.zeros((n, 32), np.int8)
+    fresh[:, :24] = START_BOARD
+    fresh[:, 28] = (gid & 1) ^ 1                           # bgx_advance_host flips the mover and rolls ply 0
+    bufs = [H.advance(fresh, fresh.copy(), SEED, ply, gid), np.zeros((n, 32), np.int8)]
+    win = np.zeros(n, np.int8)
+    finished = p1 = 0
+    cuts = [0, 1000, 1001, n]
+    for step in range(plies):
+        a, b = bufs[step & 1], bufs[1 - (step & 1)]
+        for lane, (lo, hi) in enumerate(zip(cuts[:-1], cuts[1:])):
+            eng.play_ply_restart_host_async(lane, a[lo:hi], ply[lo:hi], gid[lo:hi], stride, b[lo:hi], win[lo:hi], first_mover=FIRST_PARITY, dice_seed=SEED)
+        for lane in range(3):
+            eng.wait(lane)
+        finished += int((win >= 0).sum())
+        p1 += int((win == 0).sum())
+    got = bufs[plies & 1]
+    assert np.array_equal(ply, want_ply) and np.array_equal(gid, want_gid)
+    assert np.array_equal(got[:, :29], want_rec[:, :29])                     # position + mover (the resident slot keeps no dice)
+    assert finished == st["games_finished"] and p1 == st["p1_wins"] and finished > n
+
+
 def test_select_moves_golden_games(eng, orc, golden):
     """The reference's own greedy games (model.make_move on the reference engine), ply by ply."""
     g = golden("games.npz")
