@@ -333,18 +333,32 @@ def _reference_encoder():
     return lambda r: np.concatenate([o.encode(r[t:t + 1, :28].astype(np.int32), int(r[t, 28])) for t in range(len(r))])
 
 
-def test_cpu_baseline_driver_restatement_plays_the_reference_models_moves(golden):
+def test_cpu_baseline_driver_restatement_plays_the_reference_models_moves():
     """oracle/ref_play.py times the reference's own model.py where /root/reference is visible and a restatement of it on the
-    GPU box: on the same Philox dice both choose the same sequence at every ply of whole games (reference engine underneath)."""
+    GPU box: on the same Philox dice both choose the same sequence at every ply of whole games (reference engine underneath).
+    Runs in a process of its own: `backgammon_env` there must be the reference's build, not the compat module."""
+    import subprocess
+    import sys
     from oracle import ref_play
     if not (ref_play.available() and ref_play.reference_model_available()):
         pytest.skip("needs oracle/_ref and /root/reference")
-    import torch
-    torch.set_num_threads(1)
-    bg = ref_play._import_reference_module()
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    code = """
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, %r)
+from oracle import ref_play
+torch.set_num_threads(1)
+bg = ref_play._import_reference_module()
+with np.load(%r) as z:
     for tag in ("rand", "trained"):
-        w = golden_weights(golden("model.npz"), tag)
+        w = tuple(z[tag + "_" + k] for k in ("W1", "b1", "w2", "b2"))
         a, b = [], []
         ref_play.play(bg, w, [11, 12], 120.0, ref_play.PhiloxDice(), True, record=a)
         ref_play.play(bg, w, [11, 12], 120.0, ref_play.PhiloxDice(), False, record=b)
         assert len(a) > 60 and a == b, tag
+print("SAME MOVES")
+""" % (root, os.path.join(root, "tests", "golden", "model.npz"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SAME MOVES" in r.stdout, r.stderr[-2000:]
