@@ -179,6 +179,9 @@ static int create_into(bgx_engine *e, int device, const cudaDeviceProp &prop)
 #undef BGX_SMEM_ATTR
     CU(cudaFuncSetAttribute(k_td_replay<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
     CU(cudaFuncSetAttribute(k_td_replay<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
+    // the smallest carve-out that holds kTdCtasPerSm games (percent of the SM's 228 KB): the rest of the array is their L1
+    CU(cudaFuncSetAttribute(k_td_replay<false>, cudaFuncAttributePreferredSharedMemoryCarveout, kTdCarveoutBytes * 100 / (228 * 1024)));
+    CU(cudaFuncSetAttribute(k_td_replay<true>, cudaFuncAttributePreferredSharedMemoryCarveout, kTdCarveoutBytes * 100 / (228 * 1024)));
     return BGX_OK;
 }
 

@@ -83,17 +83,15 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b)
     return d;
 }
 
-constexpr int kTdWarps = 8;
-constexpr int kTdCtasPerSm = 2;                             // two games per SM: one hides the other's dependent-issue latency
+constexpr int kTdWarps = 4;
+constexpr int kTdCtasPerSm = 4;                             // four games per SM: the others hide a game's dependent-issue latency
 constexpr int kTdThreads = kTdWarps * 32;
-constexpr int kTdClasses = 8;                               // = warps: warp c owns class c
-constexpr int kTdClassRows = 25;                            // classes 0..5 have 25 rows, 6 and 7 have 24
+constexpr int kTdClasses = 4;                               // = warps: warp c owns class c
 
-// the fixed 8-colouring of the feature rows: the eight features of a point (4 per side) go to eight different classes,
-// rotated by the point so that "at least one checker" rows do not pile up in one class
-__host__ __device__ constexpr int td_class(int f) { return f < 192 ? ((f & 7) + (f >> 3)) & 7 : (f & 7); }
-// row r (0..24) of class c: r < 24 is the class's feature of point r, r = 24 its tail feature (classes 0..5 only)
-__host__ __device__ constexpr int td_row_of(int c, int r) { return r < 24 ? 8 * r + ((c - r) & 7) : 192 + c; }
+// the fixed 4-colouring of the feature rows: the four features of a point side go to four different classes, rotated by
+// the point so that "at least one checker" rows do not pile up in one class.  A class has two rows per point (one per
+// side) and one or two of the six tail rows: 50 or 49 rows, two per lane.
+__host__ __device__ constexpr int td_class(int f) { return f < 192 ? ((f & 3) + (f >> 3)) & 3 : (f & 3); }
 
 struct __align__(16) TdCtrl {
     long long game;
@@ -104,18 +102,22 @@ struct __align__(16) TdCtrl {
 
 // shared memory map (bytes)
 constexpr int kTdOffC = 0;                                           // c_k of every step so far
-constexpr int kTdOffZ = kTdOffC + kTdMaxSteps * 4;                   // class partial pre-activations [8][128 units][2 states]
+constexpr int kTdOffZ = kTdOffC + kTdMaxSteps * 4;                   // class partial pre-activations [4][128 units][2 states]
 constexpr int kTdOffH = kTdOffZ + kTdClasses * kHidden * 2 * 4;      // hidden activations [128 units][2 states]
 constexpr int kTdOffB1 = kTdOffH + kHidden * 2 * 4;                  // b1 [128]
 constexpr int kTdOffW2 = kTdOffB1 + kHidden * 4;                     // w2, double-buffered by step parity [2][128]
-constexpr int kTdOffRed = kTdOffW2 + 2 * kHidden * 4;                // output partials [2 parities][2 states][8]
-constexpr int kTdRing = 16;                                          // records in the ring (a power of two)
-constexpr int kTdAhead = 8;                                          // how many states ahead of the step the loader fetches
-constexpr int kTdOffRing = kTdOffRed + 2 * 2 * 8 * 4;                // records of consecutive states [kTdRing][32]
+constexpr int kTdOffRed = kTdOffW2 + 2 * kHidden * 4;                // output partials [2 parities][2 states][4 classes]
+constexpr int kTdRing = 8;                                           // records in the ring (a power of two)
+constexpr int kTdAhead = 6;                                          // how many states ahead of the step the loader fetches
+static_assert(kTdAhead + 2 <= kTdRing && kTdAhead >= 4, "the ring holds s_t-1 .. s_t+kTdAhead while s_t .. s_t+2 are read");
+constexpr int kTdOffRing = kTdOffRed + 2 * 2 * kTdClasses * 4;       // records of consecutive states [kTdRing][32]
 constexpr int kTdOffOff = kTdOffRing + kTdRing * 32;                       // the borne-off feature k / 15.0 for k = 0..15
 constexpr int kTdOffCtrl = kTdOffOff + 16 * 4;
 constexpr int kTdSmem = kTdOffCtrl + (int)sizeof(TdCtrl);
-static_assert(kTdSmem <= 232448 && kTdOffCtrl % 16 == 0, "k_td_replay: shared memory per CTA");
+// four games per SM inside the 64 KB shared-memory carve-out (1 KB per CTA is the system's, 32 B are static): the other 192 KB
+// of the SM's array are the L1 that holds the four games' windows of live rows
+constexpr int kTdCarveoutBytes = 64 * 1024;
+static_assert(kTdCtasPerSm * (kTdSmem + 32 + 1024) <= kTdCarveoutBytes && kTdOffCtrl % 16 == 0, "k_td_replay: shared memory per CTA");
 
 // loader: 4 bytes of a record, global -> shared, without passing through a register (nothing waits for the load)
 __device__ __forceinline__ void td_fetch(void *dst_smem, const void *src)
@@ -128,24 +130,31 @@ __device__ __forceinline__ void td_fetch_wait() { asm volatile("cp.async.wait_gr
 
 __device__ __forceinline__ void td_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kTdThreads) : "memory"); }
 
-// What lane r contributes to its warp's class: which record byte it looks at and how that byte becomes a feature value
-// (model.py:111-144), branch-free: d = sign * byte - threshold, then
+// What a lane contributes to its warp's class: up to two feature rows (A, B), each defined by the record byte it looks at and
+// how that byte becomes the feature value (model.py:111-144), branch-free: d = sign * byte - threshold, then
 //   form 0 (step):  d > 0 ? 1 : 0      point features "at least k+1 checkers" (sign picks the side), the two turn flags
 //   form 1 (ramp):  max(d, 0) / 2      "(n - 3) / 2" of a point side, bar counts / 2
 //   form 2 (table): off[byte]          borne-off counts / 15.0 (the fp32 divide)
-//   form 3: nothing (lanes above 24, the missing tail row of classes 6 and 7)
+//   form 3: no row
+// Lane r < 24 speaks for point r: A = the class's feature of the PLAYER1 side (row 8r + k, k = (class - r) & 3), B = the same
+// feature of the PLAYER2 side (row 8r + 4 + k).  Lane 24: class 0 -> 192 (turn == 0), 1 -> 193 (turn != 0), 2 -> 194, 3 -> 195
+// (bar counts); lane 25: class 0 -> 196, 1 -> 197 (borne-off counts).  Within a class rows ascend with (lane, A before B).
 struct TdLaneRow {
-    int byte, sign, thr, form;
-    __device__ __forceinline__ void init(int cls, int lane)
+    int row, byte, sign, thr, form;                          // row: the feature index, -1 if none
+    __device__ __forceinline__ void init(int cls, int lane, int side)
     {
-        const int j = (cls - lane) & 7, k = j & 3;           // feature j of point `lane`: side j >> 2, k-th of its four
-        byte = lane; sign = j < 4 ? 1 : -1; thr = k; form = k < 3 ? 0 : 1;
-        if (lane == 24) {
-            byte = cls < 2 ? 28 : 22 + cls;                  // turn flag | bar counts 24, 25 | borne-off counts 26, 27
-            sign = cls == 0 ? -1 : 1; thr = cls == 0 ? -1 : 0;    // 192: turn == 0, 193: turn != 0
-            form = cls < 2 ? 0 : (cls < 4 ? 1 : (cls < 6 ? 2 : 3));
-        } else if (lane > 24) {
-            byte = 31; form = 3;
+        const int k = (cls - lane) & 3;
+        row = 8 * lane + 4 * side + k; byte = lane; sign = side ? -1 : 1; thr = k; form = k < 3 ? 0 : 1;
+        if (lane >= 24) {
+            row = -1; byte = 31; sign = 1; thr = 0; form = 3;
+            if (side == 0 && lane == 24) {
+                row = 192 + cls;
+                byte = cls < 2 ? 28 : 22 + cls;              // the turn flag | bar counts (bytes 24, 25)
+                sign = cls == 0 ? -1 : 1; thr = cls == 0 ? -1 : 0;
+                form = cls < 2 ? 0 : 1;
+            } else if (side == 0 && lane == 25 && cls < 2) {
+                row = 196 + cls; byte = 26 + cls; form = 2;  // borne-off counts (bytes 26, 27)
+            }
         }
     }
     __device__ __forceinline__ float value(int v, const float *off) const
@@ -155,17 +164,6 @@ struct TdLaneRow {
         return form == 0 ? step : (form == 1 ? ramp : (form == 2 ? tab : 0.f));
     }
 };
-
-// the live rows of this warp's class at step t: lane r holds row r's feature value in s_t, s_t+1, s_t+2 (0 beyond the game)
-__device__ __forceinline__ uint32_t td_list(const int8_t *ring, const float *off, const TdLaneRow &me, int t, int T, float &x0, float &x1, float &x2)
-{
-    x0 = me.value((int)ring[(t & (kTdRing - 1)) * 32 + me.byte], off);
-    x1 = me.value((int)ring[((t + 1) & (kTdRing - 1)) * 32 + me.byte], off);
-    x2 = me.value((int)ring[((t + 2) & (kTdRing - 1)) * 32 + me.byte], off);
-    if (t + 1 >= T) x1 = 0.f;
-    if (t + 2 >= T) x2 = 0.f;
-    return __ballot_sync(kFull, x0 != 0.f || x1 != 0.f || x2 != 0.f);
-}
 
 __device__ __forceinline__ float4 fma4(float s, float4 a, float4 c)      // s * a + c
 {
@@ -216,8 +214,8 @@ template <bool kProf>
 __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams p)
 {
     extern __shared__ __align__(16) unsigned char td_smem[];
-    long long pc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;
-    __shared__ long long td_arrive[8];       // kProf: cycles per phase as seen by thread 0
+    long long pc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;   // kProf: cycles per phase as seen by lane 0 of every warp
+    __shared__ long long td_arrive[kTdWarps];
 #define TD_MARK(i) do { if (kProf) { const long long now_ = clock64(); pc[i] += now_ - pt; pt = now_; } } while (0)
     float4 *W4 = reinterpret_cast<float4 *>(p.home + (size_t)blockIdx.x * 2 * kTableFloats), *E4 = W4 + kTableFloats / 4;
     float *chist = reinterpret_cast<float *>(td_smem + kTdOffC);
@@ -232,27 +230,37 @@ __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams
     const int tid = threadIdx.x, lane = tid & 31, cls = tid >> 5;            // warp = row class
     const int col = 4 * lane;                                // this thread's hidden units: col .. col + 3
     const bool owner = cls == 0;                             // the class-0 thread of four units also keeps their b1 / w2 entries
-    const int unit = 16 * cls + (lane & 15), sig_state = lane >> 4;          // hidden-layer duty: one (unit, state) sigmoid per lane
-    const bool loader = cls == kTdWarps - 1;                 // this warp pops the queue and feeds the record ring
-    TdLaneRow me;
-    me.init(cls, lane);
+    const int unit = 32 * cls + lane;                        // hidden-layer duty: this lane runs both states of one unit
+    const bool loader = cls == kTdWarps - 1;                 // this warp feeds the record ring and picks the games
+    TdLaneRow meA, meB;
+    meA.init(cls, lane, 0);
+    meB.init(cls, lane, 1);
+    const int idxA = max(meA.row, 0) * 32, idxB = max(meB.row, 0) * 32;      // where this lane's rows start in a table (float4 units)
 
     float *mine = p.partial + (size_t)blockIdx.x * BGX_NPARAMS_PADDED;
     for (int i = tid; i < BGX_NPARAMS_PADDED; i += kTdThreads) mine[i] = 0.f;
     if (tid < 16) offtab[tid] = off_feature(tid);
     const float4 *wt4 = reinterpret_cast<const float4 *>(p.wt);
-    const int n_rows = cls < 6 ? 25 : 24;
-    for (int r = 0; r < n_rows; r++) {
-        W4[td_row_of(cls, r) * 32 + lane] = wt4[td_row_of(cls, r) * 32 + lane];
-        E4[td_row_of(cls, r) * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    {   // the CTA's home tables start as the snapshot with zero traces; every thread initialises the elements it owns
+        const uint32_t haveA = __ballot_sync(kFull, meA.row >= 0), haveB = __ballot_sync(kFull, meB.row >= 0);
+        for (int pass = 0; pass < 2; pass++) {
+            uint32_t rows = pass ? haveB : haveA;
+            while (rows) {
+                const int j = __ffs(rows) - 1;
+                rows &= rows - 1;
+                const int idx = __shfl_sync(kFull, pass ? idxB : idxA, j) + lane;
+                W4[idx] = wt4[idx];
+                E4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
     }
-    int last = -1;                                           // lane r: last step applied to the HOME copy of row r, -1 = untouched in this game
+    int lastA = -1, lastB = -1;                              // last step applied to the home copy of this lane's rows, -1 = untouched in this game
     const int8_t *traj = nullptr;                            // loader: the game's records
     long long cursor = blockIdx.x;                           // loader: the next game of this CTA
     unsigned long long steps = 0, games = 0, lazy = 0, rows_live = 0;
     double sq_sum = 0.0;
 
-    // loader: take the next finished game off the queue, publish it, stage its first three records
+    // loader: take the next finished game off the queue, publish it, stage its first records
     auto next_game = [&]() {
         td_fetch_wait<0>();                                  // nothing of the previous game is still on its way into the ring
         long long g = -1;
@@ -290,6 +298,49 @@ __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams
     };
     if (loader) next_game();
 
+    // one pass over the live rows named by `rows` (lane j speaks for the row at idx_lane of lane j, with feature values
+    // x0 / x1 / x2 in s_t / s_t+1 / s_t+2): e <- lambda*e + grad ; w <- w + c*e (train.py:141-147), and with the NEW weights the
+    // first layer of step t+1.  Two rows per trip: their loads travel together.
+    auto row_pass = [&](uint32_t rows, int idx_lane, float x0, float x1, float x2, float lam, float c, const float4 &gh, float4 &z0, float4 &z1) {
+        while (rows) {
+            const int ja = __ffs(rows) - 1;
+            rows &= rows - 1;
+            const bool two = rows != 0;
+            const int jb = two ? __ffs(rows) - 1 : ja;
+            rows &= rows - 1;
+            const int ia = __shfl_sync(kFull, idx_lane, ja) + lane, ib = __shfl_sync(kFull, idx_lane, jb) + lane;
+            float4 ea = E4[ia], wa = W4[ia], eb = E4[ib], wb = W4[ib];
+            ea = fma4(lam, ea, mul4(__shfl_sync(kFull, x0, ja), gh));
+            wa = fma4(c, ea, wa);
+            E4[ia] = ea;
+            W4[ia] = wa;
+            z0 = fma4(__shfl_sync(kFull, x1, ja), wa, z0);
+            z1 = fma4(__shfl_sync(kFull, x2, ja), wa, z1);
+            if (two) {
+                eb = fma4(lam, eb, mul4(__shfl_sync(kFull, x0, jb), gh));
+                wb = fma4(c, eb, wb);
+                E4[ib] = eb;
+                W4[ib] = wb;
+                z0 = fma4(__shfl_sync(kFull, x1, jb), wb, z0);
+                z1 = fma4(__shfl_sync(kFull, x2, jb), wb, z1);
+            }
+        }
+    };
+    // rows that enter the window after a sleep replay what they missed (first missed step .. upto) in their home copies
+    auto replay_late = [&](uint32_t late, int idx_lane, int last, int upto, float lam) {
+        while (late) {
+            const int j = __ffs(late) - 1;
+            late &= late - 1;
+            const int from = __shfl_sync(kFull, last, j) + 1;
+            const int idx = __shfl_sync(kFull, idx_lane, j) + lane;
+            float4 e = E4[idx], w = W4[idx];
+            td_replay_row(e, w, from, upto, chist, lam);
+            E4[idx] = e;
+            W4[idx] = w;
+            lazy += (unsigned)(upto + 1 - from);
+        }
+    };
+
     for (;;) {
         td_bar();                                            // game start: ctrl and the first records are ready
         if (ctrl->done) break;
@@ -298,7 +349,7 @@ __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams
         const float lam = ctrl->lam;
         const double lr = ctrl->lr;
         const float lr_hi = (float)lr, lr_lo = (float)(lr - (double)lr_hi);
-        last = -1;
+        lastA = lastB = -1;
         if (owner) {
             *reinterpret_cast<float4 *>(b1s + col) = *reinterpret_cast<const float4 *>(p.flat + kTableFloats + col);
             *reinterpret_cast<float4 *>(w2s + col) = *reinterpret_cast<const float4 *>(p.flat + kTableFloats + kHidden + col);
@@ -306,17 +357,19 @@ __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams
         float b2 = p.flat[kTableFloats + 2 * kHidden], eb2 = 0.f;            // every thread keeps its own copy
         float4 eb1 = make_float4(0.f, 0.f, 0.f, 0.f), ew2 = eb1;             // owners only
 
-        // first layer of step 0: this class's live rows against x(s_0) and x(s_1)
+        // this lane's rows in s_0, s_1, s_2 (0 beyond the game), and the first layer of step 0 against x(s_0) and x(s_1)
+        const int r0 = (int)ring[meA.byte], r1 = (int)ring[32 + meA.byte], r2 = (int)ring[64 + meA.byte];   // (A and B look at the same byte)
+        float xA0 = meA.value(r0, offtab), xA1 = T > 1 ? meA.value(r1, offtab) : 0.f, xA2 = T > 2 ? meA.value(r2, offtab) : 0.f;
+        float xB0 = meB.value(r0, offtab), xB1 = T > 1 ? meB.value(r1, offtab) : 0.f, xB2 = T > 2 ? meB.value(r2, offtab) : 0.f;
         float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f), z1 = z0;
-        float x0, x1, x2;                                    // lane r: row r's feature value in s_t, s_t+1, s_t+2
-        {
-            uint32_t live = td_list(ring, offtab, me, 0, T, x0, x1, x2);
-            while (live) {
-                const int r = __ffs(live) - 1;
-                live &= live - 1;
-                const float4 w = W4[td_row_of(cls, r) * 32 + lane];
-                z0 = fma4(__shfl_sync(kFull, x0, r), w, z0);
-                z1 = fma4(__shfl_sync(kFull, x1, r), w, z1);
+        for (int pass = 0; pass < 2; pass++) {
+            uint32_t rows = __ballot_sync(kFull, pass ? (xB0 != 0.f || xB1 != 0.f) : (xA0 != 0.f || xA1 != 0.f));
+            while (rows) {
+                const int j = __ffs(rows) - 1;
+                rows &= rows - 1;
+                const float4 w = W4[__shfl_sync(kFull, pass ? idxB : idxA, j) + lane];
+                z0 = fma4(__shfl_sync(kFull, pass ? xB0 : xA0, j), w, z0);
+                z1 = fma4(__shfl_sync(kFull, pass ? xB1 : xA1, j), w, z1);
             }
         }
 
@@ -333,56 +386,56 @@ __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams
             TD_MARK(0);
             td_bar();
             TD_MARK(1);
-            // (2) hidden layer: lane = (unit, state); output partials of the warp's 16 units
+            // (2) hidden layer: one unit per lane, both states; output partials of the warp's 32 units
             {
-                const float *zp = zpart + unit * 2 + sig_state;
-                const float za = zp[0 * kHidden * 2] + zp[1 * kHidden * 2], zb = zp[2 * kHidden * 2] + zp[3 * kHidden * 2];
-                const float zc = zp[4 * kHidden * 2] + zp[5 * kHidden * 2], zd = zp[6 * kHidden * 2] + zp[7 * kHidden * 2];
-                const float h = sigmoid_f32(((za + zb) + (zc + zd)) + b1s[unit]);
-                hs[unit * 2 + sig_state] = h;
-                float y = w2c[unit] * h;
+                const float2 *zp = reinterpret_cast<const float2 *>(zpart) + unit;
+                const float2 za = zp[0 * kHidden], zb = zp[1 * kHidden], zc = zp[2 * kHidden], zd = zp[3 * kHidden];
+                const float bias = b1s[unit], w2u = w2c[unit];
+                const float h0 = sigmoid_f32(((za.x + zb.x) + (zc.x + zd.x)) + bias), h1 = sigmoid_f32(((za.y + zb.y) + (zc.y + zd.y)) + bias);
+                reinterpret_cast<float2 *>(hs)[unit] = make_float2(h0, h1);
+                float y0 = w2u * h0, y1 = w2u * h1;
 #pragma unroll
-                for (int o = 1; o < 16; o <<= 1) y += __shfl_xor_sync(kFull, y, o);
-                if ((lane & 15) == 0) red[((t & 1) * 2 + sig_state) * 8 + cls] = y;
+                for (int o = 1; o < 32; o <<= 1) {
+                    y0 += __shfl_xor_sync(kFull, y0, o);
+                    y1 += __shfl_xor_sync(kFull, y1, o);
+                }
+                if (lane == 0) {
+                    red[((t & 1) * 2 + 0) * 4 + cls] = y0;
+                    red[((t & 1) * 2 + 1) * 4 + cls] = y1;
+                }
             }
             TD_MARK(2);
-            // (3) the live rows of this class
-            if (t > 0) {                                     // the window moves on by one state: one new feature value per lane
-                x0 = x1; x1 = x2;
-                x2 = t + 2 < T ? me.value((int)ring[((t + 2) & (kTdRing - 1)) * 32 + me.byte], offtab) : 0.f;
+            // (3) the live rows of this class: the window moves on by one state, one new feature value per row
+            if (t > 0) {
+                const int rn = (int)ring[((t + 2) & (kTdRing - 1)) * 32 + meA.byte];
+                xA0 = xA1; xA1 = xA2; xA2 = t + 2 < T ? meA.value(rn, offtab) : 0.f;
+                xB0 = xB1; xB1 = xB2; xB2 = t + 2 < T ? meB.value(rn, offtab) : 0.f;
             }
-            const uint32_t live = __ballot_sync(kFull, x0 != 0.f || x1 != 0.f || x2 != 0.f);
-            rows_live += (unsigned)__popc(live);
-            // rows that enter the window after a sleep replay what they missed (through step t-1) in their home copies
-            uint32_t late = __ballot_sync(kFull, (live >> lane & 1) && last >= 0 && last < t - 1);
-            while (late) {
-                const int j = __ffs(late) - 1;
-                late &= late - 1;
-                const int from = __shfl_sync(kFull, last, j) + 1;
-                const int idx = td_row_of(cls, j) * 32 + lane;
-                float4 e = E4[idx], w = W4[idx];
-                td_replay_row(e, w, from, t - 1, chist, lam);
-                E4[idx] = e;
-                W4[idx] = w;
-                lazy += (unsigned)(t - from);
-            }
-            if (live >> lane & 1) last = t;                  // (their update of step t follows in (6))
+            const bool onA = xA0 != 0.f || xA1 != 0.f || xA2 != 0.f, onB = xB0 != 0.f || xB1 != 0.f || xB2 != 0.f;
+            const uint32_t liveA = __ballot_sync(kFull, onA), liveB = __ballot_sync(kFull, onB);
+            rows_live += (unsigned)(__popc(liveA) + __popc(liveB));
+            // rows that enter the window after a sleep catch up through step t-1
+            const uint32_t lateA = __ballot_sync(kFull, onA && lastA >= 0 && lastA < t - 1);
+            const uint32_t lateB = __ballot_sync(kFull, onB && lastB >= 0 && lastB < t - 1);
+            if (lateA) replay_late(lateA, idxA, lastA, t - 1, lam);
+            if (lateB) replay_late(lateB, idxB, lastB, t - 1, lam);
+            if (onA) lastA = t;                              // (their update of step t follows in (6))
+            if (onB) lastB = t;
             TD_MARK(3);
             if (kProf && lane == 0) td_arrive[cls] = clock64();
             td_bar();                                        // the step's second barrier
             TD_MARK(4);
             if (kProf) {
                 long long la = 0;
-                for (int w = 0; w < 8; w++) la = max(la, td_arrive[w]);
+                for (int w = 0; w < kTdWarps; w++) la = max(la, td_arrive[w]);
                 const long long now_ = clock64();
                 pc[11] += now_ - la;                         // barrier release after the last arrival
                 pc[12] += la - td_arrive[cls];               // this warp's wait for the last arrival
                 pt = clock64();
             }
             // (4) values, TD error: odd lanes evaluate s_t+1, even lanes s_t (one sigmoid stream per warp)
-            const float4 ra = *reinterpret_cast<const float4 *>(red + ((t & 1) * 2 + (lane & 1)) * 8);
-            const float4 rb = *reinterpret_cast<const float4 *>(red + ((t & 1) * 2 + (lane & 1)) * 8 + 4);
-            const float v_mine = sigmoid_f32((((ra.x + ra.y) + (ra.z + ra.w)) + ((rb.x + rb.y) + (rb.z + rb.w))) + b2);
+            const float4 ra = *reinterpret_cast<const float4 *>(red + ((t & 1) * 2 + (lane & 1)) * 4);
+            const float v_mine = sigmoid_f32(((ra.x + ra.y) + (ra.z + ra.w)) + b2);
             const float v_cur = __shfl_sync(kFull, v_mine, 0);
             TD_MARK(8);
             float c;                                         // (float)(lr * delta), lr a double: train.py:147
@@ -415,33 +468,11 @@ __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams
                                           __fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.y), __fsub_rn(1.0f, h0.y)), h0.y),
                                           __fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.z), __fsub_rn(1.0f, h0.z)), h0.z),
                                           __fmul_rn(__fmul_rn(__fmul_rn(gv, w2v.w), __fsub_rn(1.0f, h0.w)), h0.w));
-            // (6) one pass over the live rows: e <- lambda*e + grad ; w <- w + c*e (train.py:141-147), and with the NEW weights
-            // the first layer of step t+1 (s_t+1 and s_t+2 have all their non-zero features among the live rows)
+            // (6) one pass over the live rows (s_t+1 and s_t+2 have all their non-zero features among them)
             z0 = make_float4(0.f, 0.f, 0.f, 0.f); z1 = z0;
             TD_MARK(5);
-            for (uint32_t rows = live; rows;) {              // two live rows per trip: their loads travel together
-                const int ja = __ffs(rows) - 1;
-                rows &= rows - 1;
-                const bool two = rows != 0;
-                const int jb = two ? __ffs(rows) - 1 : ja;
-                rows &= rows - 1;
-                const int ia = td_row_of(cls, ja) * 32 + lane, ib = td_row_of(cls, jb) * 32 + lane;
-                float4 ea = E4[ia], wa = W4[ia], eb = E4[ib], wb = W4[ib];
-                ea = fma4(lam, ea, mul4(__shfl_sync(kFull, x0, ja), gh));
-                wa = fma4(c, ea, wa);
-                E4[ia] = ea;
-                W4[ia] = wa;
-                z0 = fma4(__shfl_sync(kFull, x1, ja), wa, z0);
-                z1 = fma4(__shfl_sync(kFull, x2, ja), wa, z1);
-                if (two) {
-                    eb = fma4(lam, eb, mul4(__shfl_sync(kFull, x0, jb), gh));
-                    wb = fma4(c, eb, wb);
-                    E4[ib] = eb;
-                    W4[ib] = wb;
-                    z0 = fma4(__shfl_sync(kFull, x1, jb), wb, z0);
-                    z1 = fma4(__shfl_sync(kFull, x2, jb), wb, z1);
-                }
-            }
+            row_pass(liveA, idxA, xA0, xA1, xA2, lam, c, gh, z0, z1);
+            row_pass(liveB, idxB, xB0, xB1, xB2, lam, c, gh, z0, z1);
             if (owner) {                                     // fc1.bias, fc2.weight: one thread per four units
                 eb1.x = __fadd_rn(__fmul_rn(lam, eb1.x), gh.x); eb1.y = __fadd_rn(__fmul_rn(lam, eb1.y), gh.y);
                 eb1.z = __fadd_rn(__fmul_rn(lam, eb1.z), gh.z); eb1.w = __fadd_rn(__fmul_rn(lam, eb1.w), gh.w);
@@ -475,39 +506,42 @@ __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams
         }
         {
             float4 *acc = reinterpret_cast<float4 *>(mine);
-            uint32_t touched = __ballot_sync(kFull, last >= 0);
-            if (p.final_weights) touched = cls < 6 ? 0x1FFFFFFu : 0xFFFFFFu;
-            while (touched) {                                // four rows per trip: their global loads travel together
-                int idx[4], from[4], f[4];
-                bool ok[4];
-                float4 e[4], w[4], o[4], a[4];
+            for (int pass = 0; pass < 2; pass++) {
+                const int last = pass ? lastB : lastA, idx_lane = pass ? idxB : idxA, row_lane = pass ? meB.row : meA.row;
+                uint32_t touched = __ballot_sync(kFull, last >= 0);
+                if (p.final_weights) touched = __ballot_sync(kFull, row_lane >= 0);
+                while (touched) {                            // two rows per trip: their global loads travel together
+                    int idx[2], from[2], f[2];
+                    bool ok[2];
+                    float4 e[2], w[2], o[2], a[2];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    ok[i] = touched != 0;
-                    const int j = ok[i] ? __ffs(touched) - 1 : 0;
-                    touched &= touched - 1;
-                    f[i] = td_row_of(cls, j);
-                    idx[i] = f[i] * 32 + lane;
-                    from[i] = __shfl_sync(kFull, last, j) + 1;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (ok[i]) { e[i] = E4[idx[i]]; w[i] = W4[idx[i]]; o[i] = wt4[idx[i]]; a[i] = acc[idx[i]]; }
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (!ok[i]) continue;
-                    if (from[i] > 0 && from[i] <= T - 1) {
-                        td_replay_row(e[i], w[i], from[i], T - 1, chist, lam);
-                        lazy += (unsigned)(T - from[i]);
+                    for (int i = 0; i < 2; i++) {
+                        ok[i] = touched != 0;
+                        const int j = ok[i] ? __ffs(touched) - 1 : 0;
+                        touched &= touched - 1;
+                        f[i] = __shfl_sync(kFull, row_lane, j);
+                        idx[i] = __shfl_sync(kFull, idx_lane, j) + lane;
+                        from[i] = __shfl_sync(kFull, last, j) + 1;
                     }
-                    if (p.final_weights) {
-                        p.final_weights[(col + 0) * kFeatures + f[i]] = w[i].x; p.final_weights[(col + 1) * kFeatures + f[i]] = w[i].y;
-                        p.final_weights[(col + 2) * kFeatures + f[i]] = w[i].z; p.final_weights[(col + 3) * kFeatures + f[i]] = w[i].w;
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+                        if (ok[i]) { e[i] = E4[idx[i]]; w[i] = W4[idx[i]]; o[i] = wt4[idx[i]]; a[i] = acc[idx[i]]; }
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        if (!ok[i]) continue;
+                        if (from[i] > 0 && from[i] <= T - 1) {
+                            td_replay_row(e[i], w[i], from[i], T - 1, chist, lam);
+                            lazy += (unsigned)(T - from[i]);
+                        }
+                        if (p.final_weights) {
+                            p.final_weights[(col + 0) * kFeatures + f[i]] = w[i].x; p.final_weights[(col + 1) * kFeatures + f[i]] = w[i].y;
+                            p.final_weights[(col + 2) * kFeatures + f[i]] = w[i].z; p.final_weights[(col + 3) * kFeatures + f[i]] = w[i].w;
+                        }
+                        a[i].x += w[i].x - o[i].x; a[i].y += w[i].y - o[i].y; a[i].z += w[i].z - o[i].z; a[i].w += w[i].w - o[i].w;
+                        acc[idx[i]] = a[i];
+                        W4[idx[i]] = o[i];
+                        E4[idx[i]] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    a[i].x += w[i].x - o[i].x; a[i].y += w[i].y - o[i].y; a[i].z += w[i].z - o[i].z; a[i].w += w[i].w - o[i].w;
-                    acc[idx[i]] = a[i];
-                    W4[idx[i]] = o[i];
-                    E4[idx[i]] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             if (owner)
@@ -521,8 +555,8 @@ __global__ void __launch_bounds__(kTdThreads, kTdCtasPerSm) k_td_replay(TdParams
         games++;
         TD_MARK(7);
     }
-    if (lane == 0) atomicAdd(p.stats + 8, rows_live);                         // row updates of the step passes, all eight classes
-    if (lane == 0) atomicAdd(p.stats + 7, lazy);                              // row-steps replayed lazily, all eight classes
+    if (lane == 0) atomicAdd(p.stats + 8, rows_live);                         // row updates of the step passes, all four classes
+    if (lane == 0) atomicAdd(p.stats + 7, lazy);                              // row-steps replayed lazily, all four classes
     if (tid == 0) {
         atomicAdd(p.stats + 3, games);
         atomicAdd(p.stats + 6, steps);

@@ -32,7 +32,7 @@ for _ in range(reps):
     ms = eng.last_kernel_ms()
     best = ms if best is None else min(best, ms)
 print(f"td_replay {os.environ.get('BGX_TD_DENSE') and 'dense' or 'sparse'}: {best:.2f} ms, {td['td_steps'] / best / 1e3:.1f} M steps/s, "
-      f"lazy row-steps per step {td['tree_edges'] / max(td['td_steps'], 1):.1f}, games {td['games_finished']}, sq {td['td_sq_error']:.6g}, "
+      f"lazy row-steps per step {td['td_lazy_row_steps'] / max(td['td_steps'], 1):.1f}, games {td['games_finished']}, sq {td['td_sq_error']:.6g}, "
       f"|delta| {float(delta.abs().sum()):.6g}")
 if os.environ.get("BGX_TD_PROFILE"):
     eng.td_profile(True)
