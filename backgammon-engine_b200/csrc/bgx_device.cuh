@@ -69,7 +69,15 @@ struct Mover {
     // legal origins of the mover on state v for one die (bgx_core.h legal_origins) from two ballots
     __device__ __forceinline__ uint32_t legal_here(int v, int die) const
     {
+        uint32_t blots;
+        return legal_and_blots<false>(v, die, blots);
+    }
+    // ... and, on request, the enemy blots of v (one bit per LANE: landing there is a hit), from a third ballot
+    template <bool kBlots>
+    __device__ __forceinline__ uint32_t legal_and_blots(int v, int die, uint32_t &blots) const
+    {
         const int rel = lane < 24 ? v * unit : v;                         // mover-relative count; bar/off lanes as they are
+        if (kBlots) blots = __ballot_sync(kFull, rel == -1);              // (bar / off lanes hold counts >= 0)
         const uint32_t own = __ballot_sync(kFull, rel > 0);
         const uint32_t blk = __ballot_sync(kFull, rel < -1) & 0xFFFFFFu;  // points the mover cannot land on
         const uint32_t occ = (own & 0xFFFFFFu) << 1, wall = blk << 1;

@@ -146,83 +146,88 @@ struct PlyEvaluator {
 // the tag and the ply generation, so the cache can only lose time, never exactness.
 template <int kSets>
 struct PlyCache {
-    uint8_t *slots;
-    uint32_t gen;        // 1..255, bumped per ply; stale entries are the preferred victims
+    uint8_t *col;        // this lane's byte column of the cache (slots + lane)
+    uint32_t meta;       // this lane's byte of a tag-0 entry above the state bytes: lane 29 the ply generation (1..255, bumped per
+                         // ply; stale entries are the preferred victims), every other lane 0 (lanes 28..31 of a position hold 0)
     uint32_t kmul;       // this lane's hash multiplier
 
     struct Probe {
         uint32_t off;    // byte offset of the set
-        uint32_t m0, m1; // per-lane equality masks of way 0 / way 1
+        uint32_t m0, m1; // per-lane equality masks of way 0 / way 1 (lanes 30, 31 count as equal)
         uint32_t h, got0, got1;
         __device__ __forceinline__ bool hit() const { return m0 == kFull || m1 == kFull; }
     };
 
+    __device__ __forceinline__ void clear(int lane) const
+    {
+        uint32_t *w = reinterpret_cast<uint32_t *>(col - lane);
+        for (int i = lane; i < kSets * 2 * kPlyEntryBytes / 4; i += 32) w[i] = 0;
+    }
     __device__ __forceinline__ void reset(uint8_t *p, int lane)
     {
-        slots = p;
-        gen = 0;
+        col = p + lane;
+        meta = 0;
         kmul = (0x9E3779B1u * (uint32_t)(2 * lane + 1)) ^ (0x85EBCA77u >> (lane & 7));
-        uint32_t *w = reinterpret_cast<uint32_t *>(p);
-        for (int i = lane; i < kSets * 2 * kPlyEntryBytes / 4; i += 32) w[i] = 0;
+        clear(lane);
     }
     __device__ __forceinline__ void next_ply(int lane)
     {
-        gen = (gen + 1) & 0xFFu;
+        uint32_t gen = (__shfl_sync(kFull, meta, 29) + 1) & 0xFFu;
         if (gen == 0) {
-            uint32_t *w = reinterpret_cast<uint32_t *>(slots);
-            for (int i = lane; i < kSets * 2 * kPlyEntryBytes / 4; i += 32) w[i] = 0;
+            clear(lane);
             gen = 1;
             __syncwarp();
         }
+        meta = lane == 29 ? gen : 0u;
     }
-    // what this lane's byte of a matching entry holds (lanes 30, 31 match anything)
-    __device__ __forceinline__ uint32_t byte_of(int v, int tag, int lane) const
+    // what this lane's byte of a matching entry holds: a state byte, the node tag (lane 28), the generation (lane 29)
+    template <int kTag>
+    __device__ __forceinline__ uint32_t byte_of(int v, int lane) const
     {
-        const uint32_t meta = lane == 28 ? (uint32_t)tag : gen;
-        return lane < 28 ? ((uint32_t)v & 0xFFu) : meta;
+        uint32_t b = ((uint32_t)v & 0xFFu) | meta;
+        if (kTag != 0) b |= lane == 28 ? (uint32_t)kTag : 0u;
+        return b;
     }
-    __device__ __forceinline__ Probe probe(int v, int tag, int lane) const
+    template <int kTag>
+    __device__ __forceinline__ Probe probe(int v, int lane) const
     {
         Probe p;
-        uint32_t h = __reduce_add_sync(kFull, (uint32_t)(v + 16) * kmul) + (uint32_t)tag * 0x9E3779B1u;
+        uint32_t h = __reduce_add_sync(kFull, (uint32_t)v * kmul) + (uint32_t)kTag * 0x9E3779B1u;
         h ^= h >> 15;
         p.h = h;
         p.off = (((h & 0xFFFFu) * (uint32_t)kSets) >> 16) * (2 * kPlyEntryBytes);
-        const uint8_t *e = slots + p.off + lane;
+        const uint8_t *e = col + p.off;
         p.got0 = e[0];
         p.got1 = e[kPlyEntryBytes];
-        const uint32_t mine = byte_of(v, tag, lane);
-        p.m0 = __ballot_sync(kFull, lane >= 30 || p.got0 == mine);
-        p.m1 = __ballot_sync(kFull, lane >= 30 || p.got1 == mine);
+        const uint32_t mine = byte_of<kTag>(v, lane);
+        p.m0 = __ballot_sync(kFull, p.got0 == mine) | 0xC0000000u;
+        p.m1 = __ballot_sync(kFull, p.got1 == mine) | 0xC0000000u;
         return p;
     }
-    // victim: the matching way if there is one, else a way left over from an earlier ply, else pseudo-random
-    __device__ __forceinline__ void write(const Probe &p, int v, int tag, int count, int lane) const
+    // after a miss.  Victim: a way left over from an earlier ply (bit 29 of its mask: the generation differs), else pseudo-random
+    template <int kTag>
+    __device__ __forceinline__ void write(const Probe &p, int v, int count, int lane) const
     {
-        const int way = p.m0 == kFull ? 0 : p.m1 == kFull ? 1 : !((p.m0 >> 29) & 1u) ? 0 : !((p.m1 >> 29) & 1u) ? 1 : (int)((p.h >> 20) & 1u);
-        const uint32_t mine = lane == 30 ? (uint32_t)count : byte_of(v, tag, lane);
-        slots[p.off + way * kPlyEntryBytes + lane] = (uint8_t)mine;
-    }
-    // scored-afterstate set (tag 0): true if this exact state was scored earlier in this ply
-    __device__ __forceinline__ bool seen_or_insert(int v, int lane) const
-    {
-        const Probe p = probe(v, 0, lane);
-        if (p.hit()) return true;
-        write(p, v, 0, 0, lane);
-        return false;
+        const uint32_t way = (p.m0 >> 29) & (~(p.m1 >> 29) | (p.h >> 20)) & 1u;
+        uint32_t mine = byte_of<kTag>(v, lane);
+        if (kTag != 0) mine |= lane == 30 ? (uint32_t)count : 0u;
+        col[p.off + way * kPlyEntryBytes] = (uint8_t)mine;
     }
     // memo of interior nodes (tag = depth): sub-tree sequence count (<= 225), or -1
-    __device__ __forceinline__ int lookup(int v, int tag, int lane) const
+    template <int kTag>
+    __device__ __forceinline__ int lookup(int v, int lane) const
     {
-        const Probe p = probe(v, tag, lane);
+        const Probe p = probe<kTag>(v, lane);
         const int cnt = (int)__shfl_sync(kFull, p.m0 == kFull ? p.got0 : p.got1, 30);
         return p.hit() ? cnt : -1;
     }
-    __device__ __forceinline__ void store(int v, int tag, int count, int lane) const
+    // (the node cannot be in the cache: its lookup missed, and the walk below it stored deeper tags only)
+    template <int kTag>
+    __device__ __forceinline__ void store(int v, int count, int lane) const
     {
         if (count > 255) return;                      // cannot happen (<= 15 x 15 sequences below depth 2); never mis-count
-        const Probe p = probe(v, tag, lane);
-        write(p, v, tag, count, lane);
+        const Probe p = probe<kTag>(v, lane);
+        if (!p.hit()) write<kTag>(p, v, count, lane);
     }
 };
 
@@ -231,13 +236,13 @@ struct PlyCache {
 // depend on how it is computed - so the fully inlined walk carries the leaf code only at its last level
 // (the kernel's code has to stay close to the 32 KB instruction cache).  Returns NaN if scored before.
 template <int kSets>
-__device__ __noinline__ float score_early_leaf(uint8_t *slots, uint32_t gen, uint32_t kmul, const int4 *T4, int v, int lane, int player)
+__device__ __noinline__ float score_early_leaf(uint8_t *col, uint32_t meta, uint32_t kmul, const int4 *T4, int v, int lane, int player)
 {
     PlyCache<kSets> cache;
-    cache.slots = slots; cache.gen = gen; cache.kmul = kmul;
-    const typename PlyCache<kSets>::Probe pr = cache.probe(v, 0, lane);
+    cache.col = col; cache.meta = meta; cache.kmul = kmul;
+    const typename PlyCache<kSets>::Probe pr = cache.template probe<0>(v, lane);
     if (pr.hit()) return __int_as_float(0x7fc00000);
-    cache.write(pr, v, 0, 0, lane);
+    cache.template write<0>(pr, v, 0, lane);
     PlyEvaluator e;
     e.T4 = T4;
     return e.finish(e.preactivation(v, lane, player), lane);
@@ -280,11 +285,29 @@ struct PlyWalk : Mover {
         n_seq = n_scored = n_visited = 0;
     }
 
-    // pre-activation of the child reached from (vpar, zpar) by o -> d: 2 rows, 4 after a hit
-    __device__ __forceinline__ int4 child_z(const int4 &zpar, int vpar, int o, int d, int dval) const
+    // the lanes a move touches: origin code o with the die of this level -> (origin lane, landing lane); the bar is lane
+    // 24 + player, a checker borne off lands on lane 26 + player
+    __device__ __forceinline__ void lanes_of(int o, int die, int &sl, int &dl) const
     {
-        const int src = src_lane(o), dst = dst_lane(d);
-        const int sval = __shfl_sync(kFull, vpar, src);
+        sl = o == (player ? 25 : 0) ? 24 + player : o - 1;
+        const int d = o + die * unit_of_points();            // destination code; <= 0 or >= 25: borne off (game.cpp:89-97)
+        dl = (unsigned)(d - 1) > 23u ? 26 + player : d - 1;
+    }
+
+    // the child state (game.cpp:624-659) when the node's blots are known: hit = the landing point holds one enemy checker
+    __device__ __forceinline__ int apply_known(int v, int sl, int dl, uint32_t blots) const
+    {
+        const uint32_t hit = (blots >> dl) & 1u;             // (blots has no bit above 23)
+        int t = lane == dl ? unit << hit : 0;                // the checker lands, a blot is replaced
+        t -= lane == sl ? unit : 0;
+        t += (lane == 25 - player ? 1 : 0) & (int)hit;       // ... and goes to the enemy's bar
+        return v + t;
+    }
+
+    // pre-activation of the child reached from (vpar, zpar) by the move sl -> dl: 2 rows, 4 after a hit
+    __device__ __forceinline__ int4 child_z(const int4 &zpar, int vpar, int src, int dst) const
+    {
+        const int sval = __shfl_sync(kFull, vpar, src), dval = __shfl_sync(kFull, vpar, dst);
         const int4 *T4 = ev.T4 + lane;
         int4 z = zpar;
         const int n = sval < 0 ? -sval : sval;
@@ -303,13 +326,13 @@ struct PlyWalk : Mover {
 
     // a legal turn sequence ends on v (reference order); score it unless this exact state was scored before
     template <int D>
-    __device__ __forceinline__ void leaf(int v, const int4 &zpar, int vpar, int o, int d, int dval, uint32_t path)
+    __device__ __forceinline__ void leaf(int v, const int4 &zpar, int vpar, int sl, int dl, uint32_t path)
     {
         n_seq++;
-        const typename PlyCache<kSets>::Probe pr = cache.probe(v, 0, lane);
+        const typename PlyCache<kSets>::Probe pr = cache.template probe<0>(v, lane);
         if (pr.hit()) return;
-        cache.write(pr, v, 0, 0, lane);
-        const int4 z = D == 0 ? zroot : child_z(zpar, vpar, o, d, dval);
+        cache.template write<0>(pr, v, 0, lane);
+        const int4 z = D == 0 ? zroot : child_z(zpar, vpar, sl, dl);
         const float val = ev.finish(z, lane);
         n_scored++;
         const float key = player ? -val : val;
@@ -319,7 +342,7 @@ struct PlyWalk : Mover {
     __device__ __forceinline__ void early_leaf(int v, uint32_t path_and_len)
     {
         n_seq++;
-        const float val = score_early_leaf<kSets>(cache.slots, cache.gen, cache.kmul, ev.T4, v, lane, player);
+        const float val = score_early_leaf<kSets>(cache.col, cache.meta, cache.kmul, ev.T4, v, lane, player);
         if (val != val) return;
         n_scored++;
         const float key = player ? -val : val;
@@ -333,34 +356,36 @@ struct PlyWalk : Mover {
     // node, in the second pass of a non-double when o' is a root origin of the first pass.  The reference visits that twin
     // EARLIER (ascending origins; first pass first), it has the same value, and the strict first-index arg-best can never
     // prefer the later copy: such leaves are counted, not walked.  `legal_par` = all origins of the parent node.
+    // (v, path) = the node; (vpar, zpar) its parent, sl -> dl the lanes of the move that led here (path holds its origin code)
     template <int D>
-    __device__ __forceinline__ void visit(int v, const int4 &zpar, int vpar, int o, int d, int dval, uint32_t path, uint32_t legal_par = 0)
+    __device__ __forceinline__ void visit(int v, const int4 &zpar, int vpar, int sl, int dl, uint32_t path, uint32_t legal_par = 0)
     {
         constexpr int kMax = 4;
-        uint32_t legal = 0;
+        uint32_t legal = 0, blots = 0;
         if constexpr (D < kMax) {
             if (D == 1 && nd) legal = 1u;                    // a non-double pass enters at level 2: level 1 hands the root through
-            else legal = legal_here(v, (D & 1) ? dieB : dieA);
+            else legal = legal_and_blots<true>(v, (D & 1) ? dieB : dieA, blots);
             if (D == 0) legal &= root_only;
         }
         uint32_t twins = 0;
         if constexpr (D == kMax - 1) {
             const int die = (D & 1) ? dieB : dieA;
+            const int o = (int)((path >> (5 * (D - 1))) & 31u);
             twins = legal & (nd ? twin_root : legal_par & ((1u << o) - 1u));
             twins &= player ? ~((2u << die) - 1u) : (1u << (25 - die)) - 1u;      // the last move stays on the board ...
-            if (d == (player ? 0 : 25)) twins = 0;                               // ... and so did the one before it
+            if (dl >= 24) twins = 0;                                             // ... and so did the one before it
         }
         if (legal == 0) {
             // a node without a move ends the sequence (game.cpp:117-121, 148-151); the root of a
             // non-double pass emits nothing
-            if constexpr (D == kMax) leaf<D>(v, zpar, vpar, o, d, dval, path);
+            if constexpr (D == kMax) leaf<D>(v, zpar, vpar, sl, dl, path);
             else if (!(D == 2 && nd)) early_leaf(v, path | ((uint32_t)D << 20));
             return;
         }
         if constexpr (D < kMax) {
             if constexpr (D >= 2) {                          // doubles: same position, same dice left: seen before?
                 if (!nd) {
-                    const int below = cache.lookup(v, D, lane);
+                    const int below = cache.template lookup<D>(v, lane);
                     if (below >= 0) { n_seq += below; return; }
                 }
             }
@@ -369,21 +394,24 @@ struct PlyWalk : Mover {
             n_seq += __popc(twins);                          // counted, not walked (the count below stays path-independent)
             legal &= ~twins;
             if (D == kMax - 1 && legal == 0) {               // every sequence below is an earlier one's twin
-                if constexpr (D >= 2) { if (!nd) cache.store(v, D, n_seq - entered, lane); }
+                if constexpr (D >= 2) { if (!nd) cache.template store<D>(v, n_seq - entered, lane); }
                 return;
             }
             int4 z = zroot;                                  // the root of the turn: of a double at depth 0, of a non-double pass at 2
-            if (D != 0 && !(D <= 2 && nd)) z = child_z(zpar, vpar, o, d, dval);
+            if (D != 0 && !(D <= 2 && nd)) z = child_z(zpar, vpar, sl, dl);
             const int die = (D & 1) ? dieB : dieA;
             do {
                 const int oc = lowest_bit(legal);
                 legal &= legal - 1;
-                const int dc = destination(player, oc, die);
-                int dv = 0, child = v;
-                if (!(D == 1 && nd)) { child = apply(v, oc, dc, dv); n_visited++; }
-                visit<D + 1>(child, z, v, oc, dc, dv, path | ((uint32_t)oc << (5 * D)), legal_all);
+                int sc = 0, dc = 0, child = v;
+                if (!(D == 1 && nd)) {
+                    lanes_of(oc, die, sc, dc);
+                    child = apply_known(v, sc, dc, blots);
+                    n_visited++;
+                }
+                visit<D + 1>(child, z, v, sc, dc, path | ((uint32_t)oc << (5 * D)), legal_all);
             } while (legal);
-            if constexpr (D >= 2) { if (!nd) cache.store(v, D, n_seq - entered, lane); }
+            if constexpr (D >= 2) { if (!nd) cache.template store<D>(v, n_seq - entered, lane); }
         }
     }
 };
@@ -505,7 +533,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
         }
     }
     for (;;) {
-        int child = root, oc = 0, dc = 0, dv = 0;
+        int child = root, oc = 0, sc = 0, dc = 0;
         if (dbl) {
             uint32_t bit = 0;
             if (shared) {                                                // pop the lowest origin still there
@@ -524,8 +552,9 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
             }
             if (bit == 0) break;
             oc = lowest_bit(bit);
-            dc = destination(player, oc, d1);
-            child = w.apply(root, oc, dc, dv);
+            int dv;
+            child = w.apply(root, oc, destination(player, oc, d1), dv);
+            w.lanes_of(oc, d1, sc, dc);
             w.n_visited++;
         } else {                                                         // game.cpp:143-188: d1 first, then d2 first
             if (pass == 2) break;
@@ -534,7 +563,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
             if (pass) { key1 = w.best_key; w.twin_root = w.legal_here(root, d1); }
             pass++;
         }
-        w.template visit<1>(child, w.zroot, root, oc, dc, dv, (uint32_t)oc);
+        w.template visit<1>(child, w.zroot, root, sc, dc, (uint32_t)oc);
     }
     if (dbl) {
         if (shared && lane == 0) atomicAnd(share->urgent, ~share->my_bit);
