@@ -32,6 +32,12 @@ constexpr int kRowConst = kFeatures + 32;                         // every float
 // status byte (record byte 31) of a self-play slot
 enum { kRunning = 0, kP1Won = 1, kP2Won = 2, kTruncated = 3 };
 
+// The warp's index in its CTA as a value ptxas can PROVE warp-uniform (a shuffle from a fixed lane).  threadIdx.x >> 5 is
+// uniform too, but not provably: everything loaded through it (a warp's seat, its cache, its queue position) then counts as
+// divergent, every loop over a ballot mask derived from it as a divergent loop, and every *_sync intrinsic inside gets a
+// BRA.DIV guard with its reconvergence code (47 sites in k_selfplay, ~10 % of its executed instructions).
+__device__ __forceinline__ int warp_index() { return __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0); }
+
 // ------------------------------------------------------------------------------------
 // lane-distributed state
 // ------------------------------------------------------------------------------------

@@ -167,7 +167,7 @@ k_enumerate_summary(const int8_t *__restrict__ queries, long long n, int32_t *__
                     uint32_t *__restrict__ tables, uint32_t *__restrict__ gens, unsigned long long *counter)
 {
     const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_index();
     uint32_t *table = tables + (size_t)gwarp * (kUniqBytesPerWarp / 4);
     uint32_t gen = gens[gwarp];                     // the table outlives the launch, so does its generation
     for (;;) {
@@ -216,7 +216,7 @@ constexpr int kScanThreads = 256, kScanPerThread = 8, kScanTile = kScanThreads *
 
 __device__ __forceinline__ long long block_exclusive_scan(long long x, long long *warp_sums, long long &block_total)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index(), n_warps = blockDim.x >> 5;
     long long inc = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kEncWarps * 32)
 k_encode(const int8_t *__restrict__ records, long long n, float *__restrict__ X)
 {
     extern __shared__ __align__(128) float enc_tiles[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index();
     const long long n_tiles = (n + kEncRows - 1) / kEncRows;
     int buf = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, buf ^= 1) {
@@ -412,7 +412,7 @@ k_evaluate(const int8_t *__restrict__ records, long long n, float *__restrict__ 
     PlyEvaluator ev;
     ev.T4 = reinterpret_cast<const int4 *>(sT);
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += warps) {
+    for (long long q = (long long)blockIdx.x * (blockDim.x >> 5) + warp_index(); q < n; q += warps) {
         const int b = load_record_byte(records + q * 32, lane);
         const int v = lane < 28 ? b : 0;
         const float val = ev.finish(ev.preactivation(v, lane, __shfl_sync(kFull, b, 28) ? 1 : 0), lane);
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(256) k_select_order(const int8_t *__restrict__
 {
     __shared__ uint32_t hist[kOrderBuckets], base[kOrderBuckets];
     __shared__ uint8_t key[kOrderCtaQueries];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index();
     const long long q0 = (long long)blockIdx.x * kOrderCtaQueries;
     if (threadIdx.x < kOrderBuckets) hist[threadIdx.x] = 0;
     __syncthreads();
@@ -609,7 +609,7 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const PlySmem<kWarps, kSets> sm(smem);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index();
     PlyCache<kSets> cache;
     cache.reset(sm.scratch[warp].cache, lane);
     sm.init_share();
@@ -654,6 +654,7 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
             if (q >= n) {                                   // queue empty: help the owners of big doubles
                 helping = true;
                 if (lane == 0) atomicSub(&sm.share->active, 1);
+                __syncwarp();                               // reconverged before the back-edge (see k_selfplay)
                 continue;
             }
             if (region) {                                   // position in the sorted queue -> query
@@ -670,6 +671,8 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
                 u = r.x[1];
             }
         }
+        d1 = __shfl_sync(kFull, d1, 0); d2 = __shfl_sync(kFull, d2, 0);        // provably warp-uniform (see k_selfplay)
+        player = __shfl_sync(kFull, player, 0); only = __shfl_sync(kFull, only, 0);
         const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, player, d1, d2, ev, cache, explore, u, only ? only : kFull,
                                                           only ? nullptr : &mine);
         if (only) deliver_child<kWarps>(sm.share, cta_results, vw, only, c, lane);
@@ -677,6 +680,7 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
             store_choice(out, q, c, lane, player);
             if (adv.next) store_advanced(adv, q, n, c.v, lane, player);
         }
+        __syncwarp();                                       // reconverged before the back-edge (see k_selfplay)
     }
 }
 
@@ -687,7 +691,7 @@ __global__ void k_advance(const int8_t *chosen, int8_t *next, long long n, uint3
 {
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     const int lane = threadIdx.x & 31;
-    for (long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += warps) {
+    for (long long q = (long long)blockIdx.x * (blockDim.x >> 5) + warp_index(); q < n; q += warps) {
         const int b = load_record_byte(chosen + q * 32, lane);
         const int off1 = __shfl_sync(kFull, b, 26), off2 = __shfl_sync(kFull, b, 27), mover = __shfl_sync(kFull, b, 28) ? 1 : 0;
         const int win = off1 == 15 ? 0 : (off2 == 15 ? 1 : -1);            // game.cpp:388-407
@@ -722,7 +726,7 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const PlySmem<kWarps, kSets> sm(smem);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index();
     PlyCache<kSets> cache;
     cache.reset(sm.scratch[warp].cache, lane);
     sm.init_share();
@@ -759,6 +763,7 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
                 if (slot >= p.n_slots) {
                     helping = true;
                     if (lane == 0) atomicSub(&sm.share->active, 1);
+                    __syncwarp();                                // (see the end of the loop body)
                     continue;
                 }
                 const int b = load_record_byte(p.slots + slot * 32, lane);
@@ -803,6 +808,11 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
             }
         }
         if (only || seated) {
+            // what the walk branches on, as values ptxas can PROVE warp-uniform (shuffles from a fixed lane): with dice or a mover
+            // that merely happen to be uniform every loop of the walk counts as divergent and each *_sync intrinsic in it is
+            // guarded by BRA.DIV + reconvergence code
+            d1 = __shfl_sync(kFull, d1, 0); d2 = __shfl_sync(kFull, d2, 0);
+            mover = __shfl_sync(kFull, mover, 0); only = __shfl_sync(kFull, only, 0);
             const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, mover, d1, d2, ev, cache, explore, u, only ? only : kFull,
                                                               only ? nullptr : &mine);                  // model.py:180-222
             if (only) {
@@ -859,6 +869,10 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
                 p.game_id[slot] = (long long)S.gid;
             }
         }
+        // Reconverge before the back-edge: a lane-0 block that ends an iteration lets the other lanes reach the loop header
+        // first, ptxas then treats the WHOLE loop body as possibly diverged and guards every *_sync intrinsic in it - the
+        // walk included - with BRA.DIV + reconvergence code (47 sites, ~10 % of the executed instructions).
+        __syncwarp();
     }
     // the last warp to leave flushes the CTA's statistics
     __syncwarp();
@@ -875,7 +889,7 @@ __global__ void k_selfplay_reset(int8_t *slots, int32_t *ply, long long *game_id
 {
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     const int lane = threadIdx.x & 31;
-    for (long long s = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_slots; s += warps) {
+    for (long long s = (long long)blockIdx.x * (blockDim.x >> 5) + warp_index(); s < n_slots; s += warps) {
         const unsigned long long gid = advance ? (unsigned long long)(game_id[s] + id_stride) : (unsigned long long)(first_id + s);
         const int player = first_mover_of(seed_lo, seed_hi, gid, first_mover);
         const int out = lane < 28 ? start_value(lane) : (lane == 28 ? player : 0);
@@ -891,7 +905,7 @@ __global__ void k_traj_sample(const int8_t *__restrict__ traj, const int32_t *__
 {
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5), total = n_slots * per_game;
     const int lane = threadIdx.x & 31;
-    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < total; i += warps) {
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp_index(); i < total; i += warps) {
         const long long slot = i / per_game;
         const int j = (int)(i % per_game);
         int T = ply[slot];

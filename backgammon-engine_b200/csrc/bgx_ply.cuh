@@ -127,7 +127,7 @@ struct PlyEvaluator {
     // function of the position).  Resolution 2^-30 of sum |w2|: ~1e-7 of V in the worst case.
     __device__ __forceinline__ float finish(const int4 &zi, int lane) const
     {
-        const int4 wi = T4[kRowW2 * 32 + lane], ci = T4[kRowConst * 32 + lane];
+        const int4 wi = T4[kRowW2 * 32 + lane], ci = T4[kRowConst * 32];       // (one address for the warp: the value is provably uniform)
         const float c = __int_as_float(ci.y), b2 = __int_as_float(ci.z), Y = __int_as_float(ci.w);
         const float y = __int_as_float(wi.x) * sigmoid_exp2((float)zi.x * c) + __int_as_float(wi.y) * sigmoid_exp2((float)zi.y * c) +
                         __int_as_float(wi.z) * sigmoid_exp2((float)zi.z * c) + __int_as_float(wi.w) * sigmoid_exp2((float)zi.w * c);
@@ -342,7 +342,8 @@ struct PlyWalk : Mover {
     __device__ __forceinline__ void early_leaf(int v, uint32_t path_and_len)
     {
         n_seq++;
-        const float val = score_early_leaf<kSets>(cache.col, cache.meta, cache.kmul, ev.T4, v, lane, player);
+        // (a call's result counts as divergent: the shuffle makes the branches below uniform ones, see k_selfplay)
+        const float val = __shfl_sync(kFull, score_early_leaf<kSets>(cache.col, cache.meta, cache.kmul, ev.T4, v, lane, player), 0);
         if (val != val) return;
         n_scored++;
         const float key = player ? -val : val;
@@ -529,6 +530,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
                         (kids >= share->urgent_min && *(volatile const unsigned long long *)share->queue >= share->urgent_from))
                         atomicOr(share->urgent, share->my_bit);
                 }
+                __syncwarp();                                            // reconverged before the loop below (see k_selfplay)
             }
         }
     }
@@ -537,15 +539,17 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
         if (dbl) {
             uint32_t bit = 0;
             if (shared) {                                                // pop the lowest origin still there
-                if (lane == 0) {
-                    for (;;) {
-                        const uint32_t old = *(volatile uint32_t *)&slot->legal0;
-                        if (old == 0) break;
-                        const uint32_t low = old & (0u - old);
-                        if (atomicAnd(&slot->legal0, ~low) & low) { bit = low; break; }
-                    }
+                // (the whole warp runs the retry loop and every exit is decided by a broadcast value: a loop inside a
+                // lane-0 block that an atomic's result ends makes ptxas treat all that follows as diverged, see k_selfplay)
+                for (;;) {
+                    const uint32_t old = *(volatile uint32_t *)&slot->legal0;
+                    if (old == 0) break;
+                    const uint32_t low = old & (0u - old);
+                    uint32_t was = 0;
+                    if (lane == 0) was = atomicAnd(&slot->legal0, ~low);
+                    was = __shfl_sync(kFull, was, 0);
+                    if (was & low) { bit = low; break; }
                 }
-                bit = __shfl_sync(kFull, bit, 0);
             } else {
                 bit = legal & (0u - legal);
                 legal &= legal - 1;
@@ -657,6 +661,7 @@ __device__ __forceinline__ void deliver_child(StealShared<kWarps> *sh, StealResu
     __threadfence_block();
     __syncwarp();
     if (lane == 0) atomicSub(&vs->pending, 1);
+    __syncwarp();                        // the caller's loop continues from here: reconverged (see k_selfplay)
 }
 
 // greedy or exploring ply; kExplore = false compiles the epsilon path out (smaller, fewer registers)
