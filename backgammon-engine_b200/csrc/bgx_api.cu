@@ -165,17 +165,17 @@ static int create_into(bgx_engine *e, int device, const cudaDeviceProp &prop)
     CU(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, kEvalSmem));
     CU(cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmem));
     e->lane_grid = e->sm_count / 2;
-    static_assert(ply_smem<16, 110>() <= 232448 && ply_smem<20, 87>() <= 232448 && ply_smem<24, 73>() <= 232448 && ply_smem<32, 54>() <= 232448,
+    static_assert(ply_smem<16, 109>() <= 232448 && ply_smem<20, 86>() <= 232448 && ply_smem<24, 72>() <= 232448 && ply_smem<32, 53>() <= 232448,
                   "fused ply kernels: shared memory per CTA");
 #define BGX_SMEM_ATTR(W, S)                                                                                                    \
     CU(cudaFuncSetAttribute(k_select<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));            \
     CU(cudaFuncSetAttribute(k_select<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));             \
     CU(cudaFuncSetAttribute(k_selfplay<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));          \
     CU(cudaFuncSetAttribute(k_selfplay<W, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ply_smem<W, S>()));
-    BGX_SMEM_ATTR(16, 110)
-    BGX_SMEM_ATTR(20, 87)
-    BGX_SMEM_ATTR(24, 73)
-    BGX_SMEM_ATTR(32, 54)
+    BGX_SMEM_ATTR(16, 109)
+    BGX_SMEM_ATTR(20, 86)
+    BGX_SMEM_ATTR(24, 72)
+    BGX_SMEM_ATTR(32, 53)
 #undef BGX_SMEM_ATTR
     CU(cudaFuncSetAttribute(k_td_replay<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
     CU(cudaFuncSetAttribute(k_td_replay<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmem));
@@ -549,10 +549,10 @@ static int launch_select(bgx_engine *e, cudaStream_t stream, unsigned long long 
     k_select<W, S, X><<<grid, W * 32, ply_smem<W, S>(), stream>>>(queries, n, epsilon, (uint32_t)seed, \
                                                                           (uint32_t)(seed >> 32), out, e->fixed, e->flat, counter, steal, tune, region, totals, adv)
     const bool ex = epsilon > 0.f;
-    if (e->select_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 110, true); else BGX_LAUNCH_SELECT(16, 110, false); }
-    else if (e->select_warps == 20) { if (ex) BGX_LAUNCH_SELECT(20, 87, true); else BGX_LAUNCH_SELECT(20, 87, false); }
-    else if (e->select_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 73, true); else BGX_LAUNCH_SELECT(24, 73, false); }
-    else { if (ex) BGX_LAUNCH_SELECT(32, 54, true); else BGX_LAUNCH_SELECT(32, 54, false); }
+    if (e->select_warps == 16) { if (ex) BGX_LAUNCH_SELECT(16, 109, true); else BGX_LAUNCH_SELECT(16, 109, false); }
+    else if (e->select_warps == 20) { if (ex) BGX_LAUNCH_SELECT(20, 86, true); else BGX_LAUNCH_SELECT(20, 86, false); }
+    else if (e->select_warps == 24) { if (ex) BGX_LAUNCH_SELECT(24, 72, true); else BGX_LAUNCH_SELECT(24, 72, false); }
+    else { if (ex) BGX_LAUNCH_SELECT(32, 53, true); else BGX_LAUNCH_SELECT(32, 53, false); }
 #undef BGX_LAUNCH_SELECT
     e->launches++;
     CU(cudaGetLastError());
@@ -855,10 +855,10 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
     tick(e);
 #define BGX_LAUNCH_SELFPLAY(W, S, X) k_selfplay<W, S, X><<<game_grid(e), W * 32, ply_smem<W, S>(), e->stream>>>(p, e->fixed, e->flat, e->steal)
     const bool ex = epsilon > 0.f;
-    if (e->selfplay_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 110, true); else BGX_LAUNCH_SELFPLAY(16, 110, false); }
-    else if (e->selfplay_warps == 20) { if (ex) BGX_LAUNCH_SELFPLAY(20, 87, true); else BGX_LAUNCH_SELFPLAY(20, 87, false); }
-    else if (e->selfplay_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 73, true); else BGX_LAUNCH_SELFPLAY(24, 73, false); }
-    else { if (ex) BGX_LAUNCH_SELFPLAY(32, 54, true); else BGX_LAUNCH_SELFPLAY(32, 54, false); }
+    if (e->selfplay_warps == 16) { if (ex) BGX_LAUNCH_SELFPLAY(16, 109, true); else BGX_LAUNCH_SELFPLAY(16, 109, false); }
+    else if (e->selfplay_warps == 20) { if (ex) BGX_LAUNCH_SELFPLAY(20, 86, true); else BGX_LAUNCH_SELFPLAY(20, 86, false); }
+    else if (e->selfplay_warps == 24) { if (ex) BGX_LAUNCH_SELFPLAY(24, 72, true); else BGX_LAUNCH_SELFPLAY(24, 72, false); }
+    else { if (ex) BGX_LAUNCH_SELFPLAY(32, 53, true); else BGX_LAUNCH_SELFPLAY(32, 53, false); }
 #undef BGX_LAUNCH_SELFPLAY
     tock(e);
     e->launches++;

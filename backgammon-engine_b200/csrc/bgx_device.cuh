@@ -22,12 +22,17 @@ constexpr int kFeatures = 198;
 constexpr int kHidden = 128;
 constexpr int kTableFloats = kFeatures * kHidden;                 // 25 344
 constexpr int kTableBytes = kTableFloats * 4;                     // 101 376
-constexpr int kFixedRows = kFeatures + 30 + 3;                    // + borne-off step rows, b1, w2, constants (bgx_ply.cuh)
-constexpr int kFixedInts = kFixedRows * kHidden;                  // 29 568
-constexpr int kFixedBytes = kFixedInts * 4;                       // 118 272
+constexpr int kFixedRows = kFeatures + 30 + 4;                    // + borne-off step rows, b1, w2, constants, lane constants (bgx_ply.cuh)
+constexpr int kFixedInts = kFixedRows * kHidden;                  // 29 696
+constexpr int kFixedBytes = kFixedInts * 4;                       // 118 784
 constexpr int kRowB1 = kFeatures + 30;                            // round(b1 S)
 constexpr int kRowW2 = kFeatures + 31;                            // w2 (fp32 bit patterns)
 constexpr int kRowConst = kFeatures + 32;                         // every float4: {S, -log2(e)/S, b2, Y}
+constexpr int kRowLane = kFeatures + 33;                          // lane l: {hash multiplier of lane l, 0, 0, 0} (PlyCache)
+
+// the ply cache's hash multiplier of a lane: odd, and not a polynomial in the lane (moving a checker by the same die from
+// different points must not shift the hash by the same amount)
+__host__ __device__ constexpr uint32_t ply_hash_multiplier(int lane) { return (0x9E3779B1u * (uint32_t)(2 * lane + 1)) ^ (0x85EBCA77u >> (lane & 7)); }
 
 // status byte (record byte 31) of a self-play slot
 enum { kRunning = 0, kP1Won = 1, kP2Won = 2, kTruncated = 3 };

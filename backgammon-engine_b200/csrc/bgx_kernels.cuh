@@ -103,9 +103,11 @@ __global__ void k_build_fixed(const float *__restrict__ flat, const float *__res
         Ti[idx] = __float2int_rn(flat[kTableFloats + j] * S);
     } else if (f == kRowW2) {
         Ti[idx] = __float_as_int(flat[kTableFloats + kHidden + j]);
-    } else {                                       // constants, the same float4 for every lane
+    } else if (f == kRowConst) {                   // constants, the same float4 for every lane
         const float c[4] = {S, -1.4426950408889634f * aux[1], flat[kTableFloats + 2 * kHidden], aux[3]};
         Ti[idx] = __float_as_int(c[j & 3]);
+    } else {                                       // what depends on the lane only: read where needed instead of held (or recomputed) in registers
+        Ti[idx] = (j & 3) == 0 ? (int32_t)ply_hash_multiplier(j >> 2) : 0;
     }
 }
 
@@ -611,7 +613,7 @@ k_select(const int8_t *__restrict__ queries, long long n, float epsilon, uint32_
     const PlySmem<kWarps, kSets> sm(smem);
     const int lane = threadIdx.x & 31, warp = warp_index();
     PlyCache<kSets> cache;
-    cache.reset(sm.scratch[warp].cache, lane);
+    cache.reset(sm.scratch[warp].cache, reinterpret_cast<const int4 *>(sm.table), lane);
     sm.init_share();
     stage_table(sm.table, Ti, sm.bar, kFixedBytes);
     PlyEvaluator ev;
@@ -728,7 +730,7 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
     const PlySmem<kWarps, kSets> sm(smem);
     const int lane = threadIdx.x & 31, warp = warp_index();
     PlyCache<kSets> cache;
-    cache.reset(sm.scratch[warp].cache, lane);
+    cache.reset(sm.scratch[warp].cache, reinterpret_cast<const int4 *>(sm.table), lane);
     sm.init_share();
     stage_table(sm.table, Ti, sm.bar, kFixedBytes);
     PlyEvaluator ev;

@@ -149,11 +149,12 @@ struct PlyCache {
     uint8_t *col;        // this lane's byte column of the cache (slots + lane)
     uint32_t meta;       // this lane's byte of a tag-0 entry above the state bytes: lane 29 the ply generation (1..255, bumped per
                          // ply; stale entries are the preferred victims), every other lane 0 (lanes 28..31 of a position hold 0)
-    uint32_t kmul;       // this lane's hash multiplier
+    const uint32_t *kmul;// this lane's hash multiplier, in the evaluator's table (row kRowLane): one LDS per probe - held in a
+                         // register the compiler recomputed it from the lane at every probe (5 ALU instructions, 3 % of the kernel)
 
     struct Probe {
         uint32_t off;    // byte offset of the set
-        uint32_t m0, m1; // per-lane equality masks of way 0 / way 1 (lanes 30, 31 count as equal)
+        uint32_t m0, m1; // per-lane equality masks of way 0 / way 1
         uint32_t h, got0, got1;
         __device__ __forceinline__ bool hit() const { return m0 == kFull || m1 == kFull; }
     };
@@ -163,11 +164,11 @@ struct PlyCache {
         uint32_t *w = reinterpret_cast<uint32_t *>(col - lane);
         for (int i = lane; i < kSets * 2 * kPlyEntryBytes / 4; i += 32) w[i] = 0;
     }
-    __device__ __forceinline__ void reset(uint8_t *p, int lane)
+    __device__ __forceinline__ void reset(uint8_t *p, const int4 *T4, int lane)
     {
         col = p + lane;
         meta = 0;
-        kmul = (0x9E3779B1u * (uint32_t)(2 * lane + 1)) ^ (0x85EBCA77u >> (lane & 7));
+        kmul = reinterpret_cast<const uint32_t *>(T4 + kRowLane * 32 + lane);
         clear(lane);
     }
     __device__ __forceinline__ void next_ply(int lane)
@@ -180,7 +181,8 @@ struct PlyCache {
         }
         meta = lane == 29 ? gen : 0u;
     }
-    // what this lane's byte of a matching entry holds: a state byte, the node tag (lane 28), the generation (lane 29)
+    // what this lane's byte of a matching entry holds: a state byte, the node tag (lane 28), the generation (lane 29), the
+    // sub-tree count of a memo entry (lane 30, not compared), 0 (lane 31)
     template <int kTag>
     __device__ __forceinline__ uint32_t byte_of(int v, int lane) const
     {
@@ -192,16 +194,17 @@ struct PlyCache {
     __device__ __forceinline__ Probe probe(int v, int lane) const
     {
         Probe p;
-        uint32_t h = __reduce_add_sync(kFull, (uint32_t)v * kmul) + (uint32_t)kTag * 0x9E3779B1u;
-        h ^= h >> 15;
+        // the high bits of a sum of products are its best-mixed ones: they pick the set, bit 20 the random victim
+        const uint32_t h = __reduce_add_sync(kFull, (uint32_t)v * *kmul) + (uint32_t)kTag * 0x9E3779B1u;
         p.h = h;
-        p.off = (((h & 0xFFFFu) * (uint32_t)kSets) >> 16) * (2 * kPlyEntryBytes);
+        p.off = __umulhi(h, (uint32_t)kSets) * (2 * kPlyEntryBytes);
         const uint8_t *e = col + p.off;
         p.got0 = e[0];
         p.got1 = e[kPlyEntryBytes];
         const uint32_t mine = byte_of<kTag>(v, lane);
-        p.m0 = __ballot_sync(kFull, p.got0 == mine) | 0xC0000000u;
-        p.m1 = __ballot_sync(kFull, p.got1 == mine) | 0xC0000000u;
+        p.m0 = __ballot_sync(kFull, p.got0 == mine);
+        p.m1 = __ballot_sync(kFull, p.got1 == mine);
+        if (kTag != 0) { p.m0 |= 0x40000000u; p.m1 |= 0x40000000u; }       // a memo entry's count is not part of the key
         return p;
     }
     // after a miss.  Victim: a way left over from an earlier ply (bit 29 of its mask: the generation differs), else pseudo-random
@@ -236,7 +239,7 @@ struct PlyCache {
 // depend on how it is computed - so the fully inlined walk carries the leaf code only at its last level
 // (the kernel's code has to stay close to the 32 KB instruction cache).  Returns NaN if scored before.
 template <int kSets>
-__device__ __noinline__ float score_early_leaf(uint8_t *col, uint32_t meta, uint32_t kmul, const int4 *T4, int v, int lane, int player)
+__device__ __noinline__ float score_early_leaf(uint8_t *col, uint32_t meta, const uint32_t *kmul, const int4 *T4, int v, int lane, int player)
 {
     PlyCache<kSets> cache;
     cache.col = col; cache.meta = meta; cache.kmul = kmul;
@@ -260,7 +263,7 @@ template <int kSets>
 struct PlyWalk : Mover {
     const PlyEvaluator &ev;
     const PlyCache<kSets> &cache;
-    int c_me;             // feature block of the mover inside a point's 8 features (0 or 4)
+    const int4 *Tme;      // this lane's column of the evaluator's table, from the mover's feature block on (child_z)
     int dieA, dieB;       // die of even / odd depths
     uint32_t root_only;   // restricts the root's origins (all ones: no restriction)
     uint32_t twin_root;   // non-doubles, second pass: the root origins of the FIRST pass' first die (0 in the first pass)
@@ -276,7 +279,7 @@ struct PlyWalk : Mover {
     __device__ __forceinline__ PlyWalk(const PlyEvaluator &e, const PlyCache<kSets> &c, int ln, int pl)
         : Mover(ln, pl), ev(e), cache(c)
     {
-        c_me = pl ? 4 : 0;
+        Tme = e.T4 + ln + (pl ? 4 * 32 : 0);
         root_only = kFull;
         twin_root = 0;
         nd = false;
@@ -304,23 +307,24 @@ struct PlyWalk : Mover {
         return v + t;
     }
 
-    // pre-activation of the child reached from (vpar, zpar) by the move sl -> dl: 2 rows, 4 after a hit
+    // pre-activation of the child reached from (vpar, zpar) by the move sl -> dl: 2 rows, 4 after a hit.  Rows are addressed from
+    // Tme = this lane's column of the table shifted to the MOVER's feature block (row 8 p + k of Tme is "k + 1 checkers of the
+    // mover on point p"); the other rows follow from the player by one multiply-add each (cheap to recompute, nothing to hold)
     __device__ __forceinline__ int4 child_z(const int4 &zpar, int vpar, int src, int dst) const
     {
         const int sval = __shfl_sync(kFull, vpar, src), dval = __shfl_sync(kFull, vpar, dst);
-        const int4 *T4 = ev.T4 + lane;
         int4 z = zpar;
         const int n = sval < 0 ? -sval : sval;
-        const int row_src = src >= 24 ? 194 + player : 8 * src + c_me + (n < 4 ? n : 4) - 1;
-        PlyEvaluator::sub(z, T4[row_src * 32]);                             // one checker less on the origin (or the bar)
+        const int row_src = src >= 24 ? 194 - 3 * player : 8 * src + (n < 4 ? n : 4) - 1;          // (194 + player) - c_me
+        PlyEvaluator::sub(z, Tme[row_src * 32]);                            // one checker less on the origin (or the bar)
         const int k = (dval < 0 ? -dval : dval) + 1;
-        int row_dst = dst >= 24 ? kFeatures + 15 * player + dval : 8 * dst + c_me + (k < 4 ? k : 4) - 1;
+        int row_dst = dst >= 24 ? kFeatures + 11 * player + dval : 8 * dst + (k < 4 ? k : 4) - 1;  // (198 + 15 player) - c_me
         if (dst < 24 && dval * unit_of_points() == -1) {                    // a hit
-            PlyEvaluator::sub(z, T4[(8 * dst + 4 - c_me) * 32]);            // the blot leaves ...
-            PlyEvaluator::add(z, T4[(195 - player) * 32]);                  // ... for the enemy's bar
-            row_dst = 8 * dst + c_me;
+            PlyEvaluator::sub(z, Tme[(8 * dst + 4 - 8 * player) * 32]);     // the blot leaves (the enemy's block: +4 / -4) ...
+            PlyEvaluator::add(z, Tme[(195 - 5 * player) * 32]);             // ... for the enemy's bar: (195 - player) - c_me
+            row_dst = 8 * dst;
         }
-        PlyEvaluator::add(z, T4[row_dst * 32]);                             // one more on the landing point (or borne off)
+        PlyEvaluator::add(z, Tme[row_dst * 32]);                            // one more on the landing point (or borne off)
         return z;
     }
 
