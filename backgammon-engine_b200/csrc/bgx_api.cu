@@ -52,6 +52,7 @@ struct bgx_engine {
     unsigned long long *stats = nullptr;     // 8 counters
     double *dstats = nullptr;                // TD: sum of squared errors
     StealResult *steal = nullptr;            // [CTA][warp][16] sub-tree results of shared doubles (bgx_ply.cuh)
+    int4 *zstash = nullptr;                  // [CTA][32 warps][32 lanes] pre-activation of a self-play warp's best afterstate (bgx_ply.cuh)
     uint32_t *uniq_tables = nullptr;
     uint32_t *uniq_gens = nullptr;           // per-warp generation of the exact-dedup tables
     int uniq_grid = 0;
@@ -75,7 +76,7 @@ struct bgx_engine {
                                              // batches are resident at once (0: one per SM); this and the next: bgx_set_option
     long long select_order_max = 1 << 21;    // launches up to this many queries get a sorted queue (64 B of scratch per query)
     int select_urgent_min = 7, select_giant_min = kGiantMinChildren, select_urgent_from_pct = 0;   // k_select help policy
-    int selfplay_warps = 24, select_warps = 24;   // warps per CTA of k_selfplay / k_select (measured best)
+    int selfplay_warps = 20, select_warps = 20;   // warps per CTA of k_selfplay / k_select (measured best: 96 registers, 86 cache sets per warp)
     // bookkeeping
     long long launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
@@ -159,6 +160,7 @@ static int create_into(bgx_engine *e, int device, const cudaDeviceProp &prop)
     CU(cudaMalloc(&e->stats, 16 * sizeof(unsigned long long)));
     CU(cudaMalloc(&e->dstats, 2 * sizeof(double)));
     CU(cudaMalloc(&e->steal, (size_t)e->sm_count * 32 * kStealMaxResults * sizeof(StealResult)));
+    CU(cudaMalloc(&e->zstash, (size_t)e->sm_count * 32 * 32 * sizeof(int4)));
     CU(cudaEventCreate(&e->ev0));
     CU(cudaEventCreate(&e->ev1));
     CU(cudaEventCreateWithFlags(&e->ev_sync, cudaEventDisableTiming));
@@ -239,7 +241,7 @@ int bgx_destroy(bgx_engine *e)
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < bgx_engine::kScratch; i++) cudaFree(e->dbuf[i]);
-    cudaFree(e->flat); cudaFree(e->wt); cudaFree(e->fixed); cudaFree(e->aux); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats); cudaFree(e->steal);
+    cudaFree(e->flat); cudaFree(e->wt); cudaFree(e->fixed); cudaFree(e->aux); cudaFree(e->counter); cudaFree(e->stats); cudaFree(e->dstats); cudaFree(e->steal); cudaFree(e->zstash);
     cudaFree(e->uniq_tables); cudaFree(e->uniq_gens); cudaFree(e->slots); cudaFree(e->traj_pre); cudaFree(e->traj_chosen);
     cudaFree(e->ply); cudaFree(e->game_id); cudaFree(e->td_partial); cudaFree(e->td_delta); cudaFree(e->td_prof); cudaFree(e->td_home); cudaFree(e->td_sched);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -849,7 +851,7 @@ static int run_selfplay(bgx_engine *e, int n_plies, int round_mode, float epsilo
     p.seed_lo = e->seed_lo; p.seed_hi = e->seed_hi;
     p.first_mover = e->first_mover; p.traj_cap = e->traj_cap;
     p.n_plies = n_plies; p.round_mode = round_mode; p.epsilon = epsilon;
-    p.counter = e->counter; p.stats = e->stats;
+    p.counter = e->counter; p.stats = e->stats; p.zstash = e->zstash;
     CU(cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
     CU(cudaMemsetAsync(e->stats, 0, 16 * sizeof(unsigned long long), e->stream));
     tick(e);

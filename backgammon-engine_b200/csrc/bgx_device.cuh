@@ -235,6 +235,7 @@ struct Choice {
     int n_scored;     // afterstates sent through the network
     int n_visited;    // tree edges walked (moves applied)
     bool any;         // a sequence exists (N > 0)
+    bool z_ok;        // the walker's stash holds the hidden pre-activation of v (greedy_ply with a stash; false otherwise)
 };
 
 struct CountLeaf {

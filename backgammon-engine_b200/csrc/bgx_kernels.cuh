@@ -14,6 +14,8 @@ struct WarpSeat {
     long long slot;
     unsigned long long gid;
     int ply, step, status, player;
+    int carry;                                     // the warp's stash holds the pre-activation of the slot's position (greedy_ply)
+    int dice_base;                                 // lane l holds the dice of ply dice_base + l of the slot's game (-1: nothing held)
 };
 
 // dynamic shared memory of the fused ply kernels: weight table + per-warp scratch + sharing slots + seats + barrier
@@ -720,6 +722,7 @@ struct SelfplayParams {
     float epsilon;
     unsigned long long *counter;
     unsigned long long *stats;   // plies, sequences, scored, finished, p1 wins, truncated, (td steps), tree edges
+    int4 *zstash;                // [CTA][warp][32]: per lane, the hidden pre-activation of the warp's best afterstate (greedy_ply)
 };
 
 template <int kWarps, int kSets, bool kExplore>
@@ -742,8 +745,9 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
     unsigned long long *cta_stats = sm.share->stats;    // plies, sequences, scored, finished, p1 wins, truncated, -, tree edges
     const int budget = p.round_mode ? 0x7fffffff : p.n_plies;
     bool helping = false, seated = false;
-    int v = 0;
+    int v = 0, dice = 0;                                // dice: d1 | d2 << 4 of one of the game's next plies (WarpSeat::dice_base)
     WarpSeat &S = sm.seat[warp];
+    int4 *const zmine = p.zstash + ((size_t)blockIdx.x * kWarps + warp) * 32 + lane;
     // one iteration = one ply: of the slot this warp is seated at, or of a sub-tree taken from a neighbour
     // (whenever the queue is empty, and before its own next ply if the neighbour's double is a huge one)
     for (;;) {
@@ -780,6 +784,8 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
                     S.ply = p.ply[slot];
                     S.gid = (unsigned long long)p.game_id[slot];
                     S.step = 0;
+                    S.carry = 0;
+                    S.dice_base = -1;
                 }
                 __syncwarp();
                 seated = true;
@@ -792,8 +798,18 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
                 seated = false;
             } else {
                 const unsigned long long gid = S.gid;
-                const Philox r = philox4x32_10(p.seed_lo, p.seed_hi, (uint32_t)ply, (uint32_t)gid, (uint32_t)(gid >> 32), 0u);
-                d1 = die_of(r.x[0]); d2 = die_of(r.x[1]);
+                // Philox is counter-based: lane l rolls the dice of ply + l, one evaluation per 32 plies of a game instead of one per ply
+                int ahead = ply - S.dice_base;
+                if (S.dice_base < 0 || ahead < 0 || ahead >= 32) {
+                    const Philox r = philox4x32_10(p.seed_lo, p.seed_hi, (uint32_t)(ply + lane), (uint32_t)gid, (uint32_t)(gid >> 32), 0u);
+                    dice = die_of(r.x[0]) | (die_of(r.x[1]) << 4);
+                    __syncwarp();
+                    if (lane == 0) S.dice_base = ply;
+                    __syncwarp();
+                    ahead = 0;
+                }
+                const int rolled = __shfl_sync(kFull, dice, ahead);
+                d1 = rolled & 15; d2 = rolled >> 4;
                 mover = S.player;
                 rec_traj = p.traj_pre != nullptr && ply < p.traj_cap && S.status == kRunning;
                 if (rec_traj) {
@@ -816,7 +832,8 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
             d1 = __shfl_sync(kFull, d1, 0); d2 = __shfl_sync(kFull, d2, 0);
             mover = __shfl_sync(kFull, mover, 0); only = __shfl_sync(kFull, only, 0);
             const Choice c = choose_ply_fast<kSets, kExplore>(root, lane, mover, d1, d2, ev, cache, explore, u, only ? only : kFull,
-                                                              only ? nullptr : &mine);                  // model.py:180-222
+                                                              only ? nullptr : &mine, only ? nullptr : zmine,
+                                                              only == 0 && S.carry != 0);              // model.py:180-222
             if (only) {
                 deliver_child<kWarps>(sm.share, cta_results, vw, only, c, lane);
                 continue;
@@ -858,7 +875,7 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
                 }
             }
             __syncwarp();
-            if (lane == 0) { S.step = step; S.player = next_player; S.ply = next_ply; S.status = next_status; S.gid = gid; }
+            if (lane == 0) { S.step = step; S.player = next_player; S.ply = next_ply; S.status = next_status; S.gid = gid; S.carry = c.z_ok && winner < 0; if (winner >= 0) S.dice_base = -1; }
             __syncwarp();
             if (step >= budget) seated = false;
         }

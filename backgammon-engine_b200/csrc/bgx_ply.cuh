@@ -270,6 +270,8 @@ struct PlyWalk : Mover {
     bool nd;              // a pass of a NON-double: walked by the last two levels (2, 3 -> leaves at 4) of the one walk there is,
                           // so that the kernel carries one copy of the per-depth code instead of two (instruction cache)
     int4 zroot;
+    int4 *zstash;         // where this lane keeps the pre-activation of the best afterstate so far (nullptr: nowhere), and
+    bool z_ok;            // whether it is there: the next ply of the game starts from it instead of summing ~30 rows again
     // result
     float best_key;       // value, negated for PLAYER2 (who minimises): always maximised, strict > keeps the first
     int best_v;
@@ -286,6 +288,7 @@ struct PlyWalk : Mover {
         best_key = __int_as_float(0xff800000);          // -inf
         best_v = 0; best_path = 0;
         n_seq = n_scored = n_visited = 0;
+        zstash = nullptr; z_ok = false;
     }
 
     // the lanes a move touches: origin code o with the die of this level -> (origin lane, landing lane); the bar is lane
@@ -340,7 +343,10 @@ struct PlyWalk : Mover {
         const float val = ev.finish(z, lane);
         n_scored++;
         const float key = player ? -val : val;
-        if (key > best_key) { best_key = key; best_v = v; best_path = path | ((uint32_t)D << 20); }
+        if (key > best_key) {
+            best_key = key; best_v = v; best_path = path | ((uint32_t)D << 20);
+            if (zstash) { *zstash = z; z_ok = true; }
+        }
     }
 
     __device__ __forceinline__ void early_leaf(int v, uint32_t path_and_len)
@@ -351,7 +357,7 @@ struct PlyWalk : Mover {
         if (val != val) return;
         n_scored++;
         const float key = player ? -val : val;
-        if (key > best_key) { best_key = key; best_v = v; best_path = path_and_len; }
+        if (key > best_key) { best_key = key; best_v = v; best_path = path_and_len; z_ok = false; }
     }
 
     // Twins.  Two on-board moves of one turn commute: played in either order they remove the same two checkers, land on the
@@ -490,21 +496,34 @@ __device__ __forceinline__ Choice finish_choice(const uint32_t best_path, float 
         }
     }
     best.moves = mv;
+    best.z_ok = false;
     return best;
 }
 
 // root_only: bit mask over the root's origin codes (a helper walks one stolen child); kFull = the whole turn.
 // slot/results: the caller's sharing slot (nullptr: never publish).
+// zstash: this lane's 16 bytes for the pre-activation of the best afterstate (nullptr: none); carry: it holds the
+// pre-activation of `root` as the PREVIOUS mover's walk scored it (same game, one ply earlier): fixed-point sums do not depend
+// on how they were formed, so flipping the turn flag gives exactly what preactivation() would compute
 template <int kSets>
 __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int d1, int d2, const PlyEvaluator &ev,
-                                             PlyCache<kSets> &cache, uint32_t root_only = kFull, const ShareCtx *share = nullptr)
+                                             PlyCache<kSets> &cache, uint32_t root_only = kFull, const ShareCtx *share = nullptr,
+                                             int4 *zstash = nullptr, bool carry = false)
 {
     StealSlot *slot = share ? share->slot : nullptr;
     StealResult *results = share ? share->results : nullptr;
     cache.next_ply(lane);
     PlyWalk<kSets> w(ev, cache, lane, player);
     w.root_only = root_only;
-    w.zroot = ev.preactivation(root, lane, player);
+    if (carry) {
+        int4 z = *zstash;
+        PlyEvaluator::sub(z, ev.T4[(193 - player) * 32 + lane]);         // the turn flag of the ply before ...
+        PlyEvaluator::add(z, ev.T4[(192 + player) * 32 + lane]);         // ... and of this one (model.py:139-140)
+        w.zroot = z;
+    } else {
+        w.zroot = ev.preactivation(root, lane, player);
+    }
+    w.zstash = zstash;
     uint32_t best_pass = 0;
     bool shared = false;
     // One loop, ONE call site of the walk (every call site would be another inlined copy of all its levels): a double
@@ -581,6 +600,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
         w.best_path = ((w.best_path & 0xFFFFFu) >> 10) | (((w.best_path >> 20) - 2u) << 20);
     }
     Choice best = finish_choice(w.best_path, w.best_key, w.best_v, w.n_seq, w.n_scored, w.n_visited, root, player, d1, d2, best_pass);
+    best.z_ok = best.any && w.z_ok;
     if (shared) {
         // wait for the helpers, then merge their sub-trees: better value, then lower root origin
         while (*(volatile int32_t *)&slot->pending != 0) __nanosleep(64);
@@ -598,7 +618,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
             const int org = __ldcg(&r->origin);
             const bool better = !best.any || (player ? val < best.value : val > best.value) || (val == best.value && org < best_origin);
             if (better) {
-                best.any = true; best.value = val; best_origin = org;
+                best.any = true; best.value = val; best_origin = org; best.z_ok = false;
                 best.moves = __ldcg(&r->moves);
                 best.v = (int)__ldcg(reinterpret_cast<const signed char *>(r->v) + lane);
             }
@@ -672,13 +692,15 @@ __device__ __forceinline__ void deliver_child(StealShared<kWarps> *sh, StealResu
 template <int kSets, bool kExplore>
 __device__ __forceinline__ Choice choose_ply_fast(int root, int lane, int player, int d1, int d2, const PlyEvaluator &ev,
                                                   PlyCache<kSets> &cache, bool explore, uint32_t u,
-                                                  uint32_t root_only = kFull, const ShareCtx *share = nullptr)
+                                                  uint32_t root_only = kFull, const ShareCtx *share = nullptr,
+                                                  int4 *zstash = nullptr, bool carry = false)
 {
     if (kExplore && explore) {
         CountLeaf cnt;
         walk_turn(root, lane, player, d1, d2, cnt);
         Choice c;
         c.v = root; c.moves = 0; c.value = __int_as_float(0x7fc00000); c.n_seq = cnt.n; c.n_scored = 0; c.n_visited = 0; c.any = cnt.n > 0;
+        c.z_ok = false;
         if (cnt.n > 0) {
             PickLeaf pick((int)mulhi32(u, (uint32_t)cnt.n));
             walk_turn(root, lane, player, d1, d2, pick);
@@ -687,7 +709,7 @@ __device__ __forceinline__ Choice choose_ply_fast(int root, int lane, int player
         }
         return c;
     }
-    return greedy_ply<kSets>(root, lane, player, d1, d2, ev, cache, root_only, share);
+    return greedy_ply<kSets>(root, lane, player, d1, d2, ev, cache, root_only, share, zstash, carry);
 }
 
 } // namespace bgx

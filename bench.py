@@ -393,6 +393,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     w = init_weights()
     eng = BatchEngine(local)
+    if args.selfplay_warps:
+        eng.set_option("selfplay_warps", args.selfplay_warps)
+    if args.select_warps:
+        eng.set_option("select_warps", args.select_warps)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     eng.set_weights(*w)
@@ -727,6 +731,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU sample length per reference step")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--selfplay-warps", type=int, default=0, help="warps per CTA of k_selfplay (0 = the library's default)")
+    ap.add_argument("--select-warps", type=int, default=0, help="warps per CTA of k_select (0 = the library's default)")
     ap.add_argument("--side-positions", type=int, default=1000000, help="positions of the enumeration/encode side legs (0 = skip)")
     ap.add_argument("--no-td-parity", action="store_true", help="skip the TD parity block of the td_round object")
     ap.add_argument("--td-games", type=int, default=-1,

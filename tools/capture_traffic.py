@@ -44,7 +44,7 @@ def main():
     line = json.loads(open(sp_plain).read().strip().splitlines()[-1])
     plies = 65536 * 16
     out["k_selfplay"] = {
-        "sass_function": "k_selfplayILi24ELi72ELb0", "sass_sha256": bench.kernel_sass_sha("k_selfplayILi24ELi72ELb0"),
+        "sass_function": "k_selfplayILi20ELi86ELb0", "sass_sha256": bench.kernel_sass_sha("k_selfplayILi20ELi86ELb0"),
         "dram_bytes_per_launch": dram_bytes(v, u), "warp_inst_per_ply": num(v["smsp__inst_executed.sum"]) / plies,
         "tree_edges_per_ply": line["tree_edges_per_ply_rank0"],
         "issue_active_pct": num(v["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
