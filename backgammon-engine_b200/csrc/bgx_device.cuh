@@ -28,7 +28,7 @@ constexpr int kFixedBytes = kFixedInts * 4;                       // 118 784
 constexpr int kRowB1 = kFeatures + 30;                            // round(b1 S)
 constexpr int kRowW2 = kFeatures + 31;                            // w2 (fp32 bit patterns)
 constexpr int kRowConst = kFeatures + 32;                         // every float4: {S, -log2(e)/S, b2, Y}
-constexpr int kRowLane = kFeatures + 33;                          // lane l: {hash multiplier of lane l, 0, 0, 0} (PlyCache)
+constexpr int kRowLane = kFeatures + 33;                          // word l (l < 32): the hash multiplier of lane l (PlyCache)
 
 // the ply cache's hash multiplier of a lane: odd, and not a polynomial in the lane (moving a checker by the same die from
 // different points must not shift the hash by the same amount)

@@ -109,7 +109,7 @@ __global__ void k_build_fixed(const float *__restrict__ flat, const float *__res
         const float c[4] = {S, -1.4426950408889634f * aux[1], flat[kTableFloats + 2 * kHidden], aux[3]};
         Ti[idx] = __float_as_int(c[j & 3]);
     } else {                                       // what depends on the lane only: read where needed instead of held (or recomputed) in registers
-        Ti[idx] = (j & 3) == 0 ? (int32_t)ply_hash_multiplier(j >> 2) : 0;
+        Ti[idx] = j < 32 ? (int32_t)ply_hash_multiplier(j) : 0;       // word l of the row: lane l's multiplier (one bank per lane)
     }
 }
 
@@ -194,6 +194,7 @@ k_enumerate_summary(const int8_t *__restrict__ queries, long long n, int32_t *__
             n_unique[q] = leaf.overflow ? -1 : leaf.n_unique;
             digest[q] = leaf.digest;
         }
+        __syncwarp();                               // reconverged before the back-edge (see k_selfplay)
     }
     if (lane == 0) gens[gwarp] = gen;
 }
@@ -212,6 +213,7 @@ k_enumerate_count(const int8_t *__restrict__ queries, long long n, int32_t *__re
         CountLeaf leaf;
         walk_turn(root, lane, player, d1, d2, leaf);
         if (lane == 0) n_seq[q] = leaf.n;
+        __syncwarp();                               // reconverged before the back-edge (see k_selfplay)
     }
 }
 
@@ -307,6 +309,7 @@ struct WriteLeaf {
         }
         if (lane == 8) lens[row] = (int8_t)len;
         row++;
+        __syncwarp();                                                  // the walk's loop continues from here: reconverged (see k_selfplay)
     }
 };
 

@@ -168,7 +168,7 @@ struct PlyCache {
     {
         col = p + lane;
         meta = 0;
-        kmul = reinterpret_cast<const uint32_t *>(T4 + kRowLane * 32 + lane);
+        kmul = reinterpret_cast<const uint32_t *>(T4 + kRowLane * 32) + lane;
         clear(lane);
     }
     __device__ __forceinline__ void next_ply(int lane)

@@ -203,7 +203,7 @@ def capture_facts(name):
         return {}, {"verified": False, "why": f"no capture ({exc})"}
     want, got = facts.get("sass_sha256"), kernel_sass_sha(facts.get("sass_function", name))
     if not want or not got:
-        return facts, {"verified": False, "why": "no SASS hash in the capture" if not want else "cuobjdump not available", "file": facts.get("capture")}
+        return facts, {"verified": False, "why": "no SASS hash in the capture" if not want else f"no function {facts.get('sass_function', name)} in the loaded library (or no cuobjdump)", "file": facts.get("capture")}
     if want != got:
         return facts, {"verified": False, "why": f"SASS hash of the loaded kernel {got[:12]} != capture {want[:12]} (kernel changed since the capture)",
                        "file": facts.get("capture")}
@@ -652,7 +652,10 @@ def run_ours(args):
                          "note": "warp instructions per ply (smsp__inst_executed.sum of the committed capture / plies of that launch, rescaled "
                                  "by this run's tree edges per ply) x plies/s, against 4 schedulers x SMs x max clock: the share of issue "
                                  "slots the kernel fills.  It is an occupancy of the bound, not proof of minimal work: the work itself is "
-                                 "warp_inst_per_tree_edge x tree edges per ply"})
+                                 "warp_inst_per_tree_edge x tree edges per ply",
+                         "pipes_at_capture": {"issue_active_pct": facts.get("issue_active_pct"), **(facts.get("pipe_pct") or {}),
+                                              "note": "ncu, same capture: the integer ALU pipe (16 lanes per scheduler, one warp instruction "
+                                                      "per 2 cycles) is the busiest unit of the kernel, the FMA pipe is a quarter full"}})
         else:
             print("bench.py: profiles/traffic.json does not describe the k_selfplay in this libbgx.so "
                   f"({facts_state['why']}): roofline.frac is withheld; re-capture with tools/capture_traffic.py", file=sys.stderr)

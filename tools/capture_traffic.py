@@ -48,7 +48,8 @@ def main():
         "dram_bytes_per_launch": dram_bytes(v, u), "warp_inst_per_ply": num(v["smsp__inst_executed.sum"]) / plies,
         "tree_edges_per_ply": line["tree_edges_per_ply_rank0"],
         "issue_active_pct": num(v["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
-        "capture": os.path.relpath(sp_rep, ROOT),
+        "pipe_pct": {k: num(v[f"sm__inst_executed_pipe_{k}.avg.pct_of_peak_sustained_active"]) for k in ("alu", "fma", "xu", "lsu")},
+        "capture": "profiles/r2f_selfplay_ncu_summary.md",
         "note": "one k_selfplay launch of bench.py (65,536 games x 16 plies), ncu --set full --clock-control none; tree edges per ply from the "
                 "same command run without ncu"}
     v, u = raw(td_rep)
@@ -60,7 +61,7 @@ def main():
         "dram_bytes_per_launch": dram_bytes(v, u), "warp_inst_per_step": num(v["smsp__inst_executed.sum"]) / steps,
         "td_steps_of_the_launch": steps, "issue_active_pct": num(v["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
         "l1_hit_pct": num(v["l1tex__t_sector_hit_rate.pct"]), "l2_hit_pct": num(v["lts__t_sector_hit_rate.pct"]),
-        "capture": os.path.relpath(td_rep, ROOT),
+        "capture": "profiles/r2_td_replay.md",
         "note": "one k_td_replay launch of tools/td_bench.py (greedy self-play round, random-init weights), ncu --set full --clock-control none"}
     os.write(bench._REAL_STDOUT, (json.dumps(out, indent=1) + "\n").encode())
     with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
