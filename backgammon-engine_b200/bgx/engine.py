@@ -77,6 +77,12 @@ class BatchEngine:
         L.check(self._lib.bgx_kernel_config(self._h, C.byref(a), C.byref(b)))
         return {"k_selfplay": a.value, "k_select": b.value}
 
+    def sfu_monotone(self):
+        """Violations of monotonicity of ex2.approx / rcp.approx on this device (bgx_sfu_monotone): both must be 0."""
+        a, b = C.c_int64(), C.c_int64()
+        L.check(self._lib.bgx_sfu_monotone(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_option(self, key, value):
         """Tuning knobs of the fused ply kernels (bgx_set_option): selfplay_warps, select_warps, select_lane_grid, ..."""
         L.check(self._lib.bgx_set_option(self._h, key.encode(), int(value)))

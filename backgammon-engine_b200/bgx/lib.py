@@ -95,6 +95,7 @@ _SIGNATURES = {
     "bgx_launch_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "bgx_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "bgx_kernel_config": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bgx_sfu_monotone": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "bgx_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "bgx_td_profile": (C.c_int, [_vp, C.c_int, _vp]),
     "bgx_device_props": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64)]),

@@ -1216,6 +1216,22 @@ int bgx_last_kernel_ms(bgx_engine *e, float *ms)
     return BGX_OK;
 }
 
+int bgx_sfu_monotone(bgx_engine *e, int64_t *ex2_violations, int64_t *rcp_violations)
+{
+    USE(e);
+    NEED(ex2_violations && rcp_violations, "null");
+    CU(cudaMemsetAsync(e->stats, 0, 16 * sizeof(unsigned long long), e->stream));
+    k_sfu_monotone<<<e->sm_count * 8, 256, 0, e->stream>>>(e->stats);
+    e->launches++;
+    CU(cudaGetLastError());
+    unsigned long long h[2];
+    CU(cudaMemcpyAsync(h, e->stats, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *ex2_violations = (int64_t)h[0];
+    *rcp_violations = (int64_t)h[1];
+    return BGX_OK;
+}
+
 int bgx_kernel_config(bgx_engine *e, int *selfplay_warps, int *select_warps)
 {
     if (!e) { set_error("bgx_kernel_config: null"); return BGX_E_INVALID; }

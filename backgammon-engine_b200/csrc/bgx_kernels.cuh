@@ -904,6 +904,38 @@ k_selfplay(SelfplayParams p, const int32_t *__restrict__ Ti, const float *__rest
     if (__shfl_sync(kFull, last, 0) && lane < 8 && lane != 6) atomicAdd(p.stats + lane, cta_stats[lane]);
 }
 
+// ---- are the SFU approximations the ply evaluator ranks by monotone?  (PlyEvaluator::value_of) ----------------
+// The greedy ply compares integer output sums and evaluates V = 1 / (1 + 2^a) only for a sum that beats the best so far.
+// That equals comparing V itself if V is a non-decreasing function of the sum: the FFMA, the multiply and the add are
+// correctly rounded, hence monotone; ex2.approx.ftz and rcp.approx.ftz are table-based approximations with no such
+// guarantee on paper.  This kernel checks them on the device, exhaustively: every pair of neighbouring finite floats for
+// ex2, every pair of neighbours in [1, FLT_MAX] for rcp (its argument is 1 + 2^a >= 1).  out[0] / out[1]: violations.
+__device__ __forceinline__ float ordered_float(uint32_t k)            // k ascending <=> value ascending (k >= 2^31: positive)
+{
+    return __uint_as_float(k & 0x80000000u ? k ^ 0x80000000u : ~k);
+}
+__global__ void k_sfu_monotone(unsigned long long *out)
+{
+    unsigned long long bad_ex2 = 0, bad_rcp = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < 0xFFFFFFFFull; k += stride) {
+        const float a = ordered_float((uint32_t)k), b = ordered_float((uint32_t)k + 1u);
+        if (!(fabsf(a) <= 3.402823466e38f) || !(fabsf(b) <= 3.402823466e38f)) continue;       // NaN / infinity
+        float ea, eb;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(a));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(b));
+        if (!(ea <= eb)) bad_ex2++;
+        if (a >= 1.0f) {
+            float ra, rb;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(a));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(b));
+            if (!(ra >= rb)) bad_rcp++;
+        }
+    }
+    if (bad_ex2) atomicAdd(out + 0, bad_ex2);
+    if (bad_rcp) atomicAdd(out + 1, bad_rcp);
+}
+
 // (re)seat every slot: opening position, first mover, ply 0
 __global__ void k_selfplay_reset(int8_t *slots, int32_t *ply, long long *game_id, long long n_slots,
                                  long long first_id, long long id_stride, int advance,

@@ -24,6 +24,8 @@
 //  4. BYTE-PER-LANE CACHE.  An entry is the position itself, lane l owning byte l; the set
 //     index is one REDUX.SUM.  A probe is one byte load per way, one compare, one vote.
 #pragma once
+#include <climits>
+
 #include "bgx_device.cuh"
 
 namespace bgx {
@@ -125,16 +127,25 @@ struct PlyEvaluator {
     // hidden layer -> output.  The sigmoid's 2^x argument is z * (-log2(e) / S) in ONE multiply; the 32 lane sums of w2 . h are
     // added as integers at scale Y (one REDUX.SUM instead of five shuffle + add rounds; order-independent, so V stays a pure
     // function of the position).  Resolution 2^-30 of sum |w2|: ~1e-7 of V in the worst case.
-    __device__ __forceinline__ float finish(const int4 &zi, int lane) const
+    // output_sum: the integer the value is a function of; value_of: V.  V is a NON-DECREASING function of the sum (an FFMA, a
+    // multiply, ex2.approx, an add, rcp.approx: each monotone - for the two SFU approximations that is checked exhaustively on
+    // the device, bgx_sfu_monotone / test_sfu_approximations_are_monotone), so the walk compares sums and evaluates V only for
+    // a sum that beats the best one so far: the strict first-index arg-best over V is unchanged.
+    __device__ __forceinline__ int output_sum(const int4 &zi, int lane) const
     {
         const int4 wi = T4[kRowW2 * 32 + lane], ci = T4[kRowConst * 32];       // (one address for the warp: the value is provably uniform)
-        const float c = __int_as_float(ci.y), b2 = __int_as_float(ci.z), Y = __int_as_float(ci.w);
+        const float c = __int_as_float(ci.y), Y = __int_as_float(ci.w);
         const float y = __int_as_float(wi.x) * sigmoid_exp2((float)zi.x * c) + __int_as_float(wi.y) * sigmoid_exp2((float)zi.y * c) +
                         __int_as_float(wi.z) * sigmoid_exp2((float)zi.z * c) + __int_as_float(wi.w) * sigmoid_exp2((float)zi.w * c);
-        const int total = __reduce_add_sync(kFull, __float2int_rn(y * Y));
-        const float inv_y = __int_as_float(0x7F000000 - ci.w);                    // Y is a power of two
-        return fast_sigmoid(fmaf((float)total, inv_y, b2));
+        return __reduce_add_sync(kFull, __float2int_rn(y * Y));
     }
+    __device__ __forceinline__ float value_of(int total) const
+    {
+        const int4 ci = T4[kRowConst * 32];
+        const float inv_y = __int_as_float(0x7F000000 - ci.w);                    // Y is a power of two
+        return fast_sigmoid(fmaf((float)total, inv_y, __int_as_float(ci.z)));
+    }
+    __device__ __forceinline__ float finish(const int4 &zi, int lane) const { return value_of(output_sum(zi, lane)); }
 };
 
 // The per-warp cache of one ply.  Two kinds of entries share it:
@@ -237,18 +248,19 @@ struct PlyCache {
 // A sequence that ends before the dice are used up (no legal move left) is the rare kind of leaf.  Its
 // afterstate is scored FROM SCRATCH by this out-of-line routine - the fixed-point z of a position does not
 // depend on how it is computed - so the fully inlined walk carries the leaf code only at its last level
-// (the kernel's code has to stay close to the 32 KB instruction cache).  Returns NaN if scored before.
+// (the kernel's code has to stay close to the 32 KB instruction cache).  Returns the output sum, kSeenBefore if scored before.
+constexpr int kSeenBefore = INT_MIN;
 template <int kSets>
-__device__ __noinline__ float score_early_leaf(uint8_t *col, uint32_t meta, const uint32_t *kmul, const int4 *T4, int v, int lane, int player)
+__device__ __noinline__ int score_early_leaf(uint8_t *col, uint32_t meta, const uint32_t *kmul, const int4 *T4, int v, int lane, int player)
 {
     PlyCache<kSets> cache;
     cache.col = col; cache.meta = meta; cache.kmul = kmul;
     const typename PlyCache<kSets>::Probe pr = cache.template probe<0>(v, lane);
-    if (pr.hit()) return __int_as_float(0x7fc00000);
+    if (pr.hit()) return kSeenBefore;
     cache.template write<0>(pr, v, 0, lane);
     PlyEvaluator e;
     e.T4 = T4;
-    return e.finish(e.preactivation(v, lane, player), lane);
+    return e.output_sum(e.preactivation(v, lane, player), lane);
 }
 
 // ---- the walk ----------------------------------------------------------------------------
@@ -274,6 +286,7 @@ struct PlyWalk : Mover {
     bool z_ok;            // whether it is there: the next ply of the game starts from it instead of summing ~30 rows again
     // result
     float best_key;       // value, negated for PLAYER2 (who minimises): always maximised, strict > keeps the first
+    int best_sum;         // the output sum behind it (negated likewise): a sum that does not beat it cannot beat the value
     int best_v;
     uint32_t best_path;   // origins 5 bits each, length << 20
     int n_seq, n_scored, n_visited;
@@ -286,6 +299,7 @@ struct PlyWalk : Mover {
         twin_root = 0;
         nd = false;
         best_key = __int_as_float(0xff800000);          // -inf
+        best_sum = INT_MIN;
         best_v = 0; best_path = 0;
         n_seq = n_scored = n_visited = 0;
         zstash = nullptr; z_ok = false;
@@ -340,12 +354,16 @@ struct PlyWalk : Mover {
         if (pr.hit()) return;
         cache.template write<0>(pr, v, 0, lane);
         const int4 z = D == 0 ? zroot : child_z(zpar, vpar, sl, dl);
-        const float val = ev.finish(z, lane);
+        const int total = ev.output_sum(z, lane);
         n_scored++;
-        const float key = player ? -val : val;
-        if (key > best_key) {
-            best_key = key; best_v = v; best_path = path | ((uint32_t)D << 20);
-            if (zstash) { *zstash = z; z_ok = true; }
+        const int sum = player ? -total : total;
+        if (sum > best_sum) {
+            const float val = ev.value_of(total);
+            const float key = player ? -val : val;
+            if (key > best_key) {
+                best_key = key; best_sum = sum; best_v = v; best_path = path | ((uint32_t)D << 20);
+                if (zstash) { *zstash = z; z_ok = true; }
+            }
         }
     }
 
@@ -353,11 +371,15 @@ struct PlyWalk : Mover {
     {
         n_seq++;
         // (a call's result counts as divergent: the shuffle makes the branches below uniform ones, see k_selfplay)
-        const float val = __shfl_sync(kFull, score_early_leaf<kSets>(cache.col, cache.meta, cache.kmul, ev.T4, v, lane, player), 0);
-        if (val != val) return;
+        const int total = __shfl_sync(kFull, score_early_leaf<kSets>(cache.col, cache.meta, cache.kmul, ev.T4, v, lane, player), 0);
+        if (total == kSeenBefore) return;
         n_scored++;
-        const float key = player ? -val : val;
-        if (key > best_key) { best_key = key; best_v = v; best_path = path_and_len; z_ok = false; }
+        const int sum = player ? -total : total;
+        if (sum > best_sum) {
+            const float val = ev.value_of(total);
+            const float key = player ? -val : val;
+            if (key > best_key) { best_key = key; best_sum = sum; best_v = v; best_path = path_and_len; z_ok = false; }
+        }
     }
 
     // Twins.  Two on-board moves of one turn commute: played in either order they remove the same two checkers, land on the

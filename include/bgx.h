@@ -335,6 +335,10 @@ int bgx_device_props(bgx_engine *e, int *sm_count, int *clock_khz, int64_t *glob
  * (first-layer store, barrier, hidden layer, window bookkeeping + lazy replay, barrier, values + gradients, row pass, end of
  * game; a barrier's wait shows up in the phase that follows it), [15] the TD steps of that CTA. */
 int bgx_td_profile(bgx_engine *e, int on, uint64_t *cycles);
+/* Exhaustive device check of what the greedy ply's ranking relies on (bgx_ply.cuh PlyEvaluator::value_of; the reference ranks by
+ * the value itself, model.py:205-213): ex2.approx.ftz is non-decreasing over every pair of neighbouring finite floats and
+ * rcp.approx.ftz non-increasing over [1, FLT_MAX].  Both counts of violations must be 0 on the device in use. */
+int bgx_sfu_monotone(bgx_engine *e, int64_t *ex2_violations, int64_t *rcp_violations);
 /* warps per CTA of the fused ply kernels as configured */
 int bgx_kernel_config(bgx_engine *e, int *selfplay_warps, int *select_warps);
 /* tuning knobs of the fused ply kernels for benchmarks and probes; the defaults are the measured best.  Keys:

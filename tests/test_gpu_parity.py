@@ -279,6 +279,14 @@ def test_select_moves_large_sample_vs_oracle(eng, orc, golden, tag):
     assert exact[ok].all(), (int((~exact[ok]).sum()), int(ok.sum()))
 
 
+def test_sfu_approximations_are_monotone(eng):
+    """The greedy ply ranks afterstates by the integer output sum and evaluates V = sigmoid(sum / Y + b2) only for a sum that
+    beats the best so far (bgx_ply.cuh PlyEvaluator::value_of).  That is the reference's strict first-index arg-best over V
+    (model.py:205-213) exactly if V is a non-decreasing function of the sum; the two SFU approximations in it carry no such
+    guarantee on paper, so it is checked on the device, exhaustively (every neighbouring pair of finite floats)."""
+    assert eng.sfu_monotone() == (0, 0)
+
+
 @pytest.mark.parametrize("tag", ["rand", "trained"])
 def test_select_moves_is_a_pure_function_of_the_query(eng, golden, tag):
     """The choice must not depend on batch composition, on which warp walked a position, on what the
