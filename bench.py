@@ -447,7 +447,9 @@ def run_ours(args):
     # another (count the ply, restart finished games in place with the next game id).
     e2e_steps = max(2, min(args.steps, 8)) * PLIES_PER_STEP
     from bgx import host as bgx_host
-    LANES = 3
+    LANES = args.e2e_lanes
+    if args.lane_grid >= 0:
+        eng.set_option("select_lane_grid", args.lane_grid)
     pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
     bufs = [pin((G, 32), torch.int8), pin((G, 32), torch.int8)]
     win = pin((G,), torch.int8)
@@ -736,6 +738,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--selfplay-warps", type=int, default=0, help="warps per CTA of k_selfplay (0 = the library's default)")
     ap.add_argument("--select-warps", type=int, default=0, help="warps per CTA of k_select (0 = the library's default)")
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="asynchronous lanes of the end-to-end leg (parts of the population in flight)")
+    ap.add_argument("--lane-grid", type=int, default=-1, help="CTAs of a lane's launch (-1 = the library's default: half the SMs; 0 = one per SM)")
     ap.add_argument("--side-positions", type=int, default=1000000, help="positions of the enumeration/encode side legs (0 = skip)")
     ap.add_argument("--no-td-parity", action="store_true", help="skip the TD parity block of the td_round object")
     ap.add_argument("--td-games", type=int, default=-1,
