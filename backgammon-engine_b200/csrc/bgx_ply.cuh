@@ -23,6 +23,13 @@
 //     lossy in the safe direction only (a miss re-walks, never mis-counts).
 //  4. BYTE-PER-LANE CACHE.  An entry is the position itself, lane l owning byte l; the set
 //     index is one REDUX.SUM.  A probe is one byte load per way, one compare, one vote.
+//  5. NOTHING PER LANE IS A BRANCH, NOTHING PER WARP IS UNPROVEN.  Selects on the lane are written so that they
+//     compile to one LOP3 / SEL (a `lane == 28 ? a : b` inside a template-free helper became BSSY / BRA / BSYNC),
+//     and every value the walk branches on is provably warp-uniform for ptxas (ballots, REDUX, shuffles from a fixed
+//     lane): otherwise each *_sync intrinsic of the walk is guarded by BRA.DIV (the kernels reconverge
+//     before every back-edge for the same reason).
+//  6. A MOVE IS (origin lane, landing lane, blot bit).  The node's blots are one ballot; the child state is two lane
+//     compares; what stood on the landing point is fetched only where a pre-activation is computed.
 #pragma once
 #include <climits>
 
