@@ -312,55 +312,66 @@ struct PlyWalk : Mover {
         zstash = nullptr; z_ok = false;
     }
 
-    // the lanes a move touches: origin code o with the die of this level -> (origin lane, landing lane); the bar is lane
-    // 24 + player, a checker borne off lands on lane 26 + player
-    __device__ __forceinline__ void lanes_of(int o, int die, int &sl, int &dl) const
+    // What moving one checker does, as a word: bits 0..4 the landing lane | bit 5 a hit | bits 16..23 the row the origin loses |
+    // bits 24..31 the row the landing lane gains.  Rows are rows of Tme = this lane's column of the table shifted to the MOVER's
+    // feature block (row 8 p + k of Tme: "k + 1 checkers of the mover on point p"; the other rows follow from the player by one
+    // multiply-add).  src / dst: the origin and landing lanes (bar 24 + player, borne off 26 + player), sval / dval: what stands there.
+    __device__ __forceinline__ uint32_t move_word(int sval, int dval, int src, int dst) const
     {
-        sl = o == (player ? 25 : 0) ? 24 + player : o - 1;
-        const int d = o + die * unit_of_points();            // destination code; <= 0 or >= 25: borne off (game.cpp:89-97)
-        dl = (unsigned)(d - 1) > 23u ? 26 + player : d - 1;
+        const int n = sval < 0 ? -sval : sval;
+        const int row_src = src >= 24 ? 194 - 3 * player : 8 * src + (n < 4 ? n : 4) - 1;           // (194 + player) - 4 player
+        const int k = (dval < 0 ? -dval : dval) + 1;
+        const bool hit = dst < 24 && dval * unit_of_points() == -1;
+        int row_dst = dst >= 24 ? kFeatures + 11 * player + dval : 8 * dst + (k < 4 ? k : 4) - 1;   // (198 + 15 player) - 4 player
+        if (hit) row_dst = 8 * dst;
+        return (uint32_t)dst | (hit ? 32u : 0u) | ((uint32_t)row_src & 0xFFu) << 16 | (uint32_t)row_dst << 24;
     }
-
-    // the child state (game.cpp:624-659) when the node's blots are known: hit = the landing point holds one enemy checker
-    __device__ __forceinline__ int apply_known(int v, int sl, int dl, uint32_t blots) const
+    // ... for ALL origins of a node at once: lane l computes the word of "the checker on lane l moves by the node's die" (a garbage
+    // word where no legal origin stands); a child then costs one shuffle instead of this arithmetic per child
+    __device__ __forceinline__ uint32_t node_moves(int v, int die) const
     {
-        const uint32_t hit = (blots >> dl) & 1u;             // (blots has no bit above 23)
+        const int d = lane + die * unit_of_points();                     // from a point: the landing point, or off the board
+        int dl = (unsigned)d > 23u ? 26 + player : d;
+        if (lane >= 24) dl = player ? 24 - die : die - 1;                // from the bar (game.cpp:89-97)
+        return move_word(v, __shfl_sync(kFull, v, dl), lane, dl);
+    }
+    // the lane of an origin code
+    __device__ __forceinline__ int origin_lane(int o) const { return o == (player ? 25 : 0) ? 24 + player : o - 1; }
+
+    // the child state (game.cpp:624-659): the checker leaves lane sl and lands where the word says
+    __device__ __forceinline__ int apply_word(int v, int sl, uint32_t mv) const
+    {
+        const int dl = (int)(mv & 31u);
+        const uint32_t hit = (mv >> 5) & 1u;
         int t = lane == dl ? unit << hit : 0;                // the checker lands, a blot is replaced
         t -= lane == sl ? unit : 0;
         t += (lane == 25 - player ? 1 : 0) & (int)hit;       // ... and goes to the enemy's bar
         return v + t;
     }
 
-    // pre-activation of the child reached from (vpar, zpar) by the move sl -> dl: 2 rows, 4 after a hit.  Rows are addressed from
-    // Tme = this lane's column of the table shifted to the MOVER's feature block (row 8 p + k of Tme is "k + 1 checkers of the
-    // mover on point p"); the other rows follow from the player by one multiply-add each (cheap to recompute, nothing to hold)
-    __device__ __forceinline__ int4 child_z(const int4 &zpar, int vpar, int src, int dst) const
+    // pre-activation of the child reached from zpar by the move mv: 2 rows, 4 after a hit
+    __device__ __forceinline__ int4 child_z(const int4 &zpar, uint32_t mv) const
     {
-        const int sval = __shfl_sync(kFull, vpar, src), dval = __shfl_sync(kFull, vpar, dst);
         int4 z = zpar;
-        const int n = sval < 0 ? -sval : sval;
-        const int row_src = src >= 24 ? 194 - 3 * player : 8 * src + (n < 4 ? n : 4) - 1;          // (194 + player) - c_me
-        PlyEvaluator::sub(z, Tme[row_src * 32]);                            // one checker less on the origin (or the bar)
-        const int k = (dval < 0 ? -dval : dval) + 1;
-        int row_dst = dst >= 24 ? kFeatures + 11 * player + dval : 8 * dst + (k < 4 ? k : 4) - 1;  // (198 + 15 player) - c_me
-        if (dst < 24 && dval * unit_of_points() == -1) {                    // a hit
+        PlyEvaluator::sub(z, Tme[((mv >> 16) & 0xFFu) * 32]);               // one checker less on the origin (or the bar)
+        if (mv & 32u) {                                                     // a hit
+            const int dst = (int)(mv & 31u);
             PlyEvaluator::sub(z, Tme[(8 * dst + 4 - 8 * player) * 32]);     // the blot leaves (the enemy's block: +4 / -4) ...
-            PlyEvaluator::add(z, Tme[(195 - 5 * player) * 32]);             // ... for the enemy's bar: (195 - player) - c_me
-            row_dst = 8 * dst;
+            PlyEvaluator::add(z, Tme[(195 - 5 * player) * 32]);             // ... for the enemy's bar: (195 - player) - 4 player
         }
-        PlyEvaluator::add(z, Tme[row_dst * 32]);                            // one more on the landing point (or borne off)
+        PlyEvaluator::add(z, Tme[(mv >> 24) * 32]);                         // one more on the landing point (or borne off)
         return z;
     }
 
     // a legal turn sequence ends on v (reference order); score it unless this exact state was scored before
     template <int D>
-    __device__ __forceinline__ void leaf(int v, const int4 &zpar, int vpar, int sl, int dl, uint32_t path)
+    __device__ __forceinline__ void leaf(int v, const int4 &zpar, uint32_t mv, uint32_t path)
     {
         n_seq++;
         const typename PlyCache<kSets>::Probe pr = cache.template probe<0>(v, lane);
         if (pr.hit()) return;
         cache.template write<0>(pr, v, 0, lane);
-        const int4 z = D == 0 ? zroot : child_z(zpar, vpar, sl, dl);
+        const int4 z = D == 0 ? zroot : child_z(zpar, mv);
         const int total = ev.output_sum(z, lane);
         n_scored++;
         const int sum = player ? -total : total;
@@ -396,15 +407,16 @@ struct PlyWalk : Mover {
     // node, in the second pass of a non-double when o' is a root origin of the first pass.  The reference visits that twin
     // EARLIER (ascending origins; first pass first), it has the same value, and the strict first-index arg-best can never
     // prefer the later copy: such leaves are counted, not walked.  `legal_par` = all origins of the parent node.
-    // (v, path) = the node; (vpar, zpar) its parent, sl -> dl the lanes of the move that led here (path holds its origin code)
+    // (v, path) = the node; zpar its parent's pre-activation, mv the word of the move that led here (path holds its origin code),
+    // left: that move bore a checker off (kept apart from mv: it steers the walk and has to be provably warp-uniform)
     template <int D>
-    __device__ __forceinline__ void visit(int v, const int4 &zpar, int vpar, int sl, int dl, uint32_t path, uint32_t legal_par = 0)
+    __device__ __forceinline__ void visit(int v, const int4 &zpar, uint32_t mv, bool left, uint32_t path, uint32_t legal_par = 0)
     {
         constexpr int kMax = 4;
-        uint32_t legal = 0, blots = 0;
+        uint32_t legal = 0;
         if constexpr (D < kMax) {
             if (D == 1 && nd) legal = 1u;                    // a non-double pass enters at level 2: level 1 hands the root through
-            else legal = legal_and_blots<true>(v, (D & 1) ? dieB : dieA, blots);
+            else legal = legal_here(v, (D & 1) ? dieB : dieA);
             if (D == 0) legal &= root_only;
         }
         uint32_t twins = 0;
@@ -413,12 +425,12 @@ struct PlyWalk : Mover {
             const int o = (int)((path >> (5 * (D - 1))) & 31u);
             twins = legal & (nd ? twin_root : legal_par & ((1u << o) - 1u));
             twins &= player ? ~((2u << die) - 1u) : (1u << (25 - die)) - 1u;      // the last move stays on the board ...
-            if (dl >= 24) twins = 0;                                             // ... and so did the one before it
+            if (left) twins = 0;                                                 // ... and so did the one before it
         }
         if (legal == 0) {
             // a node without a move ends the sequence (game.cpp:117-121, 148-151); the root of a
             // non-double pass emits nothing
-            if constexpr (D == kMax) leaf<D>(v, zpar, vpar, sl, dl, path);
+            if constexpr (D == kMax) leaf<D>(v, zpar, mv, path);
             else if (!(D == 2 && nd)) early_leaf(v, path | ((uint32_t)D << 20));
             return;
         }
@@ -438,18 +450,23 @@ struct PlyWalk : Mover {
                 return;
             }
             int4 z = zroot;                                  // the root of the turn: of a double at depth 0, of a non-double pass at 2
-            if (D != 0 && !(D <= 2 && nd)) z = child_z(zpar, vpar, sl, dl);
+            if (D != 0 && !(D <= 2 && nd)) z = child_z(zpar, mv);
             const int die = (D & 1) ? dieB : dieA;
+            const uint32_t moves = (D == 1 && nd) ? 0u : node_moves(v, die);
             do {
                 const int oc = lowest_bit(legal);
                 legal &= legal - 1;
-                int sc = 0, dc = 0, child = v;
+                int child = v;
+                uint32_t mc = 0;
+                bool off = false;
                 if (!(D == 1 && nd)) {
-                    lanes_of(oc, die, sc, dc);
-                    child = apply_known(v, sc, dc, blots);
+                    const int sc = origin_lane(oc);
+                    mc = __shfl_sync(kFull, moves, sc);
+                    child = apply_word(v, sc, mc);
+                    if (D + 1 == kMax - 1) off = (unsigned)(oc + die * unit_of_points() - 1) > 23u;   // (game.cpp:89-97)
                     n_visited++;
                 }
-                visit<D + 1>(child, z, v, sc, dc, path | ((uint32_t)oc << (5 * D)), legal_all);
+                visit<D + 1>(child, z, mc, off, path | ((uint32_t)oc << (5 * D)), legal_all);
             } while (legal);
             if constexpr (D >= 2) { if (!nd) cache.template store<D>(v, n_seq - entered, lane); }
         }
@@ -586,8 +603,10 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
             }
         }
     }
+    const uint32_t root_moves = dbl ? w.node_moves(root, d1) : 0u;
     for (;;) {
-        int child = root, oc = 0, sc = 0, dc = 0;
+        int child = root, oc = 0;
+        uint32_t mroot = 0;
         if (dbl) {
             uint32_t bit = 0;
             if (shared) {                                                // pop the lowest origin still there
@@ -608,9 +627,9 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
             }
             if (bit == 0) break;
             oc = lowest_bit(bit);
-            int dv;
-            child = w.apply(root, oc, destination(player, oc, d1), dv);
-            w.lanes_of(oc, d1, sc, dc);
+            const int sc = w.origin_lane(oc);
+            mroot = __shfl_sync(kFull, root_moves, sc);
+            child = w.apply_word(root, sc, mroot);
             w.n_visited++;
         } else {                                                         // game.cpp:143-188: d1 first, then d2 first
             if (pass == 2) break;
@@ -619,7 +638,7 @@ __device__ __forceinline__ Choice greedy_ply(int root, int lane, int player, int
             if (pass) { key1 = w.best_key; w.twin_root = w.legal_here(root, d1); }
             pass++;
         }
-        w.template visit<1>(child, w.zroot, root, sc, dc, (uint32_t)oc);
+        w.template visit<1>(child, w.zroot, mroot, false, (uint32_t)oc);
     }
     if (dbl) {
         if (shared && lane == 0) atomicAnd(share->urgent, ~share->my_bit);
